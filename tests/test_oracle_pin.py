@@ -1,0 +1,158 @@
+"""Pins the CPU oracle (oracle/upr_oracle.c) before anything is allowed to trust it.
+
+Two independent anchors:
+  * golden vectors produced by the UNMODIFIED reference (tests/golden/make_golden.py);
+  * the cv2 binary itself (the third-party dependency that holds the arithmetic):
+    exhaustive 2^24 sweeps for RGB->Lab, Lab->RGB, RGB->Gray and CLAHE on ragged shapes.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+cv2 = pytest.importorskip("cv2")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def cube():
+    r, g, b = np.meshgrid(*(np.arange(256, dtype=np.uint8),) * 3, indexing="ij")
+    planar = np.stack([r.ravel(), g.ravel(), b.ravel()])
+    hwc = np.ascontiguousarray(planar.T.reshape(4096, 4096, 3))
+    return planar, hwc
+
+
+def test_tables_spot_values():
+    t = O.tables()
+    assert list(t["gamma"][:6]) == [0, 1, 1, 2, 2, 3] and list(t["gamma"][253:]) == [2004, 2022, 2040]
+    # entries where a float64 / libm-cbrtf build would differ (see upr_oracle.c)
+    assert t["cbrt"][49] == 9454 and t["cbrt"][628] == 22126 and t["cbrt"][324] == 17745
+    assert list(t["y"][:3]) == [0, 7, 14] and t["y"][255] == 16384
+    assert t["ify"][0] == 2260 and t["ify"][255] == 16384
+    assert list(t["invgamma"][:10]) == [0, 1, 2, 2, 3, 4, 5, 6, 6, 7]
+
+
+def test_rgb2lab_exhaustive_vs_cv2(cube):
+    planar, hwc = cube
+    ref = cv2.cvtColor(np.ascontiguousarray(hwc[:, :, ::-1]), cv2.COLOR_BGR2LAB).reshape(-1, 3).T
+    assert np.array_equal(O.rgb2lab_u8(planar), ref)
+
+
+def test_lab2rgb_exhaustive_vs_cv2(cube):
+    planar, hwc = cube
+    bgr = cv2.cvtColor(hwc, cv2.COLOR_LAB2BGR)
+    ref = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB).reshape(-1, 3).T
+    assert np.array_equal(O.lab2rgb_u8(planar), ref)
+
+
+def test_gray_exhaustive_vs_cv2(cube):
+    planar, hwc = cube
+    ref = cv2.cvtColor(np.ascontiguousarray(hwc[:, :, ::-1]), cv2.COLOR_BGR2GRAY).ravel()
+    assert np.array_equal(O.gray_u8(planar), ref)
+
+
+def test_quantize_matches_numpy_cast():
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.random(4096, dtype=np.float32) * 3 - 1,
+                        np.array([0, 1, 1.5, -0.5, 0.999999, 255 / 255, 254.9999 / 255, np.nan, np.inf, -np.inf,
+                                  1e10, -1e10, 8421504.5, -8421504.5, 1e-45, -0.0], np.float32)])
+    with np.errstate(invalid="ignore"):
+        ref = (x * 255).astype(np.uint8)
+    assert np.array_equal(O.quantize_u8(x), ref)
+
+
+@pytest.mark.parametrize("shape", [(400, 600), (1080, 1920), (403, 601), (400, 601), (401, 600), (64, 64),
+                                   (17, 23), (135, 240), (9, 9)])
+@pytest.mark.parametrize("kind", ["uniform", "dark", "const", "ramp"])
+def test_clahe_vs_cv2(shape, kind):
+    h, w = shape
+    rng = np.random.default_rng(h * 131 + w)
+    if kind == "uniform":
+        src = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    elif kind == "dark":
+        src = rng.integers(0, 77, (h, w), dtype=np.uint8)
+    elif kind == "const":
+        src = np.full((h, w), 77, np.uint8)
+    else:
+        src = ((np.arange(w)[None, :] * 255 // max(w - 1, 1)) * np.ones((h, 1))).astype(np.uint8)
+    ref = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(src)
+    got, hist, lut = O.clahe_u8(src, taps=True)
+    assert np.array_equal(got, ref)
+    hp, wp = (h, w) if (h % 8 == 0 and w % 8 == 0) else (h + 8 - h % 8, w + 8 - w % 8)
+    assert hist.sum() == hp * wp and (hist.sum(1) == hp * wp // 64).all()
+
+
+@pytest.mark.parametrize("clip,tiles", [(2.0, (8, 8)), (4.0, (4, 4)), (1.0, (16, 8)), (40.0, (8, 8)), (0.0, (8, 8))])
+def test_clahe_other_params_vs_cv2(clip, tiles):
+    rng = np.random.default_rng(77)
+    src = rng.integers(0, 256, (200, 320), dtype=np.uint8)
+    ref = cv2.createCLAHE(clipLimit=clip, tileGridSize=tiles).apply(src)
+    assert np.array_equal(O.clahe_u8(src, clip_limit=clip, tiles=tiles), ref)
+
+
+def test_golden_clahe(golden, small_cases):
+    for rec in golden["clahe"]:
+        x = O.kat_input(rec["seed"], rec["h"], rec["w"], rec["kind"])
+        assert sha(x) == rec["sha_in"]
+        out, taps = O.clahe_lab(x, taps=True)
+        assert sha(np.transpose(taps["q"], (1, 2, 0))) == rec["sha_u8_hwc"], rec
+        assert sha(out) == rec["sha_out"], rec
+        key = f"clahe_{rec['seed']}_out_u8"
+        if key in small_cases:
+            assert np.array_equal(out[0], small_cases[key].astype(np.float32) / np.float32(255.0))
+
+
+def test_golden_brightness(golden):
+    for rec in golden["bright"]:
+        x = O.kat_input(rec["seed"], rec["h"], rec["w"], rec["kind"])
+        f = O.brightness_features(x)
+        for k, v in rec["features"].items():
+            assert abs(f[k] - v) <= 1e-12, (k, f[k], v)
+        assert O.adjust_parameters(x) == rec["params"]
+
+
+def test_golden_multiscale(golden):
+    for rec in golden["multiscale"]:
+        x = O.kat_input(rec["seed"], rec["h"], rec["w"], rec["kind"])
+        means, factor = O.multiscale_means(x)
+        np.testing.assert_allclose(means, rec["means"], rtol=2e-6)
+        assert abs(factor - rec["factor"]) <= 1e-7
+
+
+def test_golden_content(golden, small_cases):
+    for rec in golden["content"]:
+        x = O.kat_input(rec["seed"], rec["h"], rec["w"], rec["kind"])
+        sal = O.saliency(x)
+        att = O.attention(x)
+        assert abs(float(sal.astype(np.float64).mean()) - rec["sal_mean"]) <= 1e-7
+        assert abs(float(att.astype(np.float64).mean()) - rec["att_mean"]) <= 1e-7
+        assert int(att.argmax()) == rec["att_argmax"] and int(sal.argmax()) == rec["sal_argmax"]
+        if f"sal_{rec['seed']}" in small_cases:
+            np.testing.assert_allclose(sal[0, 0], small_cases[f"sal_{rec['seed']}"], rtol=0, atol=1e-7)
+            np.testing.assert_allclose(att[0, 0], small_cases[f"att_{rec['seed']}"], rtol=0, atol=2e-7)
+
+
+def test_golden_retinex(small_cases):
+    refl, enh = O.retinex_recombine(small_cases["retinex_x"], small_cases["retinex_illu"], small_cases["retinex_e"])
+    assert np.array_equal(refl, small_cases["retinex_refl"])
+    np.testing.assert_allclose(enh, small_cases["retinex_enh"], rtol=3e-7, atol=0)
+
+
+def test_golden_texture(golden):
+    for rec in golden["texture"]:
+        rng = np.random.default_rng(rec["seed"])
+        a = rng.random(tuple(rec["shape"]), dtype=np.float32)
+        if rec["kind"] == "dark":
+            a = a * np.float32(0.3)
+        assert sha(a) == rec["sha_in"]
+        tv = O.texture_tv(a)
+        np.testing.assert_allclose(tv, rec["tv"], rtol=2e-6)
+        ed = O.texture_edge_density(a)
+        n = rec["shape"][2] * rec["shape"][3]
+        assert np.abs(ed - np.array(rec["edge_density"])).max() <= 4.0 / n
+        assert abs(O.dynamic_smooth_weight(tv) - rec["w_tv"]) <= 1e-6
