@@ -1,0 +1,656 @@
+// upr_clahe.cu -- CLAHE-in-Lab for sm_100a (B200).
+//
+// Replaces AdaptiveParameterAdjuster.apply_clahe_enhancement
+// (/root/reference/enhancers/adaptive_params.py:121-169), i.e. the host chain
+//   (x*255).astype(u8) -> RGB2BGR -> BGR2LAB -> split -> CLAHE(2.0,(8,8)).apply(L) -> merge
+//   -> LAB2BGR -> BGR2RGB -> /255
+// with two kernels per batch and a 3 B/px u8 Lab intermediate:
+//
+//   K1  k_hist_lab_*   one CTA per (frame, tile, row-strip): planar f32 RGB -> u8 quantise ->
+//                      OpenCV fixed-point Lab; stores L,a,b (u8 planes); per-THREAD private byte
+//                      counters in shared memory build the tile histogram without atomics
+//                      (shared atomics cost ~1-2 cycles/lane on this part: slower than the whole
+//                      budget of the kernel); the CTA (or the last strip CTA of the tile) then does
+//                      clip -> redistribute -> prefix scan -> LUT in place.
+//   K3  k_map_*        one CTA per (frame, interpolation cell, row-strip): the four tile LUTs that
+//                      surround a cell are interleaved into one 32-bit word per grey level, so the
+//                      bilinear LUT interpolation costs ONE shared-memory lookup per pixel; fused
+//                      with Lab -> sRGB (integer path) and the /255 de-quantisation.
+//
+// All fixed-point recipes follow SURVEY.md Appendix A (pinned against the cv2 binary by the
+// oracle tests).  fp32 products/sums of the interpolation use __fmul_rn/__fadd_rn so that ptxas
+// cannot contract them into FMAs: OpenCV evaluates them separately rounded (SURVEY finding 9).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "upr_common.cuh"
+#include "upr_tables_gen.h"
+
+namespace upr {
+
+// ---------------------------------------------------------------------------------------------
+// constant tables (device copies live in global memory; kernels stage what they need in smem)
+// ---------------------------------------------------------------------------------------------
+__device__ const uint16_t d_gamma[UPR_TAB_GAMMA_LEN] = UPR_TAB_GAMMA_INIT;
+__device__ const uint16_t d_cbrt[UPR_TAB_CBRT_LEN] = UPR_TAB_CBRT_INIT;
+__device__ const uint32_t d_labyf[UPR_TAB_LABYF_LEN] = UPR_TAB_LABYF_INIT;
+__device__ const uint32_t d_outf_bits[UPR_TAB_INVGAMMA_F32BITS_LEN] = UPR_TAB_INVGAMMA_F32BITS_INIT;
+
+static const uint16_t h_gamma[UPR_TAB_GAMMA_LEN] = UPR_TAB_GAMMA_INIT;
+static const uint16_t h_cbrt[UPR_TAB_CBRT_LEN] = UPR_TAB_CBRT_INIT;
+static const uint32_t h_labyf[UPR_TAB_LABYF_LEN] = UPR_TAB_LABYF_INIT;
+static const uint8_t h_invgamma[UPR_TAB_INVGAMMA_LEN] = UPR_TAB_INVGAMMA_INIT;
+
+constexpr int kMaxTiles = 16;  // per axis, fast path; larger grids take the generic path
+constexpr int kK1Threads = 256;
+constexpr int kK3Threads = 256;
+
+struct ClaheGeom {
+    int n, h, w;
+    int tiles_x, tiles_y;
+    int tw, th;        // tile size in the (possibly padded) image
+    int clip;          // integer clip limit, 0 = no clipping
+    float lut_scale;   // 255 / (tw*th)
+    int nstrips;       // K1 row strips per tile
+    int strip_rows;
+};
+
+struct MapGeom {
+    int n, h, w;
+    int tiles_x, tiles_y;
+    float inv_tw, inv_th;
+    int nstrips;
+    int bx[kMaxTiles + 2];  // cell c covers x in [bx[c], bx[c+1]); raw tile index of the cell is c-1
+    int by[kMaxTiles + 2];
+};
+
+// ---------------------------------------------------------------------------------------------
+// device arithmetic (Appendix A.1 / A.2)
+// ---------------------------------------------------------------------------------------------
+// sRGB u8 -> Lab u8.  No clamps: over the whole 2^24 cube L is 0..255, a 42..226, b 20..223.
+__device__ __forceinline__ void rgb_to_lab(int qr, int qg, int qb, const uint16_t* s_gamma, const uint16_t* s_cbrt,
+                                           int& L, int& a, int& b)
+{
+    const int R = s_gamma[qr], G = s_gamma[qg], B = s_gamma[qb];
+    const int fX = s_cbrt[(1777 * R + 1541 * G + 778 * B + 2048) >> 12];
+    const int fY = s_cbrt[(871 * R + 2929 * G + 296 * B + 2048) >> 12];
+    const int fZ = s_cbrt[(73 * R + 448 * G + 3575 * B + 2048) >> 12];
+    L = (296 * fY - 1336934 + 16384) >> 15;
+    a = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
+    b = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+}
+
+__device__ __forceinline__ int rgb_to_l_only(int qr, int qg, int qb, const uint16_t* s_gamma, const uint16_t* s_cbrt)
+{
+    const int R = s_gamma[qr], G = s_gamma[qg], B = s_gamma[qb];
+    const int fY = s_cbrt[(871 * R + 2929 * G + 296 * B + 2048) >> 12];
+    return (296 * fY - 1336934 + 16384) >> 15;
+}
+
+__device__ __forceinline__ int ab_to_xz(int i)
+{
+    const int lin = i * 108 / 841 - 290;            // C truncating division (i may be negative)
+    const int cub = (((i * i) >> 14) * i) >> 14;    // only selected for i > 3390 (all positive)
+    return i <= 3390 ? lin : cub;
+}
+
+// Lab u8 -> three de-quantised f32 channels (s_outf[c] = float(invgamma[c]) / 255.f).
+__device__ __forceinline__ void lab_to_rgb_f32(int L, int a, int b, const uint32_t* s_yf, const float* s_outf,
+                                               float& r, float& g, float& bl)
+{
+    const uint32_t yf = s_yf[L];
+    const int ify = int(yf & 0xffffu), y = int(yf >> 16);
+    const int adiv = ((a * 268435 + 128) >> 13) - 4194;   // 5*53687 = 268435
+    const int bdiv = ((b * 41943 + 16) >> 9) - 10484;
+    const int x = ab_to_xz(ify + adiv);
+    const int z = ab_to_xz(ify - bdiv);
+    int ro = (12615 * x - 6296 * y - 2223 * z + 8192) >> 14;
+    int go = (-3773 * x + 7684 * y + 185 * z + 8192) >> 14;
+    int bo = (217 * x - 836 * y + 4715 * z + 8192) >> 14;
+    ro = min(max(ro, 0), 4095);
+    go = min(max(go, 0), 4095);
+    bo = min(max(bo, 0), 4095);
+    r = s_outf[ro];
+    g = s_outf[go];
+    bl = s_outf[bo];
+}
+
+// clip -> redistribute -> inclusive scan -> LUT, for one tile; blockDim.x must be 256, thread i
+// owns bin i (Appendix A.3 steps 3-4).  s_tmp: >= 8 ints of shared scratch.
+__device__ __forceinline__ void tile_lut_256(int hbin, int clip, float lut_scale, uint8_t* __restrict__ lut_out, int* s_tmp)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (clip > 0) {
+        const int excess = max(hbin - clip, 0);
+        hbin = min(hbin, clip);
+        const int ws = warp_sum(excess);
+        if (lane == 0) s_tmp[wid] = ws;
+        __syncthreads();
+        int clipped = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) clipped += s_tmp[i];
+        __syncthreads();
+        const int batch = clipped >> 8;
+        const int resid = clipped & 255;
+        hbin += batch;
+        if (resid != 0) {
+            const int step = max(256 / resid, 1);
+            if (tid % step == 0 && tid / step < resid) ++hbin;
+        }
+    }
+    int v = hbin;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) s_tmp[wid] = v;
+    __syncthreads();
+    int base = 0;
+    for (int i = 0; i < wid; ++i) base += s_tmp[i];
+    const int sum = v + base;
+    const int r = __float2int_rn(__fmul_rn(__int2float_rn(sum), lut_scale));
+    lut_out[tid] = uint8_t(min(max(r, 0), 255));
+}
+
+// Publishes a CTA's partial tile histogram; returns true (block-uniform) if this CTA must build
+// the LUT, with `total` holding the complete histogram bin of thread `tid`.
+__device__ __forceinline__ bool publish_hist(int& total, int32_t* __restrict__ hg, unsigned* __restrict__ ticket,
+                                             int nparts, int* s_flag)
+{
+    const int tid = threadIdx.x;
+    if (nparts == 1) {
+        hg[tid] = total;
+        return true;
+    }
+    atomicAdd(&hg[tid], total);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *s_flag = (atomicAdd(ticket, 1u) == unsigned(nparts - 1));
+    __syncthreads();
+    if (!*s_flag) return false;
+    __threadfence();
+    total = __ldcg(&hg[tid]);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 fast path: W % tiles_x == 0, H % tiles_y == 0, tile width % 4 == 0, 16-byte aligned planes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kK1Threads, 3)
+k_hist_lab_vec(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
+               uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
+    uint16_t* s_gamma = reinterpret_cast<uint16_t*>(smem + 256 * kK1Threads);      // 256
+    uint16_t* s_cbrt = s_gamma + UPR_TAB_GAMMA_LEN;                                // 2048
+    __shared__ int s_tmp[8];
+    __shared__ int s_flag;
+
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x % g.nstrips;
+    const int tile = blockIdx.x / g.nstrips;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int f = blockIdx.y;
+    const int ntiles = g.tiles_x * g.tiles_y;
+
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cnt);
+#pragma unroll
+        for (int i = 0; i < 256 * kK1Threads / 16 / kK1Threads; ++i) z[tid + i * kK1Threads] = make_uint4(0, 0, 0, 0);
+        s_gamma[tid] = d_gamma[tid];
+        reinterpret_cast<uint4*>(s_cbrt)[tid] = reinterpret_cast<const uint4*>(d_cbrt)[tid];  // 256 x 16 B = 4 KB
+    }
+    __syncthreads();
+
+    const int row0 = ty * g.th + strip * g.strip_rows;
+    const int row1 = min(row0 + g.strip_rows, (ty + 1) * g.th);
+    const int tw4 = g.tw >> 2;
+    const int nitems = max(row1 - row0, 0) * tw4;
+    const size_t plane = size_t(g.h) * g.w;
+    const float* inR = in + size_t(f) * 3 * plane + size_t(row0) * g.w + tx * g.tw;
+    uint8_t* labL = lab + size_t(f) * 3 * plane + size_t(row0) * g.w + tx * g.tw;
+
+    int r = tid / tw4, c = tid - r * tw4;
+    const int dr = kK1Threads / tw4, dc = kK1Threads - dr * tw4;
+    // counter of (bin L, thread t) lives at byte ((L>>2)*256 + t)*4 + (L&3): the four counters of one
+    // 32-bit word belong to the SAME thread, so a warp always touches 32 distinct banks whatever L is.
+    unsigned char* my_cnt = s_cnt + tid * 4;
+
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    float4 vr, vg, vb;
+    size_t off = size_t(r) * g.w + c * 4;
+    if (tid < nitems) {
+        vr = ld_stream_f4(inR + off, pol_stream);
+        vg = ld_stream_f4(inR + plane + off, pol_stream);
+        vb = ld_stream_f4(inR + 2 * plane + off, pol_stream);
+    }
+    for (int i = tid; i < nitems; i += kK1Threads) {
+        const float4 cr = vr, cg = vg, cb = vb;
+        const size_t coff = off;
+        c += dc;
+        r += dr;
+        if (c >= tw4) { c -= tw4; ++r; }
+        off = size_t(r) * g.w + c * 4;
+        if (i + kK1Threads < nitems) {
+            vr = ld_stream_f4(inR + off, pol_stream);
+            vg = ld_stream_f4(inR + plane + off, pol_stream);
+            vb = ld_stream_f4(inR + 2 * plane + off, pol_stream);
+        }
+        const float pr[4] = {cr.x, cr.y, cr.z, cr.w};
+        const float pg[4] = {cg.x, cg.y, cg.z, cg.w};
+        const float pb[4] = {cb.x, cb.y, cb.z, cb.w};
+        uint32_t wl = 0, wa = 0, wb = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int L, a, b;
+            rgb_to_lab(quantize_u8(pr[k]), quantize_u8(pg[k]), quantize_u8(pb[k]), s_gamma, s_cbrt, L, a, b);
+            my_cnt[((L & 0xfc) << 8) | (L & 3)] += 1;
+            wl |= uint32_t(L) << (8 * k);
+            wa |= uint32_t(a) << (8 * k);
+            wb |= uint32_t(b) << (8 * k);
+        }
+        st_hint_u32(labL + coff, wl, pol_keep);
+        st_hint_u32(labL + plane + coff, wa, pol_keep);
+        st_hint_u32(labL + 2 * plane + coff, wb, pol_keep);
+    }
+    __syncthreads();
+
+    // thread `tid` sums bin `tid`: byte (tid&3) of the 256 words of row (tid>>2).  The four threads of a
+    // row read the same 16-byte chunks (broadcast); chunk order is rotated by the row so that the eight
+    // rows of a warp hit disjoint banks.
+    unsigned total_u = 0;
+    {
+        const uint4* row = reinterpret_cast<const uint4*>(s_cnt + (tid >> 2) * (kK1Threads * 4));
+        const unsigned sel = 1u << (8 * (tid & 3));
+#pragma unroll 8
+        for (int k = 0; k < kK1Threads / 4; ++k) {
+            const uint4 v = row[(k + (tid >> 2)) & (kK1Threads / 4 - 1)];
+            total_u = __dp4a(v.x, sel, total_u);
+            total_u = __dp4a(v.y, sel, total_u);
+            total_u = __dp4a(v.z, sel, total_u);
+            total_u = __dp4a(v.w, sel, total_u);
+        }
+    }
+    int total = int(total_u);
+    const size_t t_idx = size_t(f) * ntiles + tile;
+    if (!publish_hist(total, hist_g + t_idx * 256, tickets + t_idx, g.nstrips, &s_flag)) return;
+    tile_lut_256(total, g.clip, g.lut_scale, lut_g + t_idx * 256, s_tmp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 generic path: any size (including OpenCV's reflect-101 padding quirk, Appendix A.3 step 1).
+// One CTA per (frame, tile); per-warp shared histograms with atomics.  Correctness path for
+// ragged shapes -- the named workloads all take the vector path.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256)
+k_hist_lab_generic(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
+                   uint8_t* __restrict__ lut_g, const ClaheGeom g)
+{
+    __shared__ int s_hist[8][256];
+    __shared__ uint16_t s_gamma[UPR_TAB_GAMMA_LEN];
+    __shared__ uint16_t s_cbrt[UPR_TAB_CBRT_LEN];
+    __shared__ int s_tmp[8];
+
+    const int tid = threadIdx.x, wid = tid >> 5;
+    const int tile = blockIdx.x;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int f = blockIdx.y;
+    const int ntiles = g.tiles_x * g.tiles_y;
+    for (int i = tid; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
+    s_gamma[tid] = d_gamma[tid];
+    for (int i = tid; i < UPR_TAB_CBRT_LEN; i += 256) s_cbrt[i] = d_cbrt[i];
+    __syncthreads();
+
+    const size_t plane = size_t(g.h) * g.w;
+    const float* inR = in + size_t(f) * 3 * plane;
+    uint8_t* labL = lab + size_t(f) * 3 * plane;
+    const int area = g.tw * g.th;
+    const uint64_t pol_stream = policy_evict_first();
+    for (int i = tid; i < area; i += 256) {
+        const int py = ty * g.th + i / g.tw, px = tx * g.tw + i % g.tw;
+        const bool inside = py < g.h && px < g.w;
+        const size_t off = size_t(reflect101(py, g.h)) * g.w + reflect101(px, g.w);
+        const int qr = quantize_u8(ld_stream_f1(inR + off, pol_stream));
+        const int qg = quantize_u8(ld_stream_f1(inR + plane + off, pol_stream));
+        const int qb = quantize_u8(ld_stream_f1(inR + 2 * plane + off, pol_stream));
+        int L;
+        if (inside) {
+            int a, b;
+            rgb_to_lab(qr, qg, qb, s_gamma, s_cbrt, L, a, b);
+            labL[off] = uint8_t(L);
+            labL[plane + off] = uint8_t(a);
+            labL[2 * plane + off] = uint8_t(b);
+        } else {
+            L = rgb_to_l_only(qr, qg, qb, s_gamma, s_cbrt);
+        }
+        atomicAdd(&s_hist[wid][L], 1);
+    }
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) total += s_hist[k][tid];
+    const size_t t_idx = size_t(f) * ntiles + tile;
+    hist_g[t_idx * 256 + tid] = total;
+    tile_lut_256(total, g.clip, g.lut_scale, lut_g + t_idx * 256, s_tmp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 fast path
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kK3Threads)
+k_map_vec(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out, const MapGeom g)
+{
+    __shared__ uint32_t s_quad[256];
+    __shared__ uint32_t s_yf[256];
+    __shared__ __align__(16) float s_outf[4096];
+
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x % g.nstrips;
+    const int cell = blockIdx.x / g.nstrips;
+    const int cy = cell / (g.tiles_x + 1), cx = cell - cy * (g.tiles_x + 1);
+    const int f = blockIdx.y;
+
+    const int x0 = g.bx[cx], x1 = g.bx[cx + 1];
+    const int rows_cell = g.by[cy + 1] - g.by[cy];
+    const int srows = (rows_cell + g.nstrips - 1) / g.nstrips;
+    const int y0 = g.by[cy] + strip * srows;
+    const int y1 = min(y0 + srows, g.by[cy + 1]);
+    if (x0 >= x1 || y0 >= y1) return;
+
+    {
+        const int ty1 = max(cy - 1, 0), ty2 = min(cy, g.tiles_y - 1);
+        const int tx1 = max(cx - 1, 0), tx2 = min(cx, g.tiles_x - 1);
+        const uint8_t* lf = lut_g + size_t(f) * g.tiles_x * g.tiles_y * 256 + tid;
+        s_quad[tid] = uint32_t(lf[(ty1 * g.tiles_x + tx1) * 256]) | (uint32_t(lf[(ty1 * g.tiles_x + tx2) * 256]) << 8) |
+                      (uint32_t(lf[(ty2 * g.tiles_x + tx1) * 256]) << 16) | (uint32_t(lf[(ty2 * g.tiles_x + tx2) * 256]) << 24);
+        s_yf[tid] = d_labyf[tid];
+#pragma unroll
+        for (int i = 0; i < 4096 / 4 / kK3Threads; ++i)
+            reinterpret_cast<uint4*>(s_outf)[tid + i * kK3Threads] = reinterpret_cast<const uint4*>(d_outf_bits)[tid + i * kK3Threads];
+    }
+    __syncthreads();
+
+    const size_t plane = size_t(g.h) * g.w;
+    const uint8_t* labL = lab + size_t(f) * 3 * plane;
+    float* outR = out + size_t(f) * 3 * plane;
+    const float txbase = float(cx - 1), tybase = float(cy - 1);
+    const int cw4 = (x1 - x0) >> 2;
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+
+    for (int xc = 0; xc < cw4; xc += kK3Threads) {
+        const int cwc = min(kK3Threads, cw4 - xc);
+        const int rpi = kK3Threads / cwc;  // rows per iteration
+        const int lr = tid / cwc, lc = tid - lr * cwc;
+        if (lr >= rpi) continue;
+        const int x = x0 + (xc + lc) * 4;
+        float xa[4], xa1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float txf = __fadd_rn(__fmul_rn(float(x + k), g.inv_tw), -0.5f);
+            xa[k] = __fsub_rn(txf, txbase);
+            xa1[k] = __fsub_rn(1.0f, xa[k]);
+        }
+        for (int y = y0 + lr; y < y1; y += rpi) {
+            const float tyf = __fadd_rn(__fmul_rn(float(y), g.inv_th), -0.5f);
+            const float ya = __fsub_rn(tyf, tybase);
+            const float ya1 = __fsub_rn(1.0f, ya);
+            const size_t off = size_t(y) * g.w + x;
+            const uint32_t wl = ld_hint_u32(labL + off, pol_keep);
+            const uint32_t wa = ld_hint_u32(labL + plane + off, pol_keep);
+            const uint32_t wb = ld_hint_u32(labL + 2 * plane + off, pol_keep);
+            float o[3][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t q = s_quad[(wl >> (8 * k)) & 0xffu];
+                const float top = __fadd_rn(__fmul_rn(byte_to_float(q, 0), xa1[k]), __fmul_rn(byte_to_float(q, 1), xa[k]));
+                const float bot = __fadd_rn(__fmul_rn(byte_to_float(q, 2), xa1[k]), __fmul_rn(byte_to_float(q, 3), xa[k]));
+                const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+                // rint via the 1.5*2^23 trick (round-half-even, same as cvRound); 0 <= res < 255.5
+                const int Lc = __float_as_int(__fadd_rn(res, 12582912.0f)) & 0xff;
+                lab_to_rgb_f32(Lc, int((wa >> (8 * k)) & 0xffu), int((wb >> (8 * k)) & 0xffu), s_yf, s_outf, o[0][k], o[1][k], o[2][k]);
+            }
+            st_stream_f4(outR + off, make_float4(o[0][0], o[0][1], o[0][2], o[0][3]), pol_stream);
+            st_stream_f4(outR + plane + off, make_float4(o[1][0], o[1][1], o[1][2], o[1][3]), pol_stream);
+            st_stream_f4(outR + 2 * plane + off, make_float4(o[2][0], o[2][1], o[2][2], o[2][3]), pol_stream);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 generic path: one thread per pixel, LUTs read through L1/L2.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_map_generic(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out,
+              int h, int w, int tiles_x, int tiles_y, float inv_tw, float inv_th)
+{
+    __shared__ uint32_t s_yf[256];
+    __shared__ __align__(16) float s_outf[4096];
+    const int tid = threadIdx.x;
+    s_yf[tid] = d_labyf[tid];
+    for (int i = tid; i < 1024; i += 256) reinterpret_cast<uint4*>(s_outf)[i] = reinterpret_cast<const uint4*>(d_outf_bits)[i];
+    __syncthreads();
+
+    const int f = blockIdx.y;
+    const size_t plane = size_t(h) * w;
+    const uint8_t* labL = lab + size_t(f) * 3 * plane;
+    const uint8_t* lf = lut_g + size_t(f) * tiles_x * tiles_y * 256;
+    float* outR = out + size_t(f) * 3 * plane;
+    const uint64_t pol_stream = policy_evict_first();
+    for (size_t p = size_t(blockIdx.x) * 256 + tid; p < plane; p += size_t(gridDim.x) * 256) {
+        const int y = int(p / w), x = int(p - size_t(y) * w);
+        const float txf = __fadd_rn(__fmul_rn(float(x), inv_tw), -0.5f);
+        const float tyf = __fadd_rn(__fmul_rn(float(y), inv_th), -0.5f);
+        int tx1 = __float2int_rd(txf), ty1 = __float2int_rd(tyf);
+        const float xa = __fsub_rn(txf, float(tx1)), ya = __fsub_rn(tyf, float(ty1));
+        const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+        const int tx2 = min(tx1 + 1, tiles_x - 1), ty2 = min(ty1 + 1, tiles_y - 1);
+        tx1 = max(tx1, 0);
+        ty1 = max(ty1, 0);
+        const int v = labL[p];
+        const float l11 = float(__ldg(lf + (ty1 * tiles_x + tx1) * 256 + v));
+        const float l12 = float(__ldg(lf + (ty1 * tiles_x + tx2) * 256 + v));
+        const float l21 = float(__ldg(lf + (ty2 * tiles_x + tx1) * 256 + v));
+        const float l22 = float(__ldg(lf + (ty2 * tiles_x + tx2) * 256 + v));
+        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+        const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+        const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+        const int Lc = min(max(__float2int_rn(res), 0), 255);
+        float r, gch, b;
+        lab_to_rgb_f32(Lc, labL[plane + p], labL[2 * plane + p], s_yf, s_outf, r, gch, b);
+        st_stream_f1(outR + p, r, pol_stream);
+        st_stream_f1(outR + plane + p, gch, pol_stream);
+        st_stream_f1(outR + 2 * plane + p, b, pol_stream);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct ClaheLayout {
+    size_t off_hist, off_lut, off_tickets, off_lab, total;
+};
+
+static ClaheLayout clahe_layout(int n, int h, int w, int tiles_x, int tiles_y)
+{
+    ClaheLayout L;
+    const size_t nt = size_t(n) * tiles_x * tiles_y;
+    L.off_hist = 0;
+    L.off_tickets = align_up(L.off_hist + nt * 256 * sizeof(int32_t), 256);
+    L.off_lut = align_up(L.off_tickets + nt * sizeof(unsigned), 256);
+    L.off_lab = align_up(L.off_lut + nt * 256, 256);
+    L.total = align_up(L.off_lab + size_t(n) * 3 * h * w, 256);
+    return L;
+}
+
+static bool valid_shape(int n, int h, int w, int tiles_x, int tiles_y)
+{
+    return n >= 0 && h > 0 && w > 0 && tiles_x > 0 && tiles_y > 0 && tiles_x <= 256 && tiles_y <= 256 &&
+           size_t(h) * w <= (size_t(1) << 30);
+}
+
+// raw tile coordinate of OpenCV's interpolation: floor(p * inv - 0.5f), fp32, separately rounded
+static inline int raw_tile(int p, float inv)
+{
+    volatile float m = float(p) * inv;  // volatile: forbid host-side contraction
+    volatile float t = m - 0.5f;
+    return int(std::floor(t));
+}
+
+static int clahe_run(const float* in, float* out, int n, int h, int w, double clip_limit, int tiles_x, int tiles_y,
+                     void* ws, size_t ws_bytes, cudaStream_t stream)
+{
+    if (!valid_shape(n, h, w, tiles_x, tiles_y)) return UPR_E_SHAPE;
+    if (n == 0) return UPR_OK;
+    if (!in || !out || !ws) return UPR_E_NULL;
+    if (!(clip_limit == clip_limit)) return UPR_E_PARAM;
+    const ClaheLayout lay = clahe_layout(n, h, w, tiles_x, tiles_y);
+    if (ws_bytes < lay.total || (reinterpret_cast<uintptr_t>(ws) & 255u)) return UPR_E_WORKSPACE;
+
+    auto* base = static_cast<unsigned char*>(ws);
+    auto* hist = reinterpret_cast<int32_t*>(base + lay.off_hist);
+    auto* tickets = reinterpret_cast<unsigned*>(base + lay.off_tickets);
+    auto* lut = base + lay.off_lut;
+    auto* lab = base + lay.off_lab;
+
+    const bool padded = (w % tiles_x != 0) || (h % tiles_y != 0);
+    const int wp = padded ? w + (tiles_x - w % tiles_x) : w;
+    const int hp = padded ? h + (tiles_y - h % tiles_y) : h;
+
+    ClaheGeom g{};
+    g.n = n; g.h = h; g.w = w; g.tiles_x = tiles_x; g.tiles_y = tiles_y;
+    g.tw = wp / tiles_x; g.th = hp / tiles_y;
+    const int area = g.tw * g.th;
+    g.clip = 0;
+    if (clip_limit > 0.0) g.clip = std::max(int(clip_limit * area / 256), 1);
+    g.lut_scale = float(255) / float(area);
+    const float inv_tw = 1.0f / float(g.tw), inv_th = 1.0f / float(g.th);
+
+    // interpolation cell boundaries from the exact fp32 recipe (monotone in p)
+    MapGeom m{};
+    bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && aligned16(in) && aligned16(out);
+    if (fast) {
+        m.n = n; m.h = h; m.w = w; m.tiles_x = tiles_x; m.tiles_y = tiles_y; m.inv_tw = inv_tw; m.inv_th = inv_th;
+        int c = 0;
+        m.bx[0] = 0;
+        for (int x = 0; x < w; ++x) {
+            const int t = raw_tile(x, inv_tw) + 1;  // cell index
+            if (t < c || t > tiles_x) { fast = false; break; }
+            while (c < t) m.bx[++c] = x;
+        }
+        while (c < tiles_x + 1) m.bx[++c] = w;
+        c = 0;
+        m.by[0] = 0;
+        for (int y = 0; y < h && fast; ++y) {
+            const int t = raw_tile(y, inv_th) + 1;
+            if (t < c || t > tiles_y) { fast = false; break; }
+            while (c < t) m.by[++c] = y;
+        }
+        while (c < tiles_y + 1) m.by[++c] = h;
+        for (int i = 0; i <= tiles_x + 1 && fast; ++i) fast = (m.bx[i] % 4 == 0);
+    }
+
+    const int ntiles = tiles_x * tiles_y;
+    // a frame index rides in gridDim.y (<= 65535): run long batches in slices
+    for (int f0 = 0; f0 < n; f0 += 65535) {
+        const int nf = std::min(n - f0, 65535);
+        const size_t fplane = size_t(f0) * 3 * h * w;
+        const size_t ftile = size_t(f0) * ntiles;
+        if (fast) {
+            // K1: byte counters allow <= 255 pixels per thread between flushes -> <= 63 items/thread
+            const int tw4 = g.tw / 4;
+            const int max_rows = std::max(1, (63 * kK1Threads) / tw4);
+            int nstrips = (g.th + max_rows - 1) / max_rows;
+            const int want = (3 * kNumSMsB200 + nf * ntiles - 1) / (nf * ntiles);  // fill the machine for tiny batches
+            nstrips = std::min(std::max(nstrips, want), g.th);
+            g.strip_rows = (g.th + nstrips - 1) / nstrips;
+            g.nstrips = (g.th + g.strip_rows - 1) / g.strip_rows;
+            if (g.nstrips > 1) {
+                UPR_CUDA_TRY(cudaMemsetAsync(hist + ftile * 256, 0, size_t(nf) * ntiles * 256 * sizeof(int32_t), stream));
+                UPR_CUDA_TRY(cudaMemsetAsync(tickets + ftile, 0, size_t(nf) * ntiles * sizeof(unsigned), stream));
+            }
+            const size_t smem1 = size_t(256) * kK1Threads + UPR_TAB_GAMMA_LEN * 2 + UPR_TAB_CBRT_LEN * 2;
+            static bool attr_set = false;  // benign race: idempotent
+            if (!attr_set) {
+                UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
+                attr_set = true;
+            }
+            k_hist_lab_vec<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
+                                                                                        lut + ftile * 256, tickets + ftile, g);
+            UPR_LAUNCH_CHECK();
+            const int ncells = (tiles_x + 1) * (tiles_y + 1);
+            const int cell_rows = g.th;  // interior cells are one tile high
+            int ks = std::max(1, int((size_t(cell_rows) * g.tw + 32767) / 32768));
+            const int want3 = (8 * kNumSMsB200 + nf * ncells - 1) / (nf * ncells);
+            ks = std::min(std::max(ks, want3), std::max(cell_rows / 4, 1));
+            m.nstrips = ks;
+            k_map_vec<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
+            UPR_LAUNCH_CHECK();
+        } else {
+            g.nstrips = 1; g.strip_rows = g.th;
+            k_hist_lab_generic<<<dim3(ntiles, nf), 256, 0, stream>>>(in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, g);
+            UPR_LAUNCH_CHECK();
+            const size_t plane = size_t(h) * w;
+            const int gx = int(std::min<size_t>((plane + 255) / 256, 4096));
+            k_map_generic<<<dim3(gx, nf), 256, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, h, w, tiles_x, tiles_y, inv_tw, inv_th);
+            UPR_LAUNCH_CHECK();
+        }
+    }
+    return UPR_OK;
+}
+
+}  // namespace upr
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+size_t upr_clahe_workspace_bytes(int n, int h, int w, int tiles_x, int tiles_y)
+{
+    if (!upr::valid_shape(n, h, w, tiles_x, tiles_y)) return 0;
+    return upr::clahe_layout(std::max(n, 1), h, w, tiles_x, tiles_y).total;
+}
+
+int upr_clahe_lab_f32(const float* in_nchw, float* out_nchw, int n, int h, int w, double clip_limit, int tiles_x,
+                      int tiles_y, void* workspace, size_t workspace_bytes, upr_stream_t stream)
+{
+    return upr::clahe_run(in_nchw, out_nchw, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int upr_clahe_debug_dump(const void* workspace, int n, int h, int w, int tiles_x, int tiles_y, int32_t* hist_out,
+                         uint8_t* lut_out, uint8_t* lab_out, upr_stream_t stream)
+{
+    if (!upr::valid_shape(n, h, w, tiles_x, tiles_y)) return UPR_E_SHAPE;
+    if (!workspace) return UPR_E_NULL;
+    if (n == 0) return UPR_OK;
+    const upr::ClaheLayout lay = upr::clahe_layout(n, h, w, tiles_x, tiles_y);
+    const auto* base = static_cast<const unsigned char*>(workspace);
+    auto s = static_cast<cudaStream_t>(stream);
+    const size_t nt = size_t(n) * tiles_x * tiles_y;
+    if (hist_out) UPR_CUDA_TRY(cudaMemcpyAsync(hist_out, base + lay.off_hist, nt * 256 * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (lut_out) UPR_CUDA_TRY(cudaMemcpyAsync(lut_out, base + lay.off_lut, nt * 256, cudaMemcpyDeviceToDevice, s));
+    if (lab_out) UPR_CUDA_TRY(cudaMemcpyAsync(lab_out, base + lay.off_lab, size_t(n) * 3 * h * w, cudaMemcpyDeviceToDevice, s));
+    return UPR_OK;
+}
+
+int upr_get_tables(uint16_t* gamma, uint16_t* cbrt, uint32_t* labyf, uint8_t* invgamma)
+{
+    if (gamma) std::memcpy(gamma, upr::h_gamma, sizeof upr::h_gamma);
+    if (cbrt) std::memcpy(cbrt, upr::h_cbrt, sizeof upr::h_cbrt);
+    if (labyf) std::memcpy(labyf, upr::h_labyf, sizeof upr::h_labyf);
+    if (invgamma) std::memcpy(invgamma, upr::h_invgamma, sizeof upr::h_invgamma);
+    return UPR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// upr_common.cuh -- shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/upretinex_b200.h"
+
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ < 1000
+#error "upretinex_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+#define UPR_CUDA_TRY(expr)                          \
+    do {                                            \
+        cudaError_t _e = (expr);                    \
+        if (_e != cudaSuccess) return int(_e);      \
+    } while (0)
+
+#define UPR_LAUNCH_CHECK()                          \
+    do {                                            \
+        cudaError_t _e = cudaPeekAtLastError();     \
+        if (_e != cudaSuccess) return int(_e);      \
+    } while (0)
+
+namespace upr {
+
+constexpr int kNumSMsB200 = 148;
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------
+// streaming global accesses: every f32 pixel is touched exactly once, so keep it out of L1
+// and mark it evict-first in L2; the u8 Lab intermediate is what should stay L2-resident.
+// ---------------------------------------------------------------------------------------
+// (sm_100a accepts the bare .L2::evict_* qualifiers only on 256-bit accesses, so narrower ones
+//  carry a createpolicy descriptor through .L2::cache_hint.)
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float* p, uint64_t pol)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f1(const float* p, uint64_t pol)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v, uint64_t pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_f1(float* p, float v, uint64_t pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_u32(void* p, uint32_t v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_hint_u32(const void* p, uint64_t pol)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// numpy `(x*255).astype(uint8)` (reference adaptive_params.py:142): fp32 multiply, truncate
+// toward zero, wrap mod 256; NaN, +-inf and |v| >= 2^31 give 0 (x86 cvttss2si "indefinite").
+// cvt.rzi.s32.f32 saturates instead, so only the positive overflow needs a fix-up
+// (INT_MIN already has a zero low byte, NaN converts to 0).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int quantize_u8(float x)
+{
+    int i = __float2int_rz(__fmul_rn(x, 255.0f));
+    i = (i == 0x7fffffff) ? 0 : i;
+    return i & 0xff;
+}
+
+// u8 -> f32 without the (slower) conversion pipe: 0x4B000000 | b is 2^23 + b.
+__device__ __forceinline__ float byte_to_float(uint32_t word, int k)
+{
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 | k)) - 8388608.0f;
+}
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace upr

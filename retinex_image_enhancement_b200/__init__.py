@@ -1,0 +1,9 @@
+"""Import alias: the package directory is ``retinex-image-enhancement_b200/`` (a hyphen cannot be
+imported), so this stub points ``retinex_image_enhancement_b200`` at it."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "retinex-image-enhancement_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+del _os, _f
