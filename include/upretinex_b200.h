@@ -62,6 +62,12 @@ UPR_API size_t upr_clahe_workspace_bytes(int n, int h, int w, int tiles_x, int t
 UPR_API int upr_clahe_lab_f32(const float* in_nchw, float* out_nchw, int n, int h, int w,
                               double clip_limit, int tiles_x, int tiles_y,
                               void* workspace, size_t workspace_bytes, upr_stream_t stream);
+/* Profiling hook: runs only the selected stages of upr_clahe_lab_f32 on a workspace that a full call has
+ * already populated.  stage_mask bit 0 = K1 (quantise + Lab + tile histograms + clip/LUT), bit 1 = K3
+ * (bilinear LUT map + Lab->RGB); bench.py uses it to time each kernel with CUDA events. */
+UPR_API int upr_clahe_lab_stages_f32(const float* in_nchw, float* out_nchw, int n, int h, int w, double clip_limit,
+                                     int tiles_x, int tiles_y, void* workspace, size_t workspace_bytes, int stage_mask,
+                                     upr_stream_t stream);
 /* Copies the per-tile raw histograms ([n][tiles_y*tiles_x][256] int32), LUTs
  * ([n][tiles_y*tiles_x][256] u8) and/or the u8 Lab intermediate ([n][3][h][w]) of the LAST
  * upr_clahe_lab_f32 call that used `workspace` into caller device buffers (any may be NULL). */
@@ -71,6 +77,80 @@ UPR_API int upr_clahe_debug_dump(const void* workspace, int n, int h, int w, int
 /* Host copies of the constant tables the kernels use (for tests/audits). Any may be NULL.
  * gamma[256] u16, cbrt[2048] u16, labyf[256] u32 (ify | y<<16), invgamma[4096] u8. */
 UPR_API int upr_get_tables(uint16_t* gamma, uint16_t* cbrt, uint32_t* labyf, uint8_t* invgamma);
+
+
+/* Same op with HOST buffers (the reference returns a host tensor, adaptive_params.py:164-167): f32 NCHW in
+ * host memory in, f32 NCHW in host memory out.  The batch is pipelined through a per-device ring of three
+ * streams with library-owned device staging (H2D, kernels and D2H of neighbouring chunks overlap); returns
+ * when out_host is complete.  Pinned host memory gives full PCIe speed; pageable memory works.
+ * frames_per_chunk <= 0 selects ~96 MB chunks.  upr_host_pool_release() frees the staging pool. */
+UPR_API int upr_clahe_lab_f32_host(const float* in_host, float* out_host, int n, int h, int w, double clip_limit,
+                                   int tiles_x, int tiles_y, int frames_per_chunk);
+UPR_API int upr_host_pool_release(void);
+
+/* ---- a3: brightness histogram ---------------------------------------------------------
+ * Replaces the pixel passes of AdaptiveParameterAdjuster.calculate_brightness_features
+ * (enhancers/adaptive_params.py:24-68): trunc-quantise, OpenCV BGR2GRAY fixed point, 256-bin histogram per
+ * image ([n][256] u32, zeroed by the call).  mean/std/dark/mid/bright ratios are exact functions of it. */
+UPR_API int upr_brightness_hist_f32(const float* in_nchw, int n, int h, int w, uint32_t* hist256_per_image,
+                                    upr_stream_t stream);
+
+/* ---- a4/a5: multi-scale statistics and gain ---------------------------------------------
+ * Replaces MultiScaleEnhancer.extract_multi_scale_features (enhancers/multi_scale.py:17-60) and the gain of
+ * apply_multi_scale_enhancement (:87-94).  means_n_by_3[i] = mean of the 7 feature channels at scales
+ * {1, 1/2, 1/4}; gain_per_image[i] = float(1 + 0.1 * (0.5 m1 + 0.3 m2 + 0.2 m3)).
+ * flags bit 0: force the generic (non-fused) path.  n <= 65535. */
+UPR_API size_t upr_multiscale_workspace_bytes(int n, int h, int w);
+UPR_API int upr_multiscale_stats_f32(const float* x_nchw, int n, int h, int w, float* means_n_by_3,
+                                     float* gain_per_image, void* workspace, size_t workspace_bytes, int flags,
+                                     upr_stream_t stream);
+/* Also materialises the three feature tensors [n][7][h_s][w_s] (h_s = int(h*s), w_s = int(w*s)) that
+ * extract_multi_scale_features returns; means/gain may be NULL. */
+UPR_API int upr_multiscale_features_f32(const float* x_nchw, int n, int h, int w, float* feat_full, float* feat_half,
+                                        float* feat_quarter, float* means_n_by_3, float* gain_per_image,
+                                        void* workspace, size_t workspace_bytes, upr_stream_t stream);
+/* out = clamp(enh * gain_per_image[image], 0, 1)   (enhancers/multi_scale.py:97-98); enh is [n][c][h][w]. */
+UPR_API int upr_scale_clamp_f32(const float* enh, const float* gain_per_image, float* out, int n, int c, int h, int w,
+                                upr_stream_t stream);
+
+/* ---- a6/a7: content-aware saliency / attention ------------------------------------------
+ * upr_saliency_f32 replaces ContentAwareEnhancer.compute_saliency_map (enhancers/content_aware.py:19-59):
+ * u8 gray -> |4-neighbour Laplacian| -> 15x15 Gaussian (sigma 2.6, fp64) -> per-image min-max normalise -> f32
+ * [n][1][h][w].  upr_attention_f32 replaces compute_attention_map (:61-91): sal * (1/(luma+0.1)), min-max
+ * normalised.  upr_attention_apply_f32 is :119-120: out = clamp(enh * (1 + 0.2*att), 0, 1).  n <= 65535. */
+UPR_API size_t upr_saliency_workspace_bytes(int n, int h, int w);
+UPR_API int upr_saliency_f32(const float* x_nchw, int n, int h, int w, float* sal_n1hw, void* workspace,
+                             size_t workspace_bytes, upr_stream_t stream);
+UPR_API int upr_attention_f32(const float* x_nchw, int n, int h, int w, float* att_n1hw, void* workspace,
+                              size_t workspace_bytes, upr_stream_t stream);
+UPR_API int upr_attention_apply_f32(const float* enh, const float* att_n1hw, float* out, int n, int c, int h, int w,
+                                    upr_stream_t stream);
+
+/* ---- a8: Retinex decomposition / recombination ------------------------------------------
+ * models/model.py:405-413 (R = x / (illu + eps), illu broadcast over the 3 channels) and :442
+ * (enhanced = R*e + (1-R)*e^2).  refl may be NULL.  Bit-exact with torch eager (no FMA contraction). */
+UPR_API int upr_retinex_recombine_f32(const float* x, const float* illu, const float* e, float* refl, float* enh,
+                                      int n, int h, int w, float eps, upr_stream_t stream);
+UPR_API int upr_retinex_decompose_f32(const float* x, const float* illu, float* refl, int n, int h, int w, float eps,
+                                      upr_stream_t stream);
+
+/* ---- a9/a10: texture complexity and the dynamic smoothness weight ------------------------
+ * losses/loss.py:523-583: per_image[i] = mean|dx| + mean|dy| ('tv') or the fraction of pixels whose Sobel
+ * magnitude exceeds 1.5x its mean ('edge_density').  batch_stats2 (nullable) receives
+ * [sum_i per_image[i], n] -- the two numbers a data-parallel all-reduce(SUM) carries so that every rank
+ * derives the batch mean of loss.py:710.  The workspace must be zero-filled once before its first use
+ * (upr_texture_workspace_init); the kernels leave it clean.  n <= 65535.
+ * upr_dynamic_smooth_weight_f32 is loss.py:716-717 on the (all-reduced) pair:
+ * weight_out[0] = clamp(weight_smooth * (1 - 0.8 * stats[0]/stats[1]), 0.1, 5.0). */
+UPR_API size_t upr_texture_workspace_bytes(int n);
+UPR_API int upr_texture_workspace_init(void* workspace, size_t workspace_bytes, int n, upr_stream_t stream);
+UPR_API int upr_texture_tv_f32(const float* x, int n, int c, int h, int w, float* per_image, float* batch_stats2,
+                               void* workspace, size_t workspace_bytes, upr_stream_t stream);
+UPR_API int upr_texture_edge_density_f32(const float* x, int n, int c, int h, int w, float* per_image,
+                                         float* batch_stats2, void* workspace, size_t workspace_bytes,
+                                         upr_stream_t stream);
+UPR_API int upr_dynamic_smooth_weight_f32(const float* batch_stats2, float weight_smooth, float* weight_out,
+                                          upr_stream_t stream);
 
 #ifdef __cplusplus
 }

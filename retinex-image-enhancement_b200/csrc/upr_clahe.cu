@@ -506,8 +506,9 @@ static inline int raw_tile(int p, float inv)
     return int(std::floor(t));
 }
 
+// stage_mask: bit 0 = K1 (Lab + histograms + LUTs), bit 1 = K3 (map); 3 = the whole op
 static int clahe_run(const float* in, float* out, int n, int h, int w, double clip_limit, int tiles_x, int tiles_y,
-                     void* ws, size_t ws_bytes, cudaStream_t stream)
+                     void* ws, size_t ws_bytes, cudaStream_t stream, int stage_mask = 3)
 {
     if (!valid_shape(n, h, w, tiles_x, tiles_y)) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
@@ -574,7 +575,7 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             nstrips = std::min(std::max(nstrips, want), g.th);
             g.strip_rows = (g.th + nstrips - 1) / nstrips;
             g.nstrips = (g.th + g.strip_rows - 1) / g.strip_rows;
-            if (g.nstrips > 1) {
+            if (g.nstrips > 1 && (stage_mask & 1)) {
                 UPR_CUDA_TRY(cudaMemsetAsync(hist + ftile * 256, 0, size_t(nf) * ntiles * 256 * sizeof(int32_t), stream));
                 UPR_CUDA_TRY(cudaMemsetAsync(tickets + ftile, 0, size_t(nf) * ntiles * sizeof(unsigned), stream));
             }
@@ -584,25 +585,33 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                 UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
                 attr_set = true;
             }
-            k_hist_lab_vec<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
-                                                                                        lut + ftile * 256, tickets + ftile, g);
-            UPR_LAUNCH_CHECK();
+            if (stage_mask & 1) {
+                k_hist_lab_vec<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
+                                                                                            lut + ftile * 256, tickets + ftile, g);
+                UPR_LAUNCH_CHECK();
+            }
             const int ncells = (tiles_x + 1) * (tiles_y + 1);
             const int cell_rows = g.th;  // interior cells are one tile high
             int ks = std::max(1, int((size_t(cell_rows) * g.tw + 32767) / 32768));
             const int want3 = (8 * kNumSMsB200 + nf * ncells - 1) / (nf * ncells);
             ks = std::min(std::max(ks, want3), std::max(cell_rows / 4, 1));
             m.nstrips = ks;
-            k_map_vec<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
-            UPR_LAUNCH_CHECK();
+            if (stage_mask & 2) {
+                k_map_vec<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
+                UPR_LAUNCH_CHECK();
+            }
         } else {
             g.nstrips = 1; g.strip_rows = g.th;
-            k_hist_lab_generic<<<dim3(ntiles, nf), 256, 0, stream>>>(in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, g);
-            UPR_LAUNCH_CHECK();
+            if (stage_mask & 1) {
+                k_hist_lab_generic<<<dim3(ntiles, nf), 256, 0, stream>>>(in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, g);
+                UPR_LAUNCH_CHECK();
+            }
             const size_t plane = size_t(h) * w;
             const int gx = int(std::min<size_t>((plane + 255) / 256, 4096));
-            k_map_generic<<<dim3(gx, nf), 256, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, h, w, tiles_x, tiles_y, inv_tw, inv_th);
-            UPR_LAUNCH_CHECK();
+            if (stage_mask & 2) {
+                k_map_generic<<<dim3(gx, nf), 256, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, h, w, tiles_x, tiles_y, inv_tw, inv_th);
+                UPR_LAUNCH_CHECK();
+            }
         }
     }
     return UPR_OK;
@@ -626,6 +635,14 @@ int upr_clahe_lab_f32(const float* in_nchw, float* out_nchw, int n, int h, int w
 {
     return upr::clahe_run(in_nchw, out_nchw, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
                           static_cast<cudaStream_t>(stream));
+}
+
+int upr_clahe_lab_stages_f32(const float* in_nchw, float* out_nchw, int n, int h, int w, double clip_limit, int tiles_x,
+                             int tiles_y, void* workspace, size_t workspace_bytes, int stage_mask, upr_stream_t stream)
+{
+    if ((stage_mask & 3) == 0) return UPR_E_PARAM;
+    return upr::clahe_run(in_nchw, out_nchw, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream), stage_mask & 3);
 }
 
 int upr_clahe_debug_dump(const void* workspace, int n, int h, int w, int tiles_x, int tiles_y, int32_t* hist_out,

@@ -1,0 +1,409 @@
+// upr_multiscale.cu -- three-scale feature statistics and gain of the multi-scale enhancer (sm_100a).
+//
+// Replaces MultiScaleEnhancer.extract_multi_scale_features and the gain computation of
+// apply_multi_scale_enhancement (/root/reference/enhancers/multi_scale.py:17-60, :87-94):
+//   for s in {1, 1/2, 1/4}:  img_s = bilinear(x, size=(int(H*s), int(W*s)), align_corners=False)
+//       features_s = cat[img_s (3), luma .299/.587/.114 (1), sqrt(gx^2+gy^2) of torch.gradient per channel (3)]
+//   gain = 1 + 0.1 * sum_s w_s * mean(features_s),   w = (0.5, 0.3, 0.2)
+//
+// The reference launches ~25 eager ops and re-reads the image ~10x.  Two paths here:
+//   * fused (H % 4 == 0 and W % 4 == 0, the named 1080p/4K shapes): ONE read of x.  At exact 1/2 and 1/4
+//     scales torch's bilinear sample points fall on pixel-pair midpoints, so the 1/2 image is the 2x2 mean
+//     and the 1/4 image is the mean of the centre 2x2 of every 4x4 block -- both are built in shared memory
+//     from the full-resolution tile (+4 px halo) a CTA has already staged, and all 3 x 7 channel sums come
+//     out of that one tile.
+//   * generic (any size, and whenever the feature maps themselves are requested): a bilinear down-sample
+//     kernel followed by one feature kernel per scale.
+// Sums are fp64 per thread -> warp shuffle -> one partial per CTA -> the last CTA of the image adds the
+// partials in index order (deterministic) and writes the three means and the gain.
+#include <algorithm>
+
+#include "upr_common.cuh"
+
+namespace upr {
+
+constexpr int kMsThreads = 256;
+constexpr int kMsMaxParts = 4096;
+
+__device__ __forceinline__ double ms_block_sum(double v, double* s_red)
+{
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kMsThreads / 32; ++i) t += s_red[i];
+    return t;
+}
+
+// torch.gradient along one axis (unit spacing, edge_order=1)
+__device__ __forceinline__ float grad1(float m, float c, float p, int i, int len)
+{
+    if (len == 1) return 0.0f;
+    if (i == 0) return __fsub_rn(p, c);
+    if (i == len - 1) return __fsub_rn(c, m);
+    return __fmul_rn(__fsub_rn(p, m), 0.5f);  // (p - m) / 2 : exact halving
+}
+
+template <bool kExactSqrt>
+__device__ __forceinline__ float edge_mag(float gx, float gy)
+{
+    const float s = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
+    if (kExactSqrt) return __fsqrt_rn(s);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    return r;
+}
+
+__device__ __forceinline__ float luma601(float r, float g, float b)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+}
+
+// means3 / gain from the three fp64 sums (multi_scale.py:90-94: fp32 .item() values accumulated in a Python float)
+__device__ __forceinline__ void ms_finalize(const double sums[3], const double counts[3], float* means3, float* gain,
+                                            double* gain64)
+{
+    const double wts[3] = {0.5, 0.3, 0.2};
+    double factor = 1.0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const float m = float(sums[s] / (7.0 * counts[s]));
+        means3[s] = m;
+        factor += wts[s] * double(m) * 0.1;
+    }
+    *gain = float(factor);
+    if (gain64) *gain64 = factor;
+}
+
+// -----------------------------------------------------------------------------------------
+// generic path
+// -----------------------------------------------------------------------------------------
+// F.interpolate(mode='bilinear', align_corners=False, size=(oh, ow)) of [planes][h][w]
+__global__ void __launch_bounds__(kMsThreads)
+k_ms_downsample(const float* __restrict__ src, int h, int w, float* __restrict__ dst, int oh, int ow, long long planes)
+{
+    const float sy = __fdiv_rn(float(h), float(oh)), sx = __fdiv_rn(float(w), float(ow));
+    const long long total = planes * oh * ow;
+    const long long stride = (long long)gridDim.x * kMsThreads;
+    for (long long it = (long long)blockIdx.x * kMsThreads + threadIdx.x; it < total; it += stride) {
+        const long long pl = it / ((long long)oh * ow);
+        const int rem = int(it - pl * oh * ow);
+        const int y = rem / ow, x = rem - y * ow;
+        float fy = __fsub_rn(__fmul_rn(__fadd_rn(float(y), 0.5f), sy), 0.5f);
+        float fx = __fsub_rn(__fmul_rn(__fadd_rn(float(x), 0.5f), sx), 0.5f);
+        fy = fy < 0.0f ? 0.0f : fy;
+        fx = fx < 0.0f ? 0.0f : fx;
+        const int y0 = int(fy), x0 = int(fx);
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float ly = __fsub_rn(fy, float(y0)), hy = __fsub_rn(1.0f, ly);
+        const float lx = __fsub_rn(fx, float(x0)), hx = __fsub_rn(1.0f, lx);
+        const float* p = src + pl * (long long)h * w;
+        const float a = __ldg(p + (long long)y0 * w + x0), b = __ldg(p + (long long)y0 * w + x1);
+        const float c = __ldg(p + (long long)y1 * w + x0), d = __ldg(p + (long long)y1 * w + x1);
+        const float top = __fadd_rn(__fmul_rn(hx, a), __fmul_rn(lx, b));
+        const float bot = __fadd_rn(__fmul_rn(hx, c), __fmul_rn(lx, d));
+        dst[it] = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+    }
+}
+
+// features of one scale: img [n][3][h][w] -> optional feat [n][7][h][w], partial sums [n][parts]
+template <bool kWrite>
+__global__ void __launch_bounds__(kMsThreads)
+k_ms_features(const float* __restrict__ img, int h, int w, float* __restrict__ feat, double* __restrict__ partial)
+{
+    __shared__ double s_red[kMsThreads / 32];
+    const int f = blockIdx.y, parts = gridDim.x;
+    const long long plane = (long long)h * w;
+    const float* base = img + (long long)f * 3 * plane;
+    float* fo = kWrite ? feat + (long long)f * 7 * plane : nullptr;
+    double acc = 0.0;
+    const long long stride = (long long)parts * kMsThreads;
+    for (long long it = (long long)blockIdx.x * kMsThreads + threadIdx.x; it < plane; it += stride) {
+        const int y = int(it / w), x = int(it - (long long)y * w);
+        float v[3], e[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* p = base + c * plane + it;
+            v[c] = __ldg(p);
+            const float xm = x > 0 ? __ldg(p - 1) : 0.0f, xp = x < w - 1 ? __ldg(p + 1) : 0.0f;
+            const float ym = y > 0 ? __ldg(p - w) : 0.0f, yp = y < h - 1 ? __ldg(p + w) : 0.0f;
+            e[c] = edge_mag<true>(grad1(xm, v[c], xp, x, w), grad1(ym, v[c], yp, y, h));
+        }
+        const float lum = luma601(v[0], v[1], v[2]);
+        if (kWrite) {
+            fo[it] = v[0];
+            fo[plane + it] = v[1];
+            fo[2 * plane + it] = v[2];
+            fo[3 * plane + it] = lum;
+            fo[4 * plane + it] = e[0];
+            fo[5 * plane + it] = e[1];
+            fo[6 * plane + it] = e[2];
+        }
+        acc += double(v[0]) + double(v[1]) + double(v[2]) + double(lum) + double(e[0]) + double(e[1]) + double(e[2]);
+    }
+    acc = ms_block_sum(acc, s_red);
+    if (threadIdx.x == 0) partial[(long long)f * parts + blockIdx.x] = acc;
+}
+
+// one thread per image: add the per-CTA partials of the three scales in index order
+__global__ void k_ms_finalize(const double* __restrict__ p0, const double* __restrict__ p1, const double* __restrict__ p2,
+                              int parts0, int parts1, int parts2, double c0, double c1, double c2, int n,
+                              float* __restrict__ means, float* __restrict__ gain)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    double sums[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < parts0; ++k) sums[0] += p0[(long long)f * parts0 + k];
+    for (int k = 0; k < parts1; ++k) sums[1] += p1[(long long)f * parts1 + k];
+    for (int k = 0; k < parts2; ++k) sums[2] += p2[(long long)f * parts2 + k];
+    const double counts[3] = {c0, c1, c2};
+    ms_finalize(sums, counts, means + 3 * f, gain + f, nullptr);
+}
+
+// -----------------------------------------------------------------------------------------
+// fused path: tile = 64 x 32 full-resolution pixels (16 x 8 quarter-resolution pixels), halo 4
+// -----------------------------------------------------------------------------------------
+constexpr int kTW = 64, kTH = 32, kHalo = 4;
+constexpr int kFW = kTW + 2 * kHalo, kFH = kTH + 2 * kHalo;          // 72 x 40 full-res staging
+constexpr int kHW = kTW / 2 + 2, kHH = kTH / 2 + 2;                  // 34 x 18 half-res (+1 halo)
+constexpr int kQW = kTW / 4 + 2, kQH = kTH / 4 + 2;                  // 18 x 10 quarter-res (+1 halo)
+
+template <int kW, int kH>
+__device__ __forceinline__ double tile_feature_sum(const float* __restrict__ s, int halo, int tw, int th, int gx0, int gy0,
+                                                   int gw, int gh)
+{
+    // s: [3][kH][kW] with `halo` border; pixel (ty,tx) of the tile sits at s[c][ty+halo][tx+halo];
+    // (gx0, gy0) = image coordinate of tile pixel (0,0) at this scale; gw x gh = image size at this scale.
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < tw * th; i += kMsThreads) {
+        const int ty = i / tw, tx = i - ty * tw;
+        const int x = gx0 + tx, y = gy0 + ty;
+        if (x >= gw || y >= gh) continue;
+        float v[3], e[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* p = s + (c * kH + ty + halo) * kW + tx + halo;
+            v[c] = p[0];
+            e[c] = edge_mag<false>(grad1(p[-1], v[c], p[1], x, gw), grad1(p[-kW], v[c], p[kW], y, gh));
+        }
+        const float lum = luma601(v[0], v[1], v[2]);
+        acc += double(__fadd_rn(__fadd_rn(__fadd_rn(v[0], v[1]), __fadd_rn(v[2], lum)), __fadd_rn(__fadd_rn(e[0], e[1]), e[2])));
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kMsThreads)
+k_ms_fused(const float* __restrict__ x, int h, int w, int tiles_x, double* __restrict__ partial,
+           unsigned* __restrict__ tickets, float* __restrict__ means, float* __restrict__ gain)
+{
+    extern __shared__ __align__(16) float s_ms[];
+    float* s_full = s_ms;                          // [3][kFH][kFW]
+    float* s_half = s_full + 3 * kFH * kFW;        // [3][kHH][kHW]
+    float* s_quar = s_half + 3 * kHH * kHW;        // [3][kQH][kQW]
+    __shared__ double s_red[kMsThreads / 32];
+    __shared__ int s_flag;
+
+    const int tid = threadIdx.x;
+    const int f = blockIdx.y, parts = gridDim.x;
+    const int tyi = blockIdx.x / tiles_x, txi = blockIdx.x - tyi * tiles_x;
+    const int x0 = txi * kTW, y0 = tyi * kTH;
+    const long long plane = (long long)h * w;
+    const float* img = x + (long long)f * 3 * plane;
+    const uint64_t pol = policy_evict_first();
+
+    // stage the full-resolution tile + halo (coordinates clamped into the image: values that come from a
+    // clamp are never used, torch.gradient is one-sided at the borders)
+    constexpr int kFW4 = kFW / 4;
+    for (int i = tid; i < 3 * kFH * kFW4; i += kMsThreads) {
+        const int c = i / (kFH * kFW4), r = (i / kFW4) % kFH, q = i % kFW4;
+        const int gy = min(max(y0 - kHalo + r, 0), h - 1);
+        const int gx = x0 - kHalo + q * 4;
+        float4 v;
+        if (gx >= 0 && gx + 3 < w) {
+            v = ld_stream_f4(img + c * plane + (long long)gy * w + gx, pol);
+        } else {
+            const float* row = img + c * plane + (long long)gy * w;
+            v.x = __ldg(row + min(max(gx, 0), w - 1));
+            v.y = __ldg(row + min(max(gx + 1, 0), w - 1));
+            v.z = __ldg(row + min(max(gx + 2, 0), w - 1));
+            v.w = __ldg(row + min(max(gx + 3, 0), w - 1));
+        }
+        *reinterpret_cast<float4*>(s_full + (c * kFH + r) * kFW + q * 4) = v;
+    }
+    __syncthreads();
+    // half-resolution tile with 1 halo: half pixel (hy,hx) of the tile = full pixels (2hy..2hy+1, 2hx..2hx+1)
+    for (int i = tid; i < 3 * kHH * kHW; i += kMsThreads) {
+        const int c = i / (kHH * kHW), r = (i / kHW) % kHH, q = i % kHW;
+        const float* p = s_full + (c * kFH + (2 * (r - 1) + kHalo)) * kFW + 2 * (q - 1) + kHalo;
+        const float top = __fadd_rn(__fmul_rn(0.5f, p[0]), __fmul_rn(0.5f, p[1]));
+        const float bot = __fadd_rn(__fmul_rn(0.5f, p[kFW]), __fmul_rn(0.5f, p[kFW + 1]));
+        s_half[i] = __fadd_rn(__fmul_rn(0.5f, top), __fmul_rn(0.5f, bot));
+    }
+    // quarter-resolution tile with 1 halo: centre 2x2 of the 4x4 block
+    for (int i = tid; i < 3 * kQH * kQW; i += kMsThreads) {
+        const int c = i / (kQH * kQW), r = (i / kQW) % kQH, q = i % kQW;
+        const float* p = s_full + (c * kFH + (4 * (r - 1) + 1 + kHalo)) * kFW + 4 * (q - 1) + 1 + kHalo;
+        const float top = __fadd_rn(__fmul_rn(0.5f, p[0]), __fmul_rn(0.5f, p[1]));
+        const float bot = __fadd_rn(__fmul_rn(0.5f, p[kFW]), __fmul_rn(0.5f, p[kFW + 1]));
+        s_quar[i] = __fadd_rn(__fmul_rn(0.5f, top), __fmul_rn(0.5f, bot));
+    }
+    __syncthreads();
+
+    double a0 = tile_feature_sum<kFW, kFH>(s_full, kHalo, kTW, kTH, x0, y0, w, h);
+    double a1 = tile_feature_sum<kHW, kHH>(s_half, 1, kTW / 2, kTH / 2, x0 / 2, y0 / 2, w / 2, h / 2);
+    double a2 = tile_feature_sum<kQW, kQH>(s_quar, 1, kTW / 4, kTH / 4, x0 / 4, y0 / 4, w / 4, h / 4);
+    a0 = ms_block_sum(a0, s_red);
+    a1 = ms_block_sum(a1, s_red);
+    a2 = ms_block_sum(a2, s_red);
+    double* pp = partial + ((long long)f * parts + blockIdx.x) * 3;
+    if (tid == 0) { pp[0] = a0; pp[1] = a1; pp[2] = a2; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(tickets + f, 1u);
+        s_flag = (t == unsigned(parts - 1));
+        if (s_flag) tickets[f] = 0;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    // last CTA of the image: ordered sum of the partials (256 threads stride over them, then a fixed tree)
+    double sums[3] = {0.0, 0.0, 0.0};
+    for (int k = tid; k < parts; k += kMsThreads) {
+        const double* q = partial + ((long long)f * parts + k) * 3;
+        sums[0] += __ldcg(q);
+        sums[1] += __ldcg(q + 1);
+        sums[2] += __ldcg(q + 2);
+    }
+    sums[0] = ms_block_sum(sums[0], s_red);
+    sums[1] = ms_block_sum(sums[1], s_red);
+    sums[2] = ms_block_sum(sums[2], s_red);
+    if (tid == 0) {
+        const double counts[3] = {double(h) * w, double(h / 2) * (w / 2), double(h / 4) * (w / 4)};
+        ms_finalize(sums, counts, means + 3 * f, gain + f, nullptr);
+    }
+}
+
+struct MsLayout {
+    size_t off_partial, off_tickets, off_half, off_quar, total;
+    int oh2, ow2, oh4, ow4;
+};
+
+static MsLayout ms_layout(int n, int h, int w)
+{
+    MsLayout L;
+    L.oh2 = int(h * 0.5); L.ow2 = int(w * 0.5); L.oh4 = int(h * 0.25); L.ow4 = int(w * 0.25);
+    L.off_partial = 0;
+    L.off_tickets = align_up(size_t(n) * kMsMaxParts * 3 * sizeof(double), 256);
+    L.off_half = align_up(L.off_tickets + size_t(n) * sizeof(unsigned), 256);
+    L.off_quar = align_up(L.off_half + size_t(n) * 3 * L.oh2 * L.ow2 * sizeof(float), 256);
+    L.total = align_up(L.off_quar + size_t(n) * 3 * L.oh4 * L.ow4 * sizeof(float), 256);
+    return L;
+}
+
+static int ms_parts(int n, long long px)
+{
+    const long long by_work = std::max<long long>(1, px / (kMsThreads * 4));
+    const long long by_fill = (4LL * kNumSMsB200 + n - 1) / n;
+    return int(std::max<long long>(1, std::min<long long>(std::min(by_work, by_fill), kMsMaxParts)));
+}
+
+static int ms_run(const float* x, int n, int h, int w, float* means, float* gain, float* f1, float* f2, float* f3,
+                  void* ws, size_t ws_bytes, cudaStream_t s, bool allow_fused)
+{
+    if (n < 0 || n > 65535 || h <= 0 || w <= 0) return UPR_E_SHAPE;
+    const MsLayout lay = ms_layout(std::max(n, 1), h, w);
+    if (lay.oh4 < 1 || lay.ow4 < 1) return UPR_E_SHAPE;  // torch raises on a zero-sized interpolate target
+    if (n == 0) return UPR_OK;
+    if (!x || !ws) return UPR_E_NULL;
+    if (ws_bytes < lay.total || (reinterpret_cast<uintptr_t>(ws) & 255u)) return UPR_E_WORKSPACE;
+    auto* base = static_cast<unsigned char*>(ws);
+    auto* partial = reinterpret_cast<double*>(base + lay.off_partial);
+    auto* tickets = reinterpret_cast<unsigned*>(base + lay.off_tickets);
+    auto* half = reinterpret_cast<float*>(base + lay.off_half);
+    auto* quar = reinterpret_cast<float*>(base + lay.off_quar);
+    const bool want_feat = f1 || f2 || f3;
+    if (want_feat && !(f1 && f2 && f3)) return UPR_E_NULL;
+    if (!want_feat && (!means || !gain)) return UPR_E_NULL;
+
+    const int tiles_x = (w + kTW - 1) / kTW, tiles_y = (h + kTH - 1) / kTH;
+    const bool fused = allow_fused && !want_feat && h % 4 == 0 && w % 4 == 0 && aligned16(x) &&
+                       (long long)tiles_x * tiles_y <= kMsMaxParts * 16LL;
+    if (fused) {
+        const int parts = tiles_x * tiles_y;
+        // partial holds 3 doubles per CTA; the generic layout reserves kMsMaxParts*3 per image
+        if (parts <= kMsMaxParts) {
+            const size_t smem = size_t(3) * (kFH * kFW + kHH * kHW + kQH * kQW) * sizeof(float);
+            static bool attr_set = false;
+            if (!attr_set) {
+                UPR_CUDA_TRY(cudaFuncSetAttribute(k_ms_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+                attr_set = true;
+            }
+            k_ms_fused<<<dim3(parts, n), kMsThreads, smem, s>>>(x, h, w, tiles_x, partial, tickets, means, gain);
+            UPR_LAUNCH_CHECK();
+            return UPR_OK;
+        }
+    }
+    // generic: down-sample, then one feature kernel per scale
+    {
+        const long long t2 = (long long)n * 3 * lay.oh2 * lay.ow2, t4 = (long long)n * 3 * lay.oh4 * lay.ow4;
+        const int g2 = int(std::min<long long>((t2 + kMsThreads - 1) / kMsThreads, 8LL * kNumSMsB200));
+        const int g4 = int(std::min<long long>((t4 + kMsThreads - 1) / kMsThreads, 8LL * kNumSMsB200));
+        k_ms_downsample<<<g2, kMsThreads, 0, s>>>(x, h, w, half, lay.oh2, lay.ow2, (long long)n * 3);
+        UPR_LAUNCH_CHECK();
+        k_ms_downsample<<<g4, kMsThreads, 0, s>>>(x, h, w, quar, lay.oh4, lay.ow4, (long long)n * 3);
+        UPR_LAUNCH_CHECK();
+    }
+    const int p0 = ms_parts(n, (long long)h * w), p1 = ms_parts(n, (long long)lay.oh2 * lay.ow2),
+              p2 = ms_parts(n, (long long)lay.oh4 * lay.ow4);
+    double* pp0 = partial;
+    double* pp1 = pp0 + (size_t)n * p0;
+    double* pp2 = pp1 + (size_t)n * p1;
+    if (want_feat) {
+        k_ms_features<true><<<dim3(p0, n), kMsThreads, 0, s>>>(x, h, w, f1, pp0);
+        k_ms_features<true><<<dim3(p1, n), kMsThreads, 0, s>>>(half, lay.oh2, lay.ow2, f2, pp1);
+        k_ms_features<true><<<dim3(p2, n), kMsThreads, 0, s>>>(quar, lay.oh4, lay.ow4, f3, pp2);
+    } else {
+        k_ms_features<false><<<dim3(p0, n), kMsThreads, 0, s>>>(x, h, w, nullptr, pp0);
+        k_ms_features<false><<<dim3(p1, n), kMsThreads, 0, s>>>(half, lay.oh2, lay.ow2, nullptr, pp1);
+        k_ms_features<false><<<dim3(p2, n), kMsThreads, 0, s>>>(quar, lay.oh4, lay.ow4, nullptr, pp2);
+    }
+    UPR_LAUNCH_CHECK();
+    if (means && gain) {
+        k_ms_finalize<<<(n + 63) / 64, 64, 0, s>>>(pp0, pp1, pp2, p0, p1, p2, double(h) * w, double(lay.oh2) * lay.ow2,
+                                                    double(lay.oh4) * lay.ow4, n, means, gain);
+        UPR_LAUNCH_CHECK();
+    }
+    return UPR_OK;
+}
+
+}  // namespace upr
+
+extern "C" {
+
+size_t upr_multiscale_workspace_bytes(int n, int h, int w)
+{
+    if (n < 0 || h <= 0 || w <= 0) return 0;
+    return upr::ms_layout(std::max(n, 1), h, w).total;
+}
+
+int upr_multiscale_stats_f32(const float* x_nchw, int n, int h, int w, float* means_n_by_3, float* gain_per_image,
+                             void* workspace, size_t workspace_bytes, int flags, upr_stream_t stream)
+{
+    return upr::ms_run(x_nchw, n, h, w, means_n_by_3, gain_per_image, nullptr, nullptr, nullptr, workspace,
+                       workspace_bytes, static_cast<cudaStream_t>(stream), (flags & 1) == 0);
+}
+
+int upr_multiscale_features_f32(const float* x_nchw, int n, int h, int w, float* feat_full, float* feat_half,
+                                float* feat_quarter, float* means_n_by_3, float* gain_per_image, void* workspace,
+                                size_t workspace_bytes, upr_stream_t stream)
+{
+    if (!feat_full || !feat_half || !feat_quarter) return UPR_E_NULL;
+    return upr::ms_run(x_nchw, n, h, w, means_n_by_3, gain_per_image, feat_full, feat_half, feat_quarter, workspace,
+                       workspace_bytes, static_cast<cudaStream_t>(stream), false);
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// upr_stats.cu -- per-image statistics kernels (sm_100a).
+//
+//   a3   brightness histogram       /root/reference/enhancers/adaptive_params.py:24-68
+//          u8 gray (OpenCV BGR2GRAY fixed point) of the trunc-quantised image, 256 bins.
+//          mean/std/dark/mid/bright ratios are exact functions of this histogram (host side).
+//   a9   texture complexity         /root/reference/losses/loss.py:523-583
+//          'tv'           mean|dx| + mean|dy| per image
+//          'edge_density' frac(Sobel magnitude > 1.5 * mean magnitude), gray = channel mean,
+//                         reflect(-101) padding
+//   a10  dynamic smoothness weight  /root/reference/losses/loss.py:704-720
+//          w = clamp(w0 * (1 - 0.8 * mean_B(c)), 0.1, 5.0)   from the (all-reduced) [sum c, B]
+//
+// Reductions: fp64 per-thread accumulators -> warp shuffles -> one partial per CTA written
+// to the workspace -> the last CTA of an image (ticket) adds the partials in index order.
+// No floating-point atomics: results are deterministic run to run.
+#include <algorithm>
+
+#include "upr_common.cuh"
+
+namespace upr {
+
+constexpr int kStThreads = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* s_red)
+{
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kStThreads / 32; ++i) t += s_red[i];
+    return t;
+}
+
+// true (block-uniform) in exactly one CTA per image: the one that arrived last
+__device__ __forceinline__ bool last_cta_of(unsigned* ticket, unsigned nparts, int* s_flag)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        *s_flag = (t == nparts - 1);
+        if (t == nparts - 1) *ticket = 0;  // self-cleaning: ready for the next call on this workspace
+    }
+    __syncthreads();
+    const bool last = *s_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+// Called by thread 0 of the CTA that finished image f: the image that finishes LAST adds the
+// per-image values in index order (deterministic) into stats2 = [sum of complexity, image count],
+// the two numbers the data-parallel all-reduce carries (loss.py:710 batch mean).
+__device__ __forceinline__ void finish_batch(unsigned* batch_ticket, int n, const float* per_image, float* stats2)
+{
+    if (!stats2) return;
+    __threadfence();
+    const unsigned t = atomicAdd(batch_ticket, 1u);
+    if (t != unsigned(n - 1)) return;
+    *batch_ticket = 0;
+    __threadfence();
+    float s = 0.0f;
+    for (int i = 0; i < n; ++i) s = __fadd_rn(s, __ldcg(per_image + i));
+    stats2[0] = s;
+    stats2[1] = float(n);
+}
+
+// -----------------------------------------------------------------------------------------
+// a3: brightness histogram.  grid = (parts, n); per-warp private shared histograms.
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ int gray_u8(int r, int g, int b) { return (r * 9798 + g * 19235 + b * 3735 + 16384) >> 15; }
+
+__global__ void __launch_bounds__(kStThreads)
+k_brightness_hist(const float* __restrict__ in, unsigned* __restrict__ hist, long long plane)
+{
+    __shared__ unsigned s_h[kStThreads / 32][256];
+    const int tid = threadIdx.x, wid = tid >> 5;
+    for (int i = tid; i < (kStThreads / 32) * 256; i += kStThreads) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const float* R = in + (long long)blockIdx.y * 3 * plane;
+    const uint64_t pol = policy_evict_first();
+    const long long stride = (long long)gridDim.x * kStThreads;
+    if (plane % 4 == 0 && aligned16(R)) {
+        const long long p4 = plane / 4;
+        for (long long i = (long long)blockIdx.x * kStThreads + tid; i < p4; i += stride) {
+            const float4 r = ld_stream_f4(R + i * 4, pol), g = ld_stream_f4(R + plane + i * 4, pol),
+                         b = ld_stream_f4(R + 2 * plane + i * 4, pol);
+            atomicAdd(&s_h[wid][gray_u8(quantize_u8(r.x), quantize_u8(g.x), quantize_u8(b.x))], 1u);
+            atomicAdd(&s_h[wid][gray_u8(quantize_u8(r.y), quantize_u8(g.y), quantize_u8(b.y))], 1u);
+            atomicAdd(&s_h[wid][gray_u8(quantize_u8(r.z), quantize_u8(g.z), quantize_u8(b.z))], 1u);
+            atomicAdd(&s_h[wid][gray_u8(quantize_u8(r.w), quantize_u8(g.w), quantize_u8(b.w))], 1u);
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * kStThreads + tid; i < plane; i += stride)
+            atomicAdd(&s_h[wid][gray_u8(quantize_u8(R[i]), quantize_u8(R[plane + i]), quantize_u8(R[2 * plane + i]))], 1u);
+    }
+    __syncthreads();
+    unsigned t = 0;
+#pragma unroll
+    for (int k = 0; k < kStThreads / 32; ++k) t += s_h[k][tid];
+    if (t) atomicAdd(&hist[(long long)blockIdx.y * 256 + tid], t);
+}
+
+// -----------------------------------------------------------------------------------------
+// a9 'tv'.  grid = (parts, n).  A work item is one row segment of 4 pixels of one channel.
+// -----------------------------------------------------------------------------------------
+// workspace: partial [n][parts][2] fp64, tickets [n] + 1 batch ticket, mean magnitude [n] fp64
+__global__ void __launch_bounds__(kStThreads)
+k_texture_tv(const float* __restrict__ x, int c, int h, int w, double* __restrict__ partial,
+             unsigned* __restrict__ tickets, float* __restrict__ per_image, float* __restrict__ stats2)
+{
+    __shared__ double s_red[kStThreads / 32];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    const int f = blockIdx.y, parts = gridDim.x;
+    const long long plane = (long long)h * w;
+    const float* img = x + (long long)f * c * plane;
+    double sh = 0.0, sv = 0.0;
+    const long long rows = (long long)c * h;  // (channel,row) pairs
+    const long long stride = (long long)parts * kStThreads;
+    if (w % 4 == 0 && aligned16(img)) {
+        const int w4 = w / 4;
+        const long long items = rows * w4;
+        for (long long it = (long long)blockIdx.x * kStThreads + tid; it < items; it += stride) {
+            const long long row = it / w4;
+            const int q = int(it - row * w4);
+            const int y = int(row % h);
+            const float* p = img + row * w + q * 4;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+            float hsum = fabsf(a.x - a.y) + fabsf(a.y - a.z) + fabsf(a.z - a.w);
+            if (q + 1 < w4) hsum += fabsf(a.w - __ldg(p + 4));
+            sh += double(hsum);
+            if (y + 1 < h) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p + w));
+                sv += double(fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w));
+            }
+        }
+    } else {
+        const long long items = rows * w;
+        for (long long it = (long long)blockIdx.x * kStThreads + tid; it < items; it += stride) {
+            const long long row = it / w;
+            const int xx = int(it - row * w);
+            const int y = int(row % h);
+            const float a = img[it];
+            if (xx + 1 < w) sh += double(fabsf(a - img[it + 1]));
+            if (y + 1 < h) sv += double(fabsf(a - img[it + w]));
+        }
+    }
+    sh = block_sum(sh, s_red);
+    sv = block_sum(sv, s_red);
+    if (tid == 0) {
+        partial[((long long)f * parts + blockIdx.x) * 2 + 0] = sh;
+        partial[((long long)f * parts + blockIdx.x) * 2 + 1] = sv;
+    }
+    if (!last_cta_of(tickets + f, parts, &s_flag)) return;
+    if (tid == 0) {
+        double th = 0.0, tv = 0.0;
+        for (int k = 0; k < parts; ++k) {
+            th += __ldcg(&partial[((long long)f * parts + k) * 2 + 0]);
+            tv += __ldcg(&partial[((long long)f * parts + k) * 2 + 1]);
+        }
+        // torch.mean of an empty slice is NaN (w == 1 or h == 1): 0/0 reproduces that
+        const float mh = float(th / (double(c) * h * (w - 1)));
+        const float mv = float(tv / (double(c) * (h - 1) * w));
+        const float cx = __fadd_rn(mh, mv);
+        per_image[f] = cx;
+        finish_batch(tickets + gridDim.y, gridDim.y, per_image, stats2);
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// a9 'edge_density'.  Pass 1 sums the Sobel magnitude, pass 2 recomputes it with the same
+// device function (bit-identical) and counts pixels above 1.5 * mean.
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101_dev(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+__device__ __forceinline__ float gray_mean(const float* __restrict__ img, long long plane, long long off, int c)
+{
+    if (c == 1) return __ldg(img + off);
+    float s = 0.0f;
+    for (int ch = 0; ch < c; ++ch) s = __fadd_rn(s, __ldg(img + ch * plane + off));
+    return __fdiv_rn(s, float(c));
+}
+
+__device__ __forceinline__ float sobel_mag(const float* __restrict__ img, long long plane, int c, int h, int w, int y, int x)
+{
+    const int ym = reflect101_dev(y - 1, h), yp = reflect101_dev(y + 1, h);
+    const int xm = reflect101_dev(x - 1, w), xp = reflect101_dev(x + 1, w);
+    const float a = gray_mean(img, plane, (long long)ym * w + xm, c), b = gray_mean(img, plane, (long long)ym * w + x, c),
+                cc = gray_mean(img, plane, (long long)ym * w + xp, c);
+    const float d = gray_mean(img, plane, (long long)y * w + xm, c), f = gray_mean(img, plane, (long long)y * w + xp, c);
+    const float g = gray_mean(img, plane, (long long)yp * w + xm, c), hh = gray_mean(img, plane, (long long)yp * w + x, c),
+                k = gray_mean(img, plane, (long long)yp * w + xp, c);
+    const float gx = __fadd_rn(__fadd_rn(__fsub_rn(cc, a), __fmul_rn(2.0f, __fsub_rn(f, d))), __fsub_rn(k, g));
+    const float gy = __fadd_rn(__fadd_rn(__fsub_rn(g, a), __fmul_rn(2.0f, __fsub_rn(hh, b))), __fsub_rn(k, cc));
+    return __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+}
+
+template <int kPass>
+__global__ void __launch_bounds__(kStThreads)
+k_texture_edge(const float* __restrict__ x, int c, int h, int w, double* __restrict__ partial,
+               unsigned* __restrict__ tickets, double* __restrict__ mean_mag, float* __restrict__ per_image,
+               float* __restrict__ stats2)
+{
+    __shared__ double s_red[kStThreads / 32];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    const int f = blockIdx.y, parts = gridDim.x;
+    const long long plane = (long long)h * w;
+    const float* img = x + (long long)f * c * plane;
+    float thr = 0.0f;
+    if (kPass == 2) thr = __fmul_rn(float(__ldcg(&mean_mag[f])), 1.5f);
+    double acc = 0.0;
+    const long long stride = (long long)parts * kStThreads;
+    for (long long it = (long long)blockIdx.x * kStThreads + tid; it < plane; it += stride) {
+        const int y = int(it / w), xx = int(it - (long long)y * w);
+        const float m = sobel_mag(img, plane, c, h, w, y, xx);
+        acc += (kPass == 1) ? double(m) : (m > thr ? 1.0 : 0.0);
+    }
+    acc = block_sum(acc, s_red);
+    if (tid == 0) partial[(long long)f * parts + blockIdx.x] = acc;
+    if (!last_cta_of(tickets + f, parts, &s_flag)) return;
+    if (tid == 0) {
+        double t = 0.0;
+        for (int k = 0; k < parts; ++k) t += __ldcg(&partial[(long long)f * parts + k]);
+        if (kPass == 1) {
+            mean_mag[f] = double(float(t / double(plane)));  // torch.mean result is fp32
+        } else {
+            const float cx = float(t / double(plane));
+            per_image[f] = cx;
+            finish_batch(tickets + gridDim.y, gridDim.y, per_image, stats2);
+        }
+    }
+}
+
+__global__ void k_dynamic_weight(const float* __restrict__ stats2, float w0, float* __restrict__ out)
+{
+    const float avg = __fdiv_rn(stats2[0], stats2[1]);
+    const float wv = __fmul_rn(w0, __fsub_rn(1.0f, __fmul_rn(avg, 0.8f)));
+    out[0] = wv < 0.1f ? 0.1f : (wv > 5.0f ? 5.0f : wv);
+}
+
+static int tex_parts(int n, long long items_per_image)
+{
+    const long long by_work = std::max<long long>(1, items_per_image / (kStThreads * 4));
+    const long long by_fill = (4LL * kNumSMsB200 + n - 1) / n;
+    return int(std::max<long long>(1, std::min<long long>(std::min(by_work, by_fill), 1024)));
+}
+
+struct TexLayout {
+    size_t off_partial, off_tickets, off_mean, total;
+};
+static TexLayout tex_layout(int n)
+{
+    TexLayout L;
+    L.off_partial = 0;
+    L.off_tickets = align_up(size_t(n) * 1024 * 2 * sizeof(double), 256);
+    L.off_mean = align_up(L.off_tickets + (size_t(n) + 1) * sizeof(unsigned), 256);
+    L.total = align_up(L.off_mean + size_t(n) * sizeof(double), 256);
+    return L;
+}
+
+}  // namespace upr
+
+extern "C" {
+
+int upr_brightness_hist_f32(const float* in_nchw, int n, int h, int w, uint32_t* hist256_per_image, upr_stream_t stream)
+{
+    if (n < 0 || h <= 0 || w <= 0) return UPR_E_SHAPE;
+    if (n == 0) return UPR_OK;
+    if (!in_nchw || !hist256_per_image) return UPR_E_NULL;
+    auto s = static_cast<cudaStream_t>(stream);
+    const long long plane = (long long)h * w;
+    UPR_CUDA_TRY(cudaMemsetAsync(hist256_per_image, 0, size_t(n) * 256 * sizeof(uint32_t), s));
+    const int parts = upr::tex_parts(n, plane / 4 + 1);
+    for (int f0 = 0; f0 < n; f0 += 65535) {
+        const int nf = std::min(n - f0, 65535);
+        upr::k_brightness_hist<<<dim3(parts, nf), upr::kStThreads, 0, s>>>(in_nchw + (long long)f0 * 3 * plane,
+                                                                           hist256_per_image + (long long)f0 * 256, plane);
+        UPR_LAUNCH_CHECK();
+    }
+    return UPR_OK;
+}
+
+size_t upr_texture_workspace_bytes(int n)
+{
+    if (n < 0) return 0;
+    return upr::tex_layout(std::max(n, 1)).total;
+}
+
+int upr_texture_workspace_init(void* workspace, size_t workspace_bytes, int n, upr_stream_t stream)
+{
+    if (n < 0) return UPR_E_SHAPE;
+    if (!workspace) return UPR_E_NULL;
+    const upr::TexLayout lay = upr::tex_layout(std::max(n, 1));
+    if (workspace_bytes < lay.total) return UPR_E_WORKSPACE;
+    UPR_CUDA_TRY(cudaMemsetAsync(workspace, 0, lay.total, static_cast<cudaStream_t>(stream)));
+    return UPR_OK;
+}
+
+static int texture_run(int method, const float* x, int n, int c, int h, int w, float* per_image, float* stats2,
+                       void* ws, size_t ws_bytes, cudaStream_t s)
+{
+    if (n < 0 || n > 65535 || c <= 0 || h <= 0 || w <= 0) return UPR_E_SHAPE;
+    if (n == 0) return UPR_OK;
+    if (!x || !per_image || !ws) return UPR_E_NULL;
+    const upr::TexLayout lay = upr::tex_layout(n);
+    if (ws_bytes < lay.total || (reinterpret_cast<uintptr_t>(ws) & 255u)) return UPR_E_WORKSPACE;
+    auto* base = static_cast<unsigned char*>(ws);
+    auto* partial = reinterpret_cast<double*>(base + lay.off_partial);
+    auto* tickets = reinterpret_cast<unsigned*>(base + lay.off_tickets);
+    auto* mean = reinterpret_cast<double*>(base + lay.off_mean);
+    const long long plane = (long long)h * w;
+    {
+        const int nf = n, f0 = 0;
+        const float* xf = x;
+        if (method == 0) {
+            const int parts = upr::tex_parts(n, (long long)c * plane / 4 + 1);
+            upr::k_texture_tv<<<dim3(parts, nf), upr::kStThreads, 0, s>>>(xf, c, h, w, partial + (long long)f0 * parts * 2,
+                                                                         tickets + f0, per_image + f0, stats2);
+            UPR_LAUNCH_CHECK();
+        } else {
+            const int parts = upr::tex_parts(n, plane);
+            upr::k_texture_edge<1><<<dim3(parts, nf), upr::kStThreads, 0, s>>>(xf, c, h, w, partial + (long long)f0 * parts,
+                                                                              tickets + f0, mean + f0, per_image + f0, nullptr);
+            UPR_LAUNCH_CHECK();
+            upr::k_texture_edge<2><<<dim3(parts, nf), upr::kStThreads, 0, s>>>(xf, c, h, w, partial + (long long)f0 * parts,
+                                                                              tickets + f0, mean + f0, per_image + f0, stats2);
+            UPR_LAUNCH_CHECK();
+        }
+    }
+    return UPR_OK;
+}
+
+int upr_texture_tv_f32(const float* x, int n, int c, int h, int w, float* per_image, float* batch_stats2, void* workspace,
+                       size_t workspace_bytes, upr_stream_t stream)
+{
+    return texture_run(0, x, n, c, h, w, per_image, batch_stats2, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int upr_texture_edge_density_f32(const float* x, int n, int c, int h, int w, float* per_image, float* batch_stats2,
+                                 void* workspace, size_t workspace_bytes, upr_stream_t stream)
+{
+    return texture_run(1, x, n, c, h, w, per_image, batch_stats2, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int upr_dynamic_smooth_weight_f32(const float* batch_stats2, float weight_smooth, float* weight_out, upr_stream_t stream)
+{
+    if (!batch_stats2 || !weight_out) return UPR_E_NULL;
+    upr::k_dynamic_weight<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(batch_stats2, weight_smooth, weight_out);
+    UPR_LAUNCH_CHECK();
+    return UPR_OK;
+}
+
+}  // extern "C"

@@ -81,8 +81,12 @@ class AdaptiveParameterAdjuster:
 
     # -- a1 ------------------------------------------------------------------------------------
     def apply_clahe_enhancement(self, image_tensor, keep_on_device: bool = False):
-        x = _to_device(_as_batch(image_tensor))
-        out = native.clahe_lab(x, self.CLIP_LIMIT, self.TILE_GRID)
+        image_tensor = _as_batch(image_tensor)
+        if not image_tensor.is_cuda and not keep_on_device:
+            # host in -> host out, like the reference (:136 / :164): H2D, kernels and D2H are pipelined
+            # inside the library (upr_clahe_lab_f32_host)
+            return native.clahe_lab_host(image_tensor.detach().to(torch.float32), self.CLIP_LIMIT, self.TILE_GRID)
+        out = native.clahe_lab(_to_device(image_tensor), self.CLIP_LIMIT, self.TILE_GRID)
         return out if keep_on_device else out.cpu()
 
     # -- a2 ------------------------------------------------------------------------------------

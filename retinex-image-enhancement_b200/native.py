@@ -39,10 +39,48 @@ def _declare(lib):
     lib.upr_clahe_workspace_bytes.argtypes = [i32] * 5
     lib.upr_clahe_lab_f32.restype = i32
     lib.upr_clahe_lab_f32.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, vp, sz, vp]
+    lib.upr_clahe_lab_stages_f32.restype = i32
+    lib.upr_clahe_lab_stages_f32.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, vp, sz, i32, vp]
     lib.upr_clahe_debug_dump.restype = i32
     lib.upr_clahe_debug_dump.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.upr_get_tables.restype = i32
     lib.upr_get_tables.argtypes = [vp] * 4
+    f32 = C.c_float
+    lib.upr_clahe_lab_f32_host.restype = i32
+    lib.upr_clahe_lab_f32_host.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, i32]
+    lib.upr_host_pool_release.restype = i32
+    lib.upr_brightness_hist_f32.restype = i32
+    lib.upr_brightness_hist_f32.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.upr_multiscale_workspace_bytes.restype = sz
+    lib.upr_multiscale_workspace_bytes.argtypes = [i32] * 3
+    lib.upr_multiscale_stats_f32.restype = i32
+    lib.upr_multiscale_stats_f32.argtypes = [vp, i32, i32, i32, vp, vp, vp, sz, i32, vp]
+    lib.upr_multiscale_features_f32.restype = i32
+    lib.upr_multiscale_features_f32.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.upr_scale_clamp_f32.restype = i32
+    lib.upr_scale_clamp_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.upr_saliency_workspace_bytes.restype = sz
+    lib.upr_saliency_workspace_bytes.argtypes = [i32] * 3
+    lib.upr_saliency_f32.restype = i32
+    lib.upr_saliency_f32.argtypes = [vp, i32, i32, i32, vp, vp, sz, vp]
+    lib.upr_attention_f32.restype = i32
+    lib.upr_attention_f32.argtypes = [vp, i32, i32, i32, vp, vp, sz, vp]
+    lib.upr_attention_apply_f32.restype = i32
+    lib.upr_attention_apply_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.upr_retinex_recombine_f32.restype = i32
+    lib.upr_retinex_recombine_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    lib.upr_retinex_decompose_f32.restype = i32
+    lib.upr_retinex_decompose_f32.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp]
+    lib.upr_texture_workspace_bytes.restype = sz
+    lib.upr_texture_workspace_bytes.argtypes = [i32]
+    lib.upr_texture_workspace_init.restype = i32
+    lib.upr_texture_workspace_init.argtypes = [vp, sz, i32, vp]
+    lib.upr_texture_tv_f32.restype = i32
+    lib.upr_texture_tv_f32.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.upr_texture_edge_density_f32.restype = i32
+    lib.upr_texture_edge_density_f32.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.upr_dynamic_smooth_weight_f32.restype = i32
+    lib.upr_dynamic_smooth_weight_f32.argtypes = [vp, f32, vp, vp]
 
 
 def lib():
@@ -104,14 +142,16 @@ def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
 
 def release_workspaces() -> None:
     _workspaces.clear()
+    _zero_ws.clear()
 
 
 # ------------------------------------------------------------------------------------------------
 # a1: CLAHE in Lab
 # ------------------------------------------------------------------------------------------------
 def clahe_lab(x: torch.Tensor, clip_limit: float = 2.0, tiles: Tuple[int, int] = (8, 8),
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x: [N,3,H,W] f32 CUDA -> [N,3,H,W] f32 CUDA (upr_clahe_lab_f32)."""
+              out: Optional[torch.Tensor] = None, stage_mask: int = 3) -> torch.Tensor:
+    """x: [N,3,H,W] f32 CUDA -> [N,3,H,W] f32 CUDA (upr_clahe_lab_f32).  stage_mask != 3 is the profiling
+    hook upr_clahe_lab_stages_f32 (only meaningful right after a full call with the same arguments)."""
     x = _require_cuda_f32(x, "x")
     if x.dim() != 4 or x.shape[1] != 3:
         raise ValueError(f"expected [N,3,H,W], got {tuple(x.shape)}")
@@ -127,8 +167,13 @@ def clahe_lab(x: torch.Tensor, clip_limit: float = 2.0, tiles: Tuple[int, int] =
         if nbytes == 0:
             raise UprError(-2, "upr_clahe_workspace_bytes")
         ws = workspace(nbytes, x.device)
-        check(L.upr_clahe_lab_f32(x.data_ptr(), out.data_ptr(), n, h, w, float(clip_limit), tx, ty,
-                                  ws.data_ptr(), ws.numel(), _stream()), "upr_clahe_lab_f32")
+        if stage_mask == 3:
+            check(L.upr_clahe_lab_f32(x.data_ptr(), out.data_ptr(), n, h, w, float(clip_limit), tx, ty,
+                                      ws.data_ptr(), ws.numel(), _stream()), "upr_clahe_lab_f32")
+        else:
+            check(L.upr_clahe_lab_stages_f32(x.data_ptr(), out.data_ptr(), n, h, w, float(clip_limit), tx, ty,
+                                             ws.data_ptr(), ws.numel(), int(stage_mask), _stream()),
+                  "upr_clahe_lab_stages_f32")
     return out
 
 
@@ -155,3 +200,209 @@ def tables():
     check(lib().upr_get_tables(g.ctypes.data, c.ctypes.data, yf.ctypes.data, ig.ctypes.data), "upr_get_tables")
     return {"gamma": g, "cbrt": c, "ify": (yf & 0xFFFF).astype(np.uint16), "y": (yf >> 16).astype(np.uint16),
             "invgamma": ig}
+
+
+def clahe_lab_host(x: torch.Tensor, clip_limit: float = 2.0, tiles: Tuple[int, int] = (8, 8),
+                   out: Optional[torch.Tensor] = None, frames_per_chunk: int = 0) -> torch.Tensor:
+    """x: [N,3,H,W] f32 HOST tensor -> [N,3,H,W] f32 HOST (pinned) tensor (upr_clahe_lab_f32_host).
+
+    H2D, kernels and D2H are pipelined inside the library; pin ``x`` for full PCIe speed."""
+    if x.is_cuda or x.dtype != torch.float32:
+        raise TypeError("clahe_lab_host expects a float32 host tensor")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"expected [N,3,H,W], got {tuple(x.shape)}")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: upretinex-b200 has no CPU path")
+    x = x.contiguous()
+    n, _, h, w = x.shape
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+    elif out.is_cuda or out.shape != x.shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 host tensor shaped like x")
+    check(lib().upr_clahe_lab_f32_host(x.data_ptr(), out.data_ptr(), n, h, w, float(clip_limit), int(tiles[0]),
+                                       int(tiles[1]), int(frames_per_chunk)), "upr_clahe_lab_f32_host")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a3: brightness histogram
+# ------------------------------------------------------------------------------------------------
+def brightness_hist(x: torch.Tensor) -> torch.Tensor:
+    """x: [N,3,H,W] f32 CUDA -> [N,256] int32 CUDA histogram of the u8 gray image."""
+    x = _require_cuda_f32(x, "x")
+    n, c, h, w = x.shape
+    if c != 3:
+        raise ValueError("expected 3 channels")
+    hist = torch.empty((n, 256), dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().upr_brightness_hist_f32(x.data_ptr(), n, h, w, hist.data_ptr(), _stream()), "upr_brightness_hist_f32")
+    return hist
+
+
+# ------------------------------------------------------------------------------------------------
+# a4/a5: multi-scale statistics
+# ------------------------------------------------------------------------------------------------
+def multiscale_stats(x: torch.Tensor, force_generic: bool = False):
+    """x: [N,3,H,W] -> (means [N,3] f32, gain [N] f32), both on the device (no host sync)."""
+    x = _require_cuda_f32(x, "x")
+    n, c, h, w = x.shape
+    if c != 3:
+        raise ValueError("expected 3 channels")
+    if int(h * 0.25) < 1 or int(w * 0.25) < 1:
+        raise ValueError("image too small for the 1/4 scale")
+    means = torch.empty((n, 3), dtype=torch.float32, device=x.device)
+    gain = torch.empty((n,), dtype=torch.float32, device=x.device)
+    L = lib()
+    with torch.cuda.device(x.device):
+        ws = zero_workspace("ms", L.upr_multiscale_workspace_bytes(n, h, w), x.device)
+        check(L.upr_multiscale_stats_f32(x.data_ptr(), n, h, w, means.data_ptr(), gain.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), 1 if force_generic else 0, _stream()), "upr_multiscale_stats_f32")
+    return means, gain
+
+
+def multiscale_features(x: torch.Tensor):
+    """x: [N,3,H,W] -> ([N,7,H,W], [N,7,H/2,W/2], [N,7,H/4,W/4], means [N,3], gain [N])."""
+    x = _require_cuda_f32(x, "x")
+    n, c, h, w = x.shape
+    if c != 3:
+        raise ValueError("expected 3 channels")
+    h2, w2, h4, w4 = int(h * 0.5), int(w * 0.5), int(h * 0.25), int(w * 0.25)
+    if h4 < 1 or w4 < 1:
+        raise ValueError("image too small for the 1/4 scale")
+    f1 = torch.empty((n, 7, h, w), dtype=torch.float32, device=x.device)
+    f2 = torch.empty((n, 7, h2, w2), dtype=torch.float32, device=x.device)
+    f3 = torch.empty((n, 7, h4, w4), dtype=torch.float32, device=x.device)
+    means = torch.empty((n, 3), dtype=torch.float32, device=x.device)
+    gain = torch.empty((n,), dtype=torch.float32, device=x.device)
+    L = lib()
+    with torch.cuda.device(x.device):
+        ws = zero_workspace("ms", L.upr_multiscale_workspace_bytes(n, h, w), x.device)
+        check(L.upr_multiscale_features_f32(x.data_ptr(), n, h, w, f1.data_ptr(), f2.data_ptr(), f3.data_ptr(),
+                                            means.data_ptr(), gain.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+              "upr_multiscale_features_f32")
+    return f1, f2, f3, means, gain
+
+
+def scale_clamp(enh: torch.Tensor, gain: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """clamp(enh * gain[image], 0, 1); enh [N,C,H,W], gain [N] f32 on the same device."""
+    enh = _require_cuda_f32(enh, "enh")
+    gain = _require_cuda_f32(gain, "gain").reshape(-1)
+    n, c, h, w = enh.shape
+    if gain.numel() != n:
+        raise ValueError("gain must have one entry per image")
+    out = torch.empty_like(enh) if out is None else out
+    with torch.cuda.device(enh.device):
+        check(lib().upr_scale_clamp_f32(enh.data_ptr(), gain.data_ptr(), out.data_ptr(), n, c, h, w, _stream()),
+              "upr_scale_clamp_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a6/a7: saliency / attention
+# ------------------------------------------------------------------------------------------------
+def _sal(fn_name: str, x: torch.Tensor) -> torch.Tensor:
+    x = _require_cuda_f32(x, "x")
+    n, c, h, w = x.shape
+    if c != 3:
+        raise ValueError("expected 3 channels")
+    out = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
+    L = lib()
+    with torch.cuda.device(x.device):
+        ws = workspace(L.upr_saliency_workspace_bytes(n, h, w), x.device)
+        check(getattr(L, fn_name)(x.data_ptr(), n, h, w, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), fn_name)
+    return out
+
+
+def saliency(x: torch.Tensor) -> torch.Tensor:
+    return _sal("upr_saliency_f32", x)
+
+
+def attention(x: torch.Tensor) -> torch.Tensor:
+    return _sal("upr_attention_f32", x)
+
+
+def attention_apply(enh: torch.Tensor, att: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    enh = _require_cuda_f32(enh, "enh")
+    att = _require_cuda_f32(att, "att")
+    n, c, h, w = enh.shape
+    if att.numel() != n * h * w:
+        raise ValueError("att must be [N,1,H,W]")
+    out = torch.empty_like(enh) if out is None else out
+    with torch.cuda.device(enh.device):
+        check(lib().upr_attention_apply_f32(enh.data_ptr(), att.data_ptr(), out.data_ptr(), n, c, h, w, _stream()),
+              "upr_attention_apply_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a8: Retinex decomposition / recombination
+# ------------------------------------------------------------------------------------------------
+def retinex_recombine(x: torch.Tensor, illu: torch.Tensor, e: torch.Tensor, want_reflectance: bool = True,
+                      eps: float = 1e-6):
+    """(reflectance | None, enhanced) for x,e [N,3,H,W] and illu [N,1,H,W]."""
+    x = _require_cuda_f32(x, "x"); illu = _require_cuda_f32(illu, "illu"); e = _require_cuda_f32(e, "e")
+    n, c, h, w = x.shape
+    if c != 3 or e.shape != x.shape or illu.numel() != n * h * w:
+        raise ValueError("expected x,e [N,3,H,W] and illu [N,1,H,W]")
+    refl = torch.empty_like(x) if want_reflectance else None
+    enh = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().upr_retinex_recombine_f32(x.data_ptr(), illu.data_ptr(), e.data_ptr(),
+                                              refl.data_ptr() if refl is not None else None, enh.data_ptr(), n, h, w,
+                                              float(eps), _stream()), "upr_retinex_recombine_f32")
+    return refl, enh
+
+
+def retinex_decompose(x: torch.Tensor, illu: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    x = _require_cuda_f32(x, "x"); illu = _require_cuda_f32(illu, "illu")
+    n, c, h, w = x.shape
+    if c != 3 or illu.numel() != n * h * w:
+        raise ValueError("expected x [N,3,H,W] and illu [N,1,H,W]")
+    refl = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().upr_retinex_decompose_f32(x.data_ptr(), illu.data_ptr(), refl.data_ptr(), n, h, w, float(eps), _stream()),
+              "upr_retinex_decompose_f32")
+    return refl
+
+
+# ------------------------------------------------------------------------------------------------
+# a9/a10: texture complexity, dynamic smoothness weight
+# ------------------------------------------------------------------------------------------------
+_zero_ws = {}
+
+
+def zero_workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
+    """Workspace that is zero-filled when (re)allocated; the ticket kernels leave it clean."""
+    key = (tag, device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _zero_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _zero_ws[key] = ws
+    return ws
+
+
+def texture_complexity(x: torch.Tensor, method: str = "tv", want_batch_stats: bool = False):
+    """x: [B,C,H,W] f32 CUDA -> per-image complexity [B] (and [sum, B] if want_batch_stats)."""
+    if method not in ("tv", "edge_density"):
+        raise ValueError(f"unsupported texture complexity method: {method}")
+    x = _require_cuda_f32(x, "x")
+    b, c, h, w = x.shape
+    out = torch.empty((b,), dtype=torch.float32, device=x.device)
+    stats = torch.empty((2,), dtype=torch.float32, device=x.device) if want_batch_stats else None
+    L = lib()
+    fn = L.upr_texture_tv_f32 if method == "tv" else L.upr_texture_edge_density_f32
+    with torch.cuda.device(x.device):
+        ws = zero_workspace("tex", L.upr_texture_workspace_bytes(b), x.device)
+        check(fn(x.data_ptr(), b, c, h, w, out.data_ptr(), stats.data_ptr() if stats is not None else None,
+                 ws.data_ptr(), ws.numel(), _stream()), f"upr_texture_{method}_f32")
+    return (out, stats) if want_batch_stats else out
+
+
+def dynamic_smooth_weight(batch_stats2: torch.Tensor, weight_smooth: float = 1.0) -> torch.Tensor:
+    """0-dim f32 CUDA tensor: clamp(w0 * (1 - 0.8 * stats[0]/stats[1]), 0.1, 5.0)."""
+    s = _require_cuda_f32(batch_stats2, "batch_stats2")
+    out = torch.empty((), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        check(lib().upr_dynamic_smooth_weight_f32(s.data_ptr(), float(weight_smooth), out.data_ptr(), _stream()),
+              "upr_dynamic_smooth_weight_f32")
+    return out

@@ -156,3 +156,14 @@ def test_golden_texture(golden):
         n = rec["shape"][2] * rec["shape"][3]
         assert np.abs(ed - np.array(rec["edge_density"])).max() <= 4.0 / n
         assert abs(O.dynamic_smooth_weight(tv) - rec["w_tv"]) <= 1e-6
+
+
+def test_cv2_chain_matches_oracle():
+    """bench.py's CPU arm (oracle/cv2_chain.py, the reference's own cv2 call sequence) == the C oracle."""
+    from oracle import cv2_chain
+    for seed, (h, w), kind in [(2, (400, 600), "dark"), (7, (403, 601), "uniform"), (9, (270, 480), "ramp")]:
+        x = O.kat_input(seed, h, w, kind)
+        assert np.array_equal(np.ascontiguousarray(cv2_chain.clahe_lab_frame(x[0])), O.clahe_lab(x)[0])
+    xs = np.concatenate([O.kat_input(40 + i, 64, 96, "uniform") for i in range(4)])
+    for got, x in zip(cv2_chain.clahe_lab_batch(xs, workers=3), xs):
+        assert np.array_equal(np.ascontiguousarray(got), O.clahe_lab(x)[0])
