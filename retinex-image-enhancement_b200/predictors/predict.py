@@ -1,0 +1,88 @@
+"""Drop-in for the reference's ``predictors/predict.py`` inference drivers (:144-235) and CLI (:238-310).
+
+The reference unpacks two values from a model that returns three (predict.py:163 vs models/model.py:455) and
+raises ``ValueError``; this module unpacks ``(enhanced, reflectance, illu)``.  Output names and flags are the
+reference's: ``--checkpoint --input --output --max_size --no_comparison --device``.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import time
+
+import numpy as np
+import torch
+
+from ..enhancers.simple_enhance import _to_u8_hwc, list_images, load_image, save_image, shard_for_rank
+from ..models.model import UP_Retinex
+
+
+def create_comparison(img_low, img_enhanced, illu_map, save_path):
+    """Three-panel strip input | enhanced | illumination (predict.py:100-141)."""
+    from PIL import Image
+    Image.fromarray(np.concatenate([_to_u8_hwc(img_low), _to_u8_hwc(img_enhanced), _to_u8_hwc(illu_map)], axis=1)).save(save_path)
+    print(f"Saved comparison: {save_path}")
+
+
+def predict_single_image(model, image_path, output_dir, device, max_size=None, save_comparison=True):
+    img_low, _ = load_image(image_path, max_size)
+    img_low = img_low.to(device)
+    start = time.time()
+    with torch.no_grad():
+        img_enhanced, _reflectance, illu_map = model(img_low)
+    if img_enhanced.is_cuda:
+        torch.cuda.synchronize(img_enhanced.device)
+    print(f"Inference time: {time.time() - start:.4f}s")
+    os.makedirs(output_dir, exist_ok=True)
+    stem = os.path.splitext(os.path.basename(image_path))[0]
+    save_image(img_enhanced, os.path.join(output_dir, f"{stem}_enhanced.png"))
+    save_image(illu_map, os.path.join(output_dir, f"{stem}_illumination.png"))
+    if save_comparison:
+        create_comparison(img_low, img_enhanced, illu_map, os.path.join(output_dir, f"{stem}_comparison.png"))
+
+
+def predict_batch(model, input_dir, output_dir, device, max_size=None, save_comparison=True):
+    files = [f for f in list_images(input_dir) if os.path.splitext(f)[1].lower() in {".jpg", ".jpeg", ".png", ".bmp"}]
+    if not files:
+        print(f"No images found in {input_dir}")
+        return
+    mine = shard_for_rank(files)
+    print(f"Found {len(files)} images ({len(mine)} on this rank)")
+    t0 = time.time()
+    for i, path in enumerate(mine, 1):
+        print(f"Processing [{i}/{len(mine)}]: {os.path.basename(path)}")
+        predict_single_image(model, path, output_dir, device, max_size, save_comparison)
+    total = time.time() - t0
+    print(f"Total images processed: {len(mine)}\nTotal time: {total:.2f}s")
+    if mine:
+        print(f"Average time per image: {total / len(mine):.4f}s")
+
+
+def load_checkpoint(model, checkpoint_path, device):
+    """trainers/train.py:165-186 format: {'epoch', 'model_state_dict', 'optimizer_state_dict'}."""
+    ckpt = torch.load(checkpoint_path, map_location=device)
+    model.load_state_dict(ckpt["model_state_dict"] if "model_state_dict" in ckpt else ckpt)
+    return model
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser(description="UP-Retinex Inference")
+    p.add_argument("--checkpoint", type=str, default=None)
+    p.add_argument("--input", type=str, required=True)
+    p.add_argument("--output", type=str, default="./results")
+    p.add_argument("--max_size", type=int, default=None)
+    p.add_argument("--no_comparison", action="store_true")
+    p.add_argument("--device", type=str, default=None)
+    args = p.parse_args(argv)
+    device = args.device or ("cuda" if torch.cuda.is_available() else "cpu")
+    model = UP_Retinex().to(device).eval()
+    if args.checkpoint:
+        load_checkpoint(model, args.checkpoint, device)
+    if os.path.isdir(args.input):
+        predict_batch(model, args.input, args.output, device, args.max_size, not args.no_comparison)
+    else:
+        predict_single_image(model, args.input, args.output, device, args.max_size, not args.no_comparison)
+
+
+if __name__ == "__main__":
+    main()

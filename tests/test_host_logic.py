@@ -1,0 +1,119 @@
+"""CPU-only checks of the host-side logic: histogram features, sharding, letterbox boundary, CLI flags, the model
+contract and the world_size-2 data-parallel batch statistics (gloo)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+
+def test_features_from_histogram_match_oracle():
+    from retinex_image_enhancement_b200.enhancers._stats import features_from_histogram
+    x = O.kat_input(2, 400, 600, "dark")
+    h = O.brightness_hist(x)
+    got = features_from_histogram(h.astype(np.int64))[0]
+    ref = O.features_from_hist(h)
+    assert got == ref
+
+
+def test_adjust_rules_match_oracle(golden):
+    from retinex_image_enhancement_b200.enhancers._stats import features_from_histogram
+    from retinex_image_enhancement_b200.enhancers.adaptive_params import AdaptiveParameterAdjuster
+    adj = AdaptiveParameterAdjuster()
+    for rec in golden["bright"]:
+        x = O.kat_input(rec["seed"], rec["h"], rec["w"], rec["kind"])
+        f = features_from_histogram(O.brightness_hist(x).astype(np.int64))[0]
+        assert adj._rules(f) == rec["params"]
+
+
+@pytest.mark.parametrize("n,world", [(10, 4), (3, 8), (64, 8), (0, 2), (7, 1)])
+def test_shard_for_rank_partitions(n, world):
+    from retinex_image_enhancement_b200.enhancers.simple_enhance import shard_for_rank
+    items = list(range(n))
+    parts = [shard_for_rank(items, r, world) for r in range(world)]
+    assert sum(parts, []) == items                       # contiguous blocks, every frame exactly once
+    assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_letterbox_identity_and_resize():
+    cv2 = pytest.importorskip("cv2")
+    from retinex_image_enhancement_b200.utils.letterbox import letterbox_tensor
+    rng = np.random.default_rng(3)
+    u8 = rng.integers(0, 256, (3, 50, 70), dtype=np.uint8)
+    t = torch.from_numpy(u8.astype(np.float32) / 255.0)
+    same, ratio, pad = letterbox_tensor(t, new_shape=(50, 70), auto=True, scaleup=False)
+    assert torch.equal(same, t) and ratio == (1.0, 1.0) and pad == (0.0, 0.0)
+    small, ratio, pad = letterbox_tensor(t, new_shape=32, auto=True, scaleup=False)
+    r = min(32 / 50, 32 / 70)
+    unpad = (int(round(70 * r)), int(round(50 * r)))
+    ref = cv2.resize(u8.transpose(1, 2, 0), unpad, interpolation=cv2.INTER_LINEAR)
+    dh = ((32 - unpad[1]) % 32) / 2
+    ref = cv2.copyMakeBorder(ref, int(round(dh - 0.1)), int(round(dh + 0.1)), 0, 0, cv2.BORDER_CONSTANT, value=(114, 114, 114))
+    assert np.array_equal((small.numpy().transpose(1, 2, 0) * 255).round().astype(np.uint8), ref)
+
+
+def test_cli_flags_of_the_reference_are_accepted():
+    from retinex_image_enhancement_b200.cli import build_main_parser
+    a, unknown = build_main_parser().parse_known_args(
+        ["--mode", "enhance", "--input_path", "d", "--output_dir", "o", "--max_size", "512", "--device", "cuda", "--multi_scale",
+         "--content_aware", "--use_preact", "--use_aspp", "--batch_size", "8"])
+    assert a.mode == "enhance" and a.multi_scale and a.content_aware and a.max_size == 512 and unknown == ["--batch_size", "8"]
+
+
+def test_model_contract_training_path_on_cpu():
+    from retinex_image_enhancement_b200.models.model import UP_Retinex, retinex_recombine
+    m = UP_Retinex(use_preact=False, use_aspp=False)
+    x = torch.rand(2, 3, 32, 48)
+    enhanced, reflectance, illu = m(x)                      # autograd enabled: stock torch ops
+    assert enhanced.shape == x.shape and reflectance.shape == x.shape and illu.shape == (2, 1, 32, 48)
+    enhanced.mean().backward()
+    assert m.output_layer.weight.grad is not None
+    with torch.no_grad(), pytest.raises(RuntimeError):      # inference needs the CUDA kernel: no CPU path
+        retinex_recombine(x, illu.detach(), x)
+
+
+def test_hot_path_ops_refuse_cpu_tensors():
+    from retinex_image_enhancement_b200 import native
+    x = torch.rand(1, 3, 16, 16)
+    for fn in (native.clahe_lab, native.brightness_hist, native.multiscale_stats, native.saliency, native.attention,
+               native.texture_complexity):
+        with pytest.raises(RuntimeError):
+            fn(x)
+
+
+# ---- world_size 2 over gloo: the batch statistics of the dynamic smoothness weight -------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _dp_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from oracle import oracle as Or
+    from retinex_image_enhancement_b200.enhancers.simple_enhance import shard_for_rank
+    from retinex_image_enhancement_b200.losses.loss import all_reduce_batch_stats, weight_from_stats
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = np.random.default_rng(11).random((8, 3, 64, 64), dtype=np.float32)
+    mine = shard_for_rank(list(range(8)))                       # env-driven sharding
+    local = Or.texture_tv(full[mine])                             # stand-in for the per-rank CUDA kernel
+    stats = torch.tensor([np.float32(local.sum(dtype=np.float32)), float(len(mine))], dtype=torch.float32)
+    all_reduce_batch_stats(stats)
+    w = weight_from_stats(stats, 1.0)
+    np.save(os.path.join(out_dir, f"w{rank}.npy"), np.array([float(w), float(stats[0]), float(stats[1])]))
+    dist.destroy_process_group()
+
+
+def test_dp_batch_stats_world2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    full = np.random.default_rng(11).random((8, 3, 64, 64), dtype=np.float32)
+    ref = O.dynamic_smooth_weight(O.texture_tv(full))
+    r0, r1 = np.load(tmp_path / "w0.npy"), np.load(tmp_path / "w1.npy")
+    assert np.array_equal(r0, r1)                                # every rank derives the same weight
+    assert r0[2] == 8.0 and abs(r0[0] - ref) <= 1e-6
