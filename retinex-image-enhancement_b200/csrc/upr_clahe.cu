@@ -22,6 +22,7 @@
 // cannot contract them into FMAs: OpenCV evaluates them separately rounded (SURVEY finding 9).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "upr_common.cuh"
@@ -426,6 +427,196 @@ k_map_vec(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, fl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K3 fast path, second generation ("instruction diet", profiles/r1_clahe_full.md showed the first one issue-bound
+// at 94 SASS instructions per pixel):
+//   * clamp(v, 0, 4095) is ONE VIMNMX.RELU (__vimin_s32_relu);
+//   * the rounded L' is never masked/shifted: the fp32 magic-add leaves 0x4B400000 + L' in the register and the
+//     constant folds into the table address;
+//   * abToXZ selects with a predicated add instead of SEL and keeps the exact truncating division;
+//   * two of the four LUT bytes are converted by the conversion pipe (I2F.U8 with a byte selector, 1 instruction),
+//     two by PRMT+FADD on the ALU/FMA pipes, so neither pipe carries all four;
+//   * 32-bit element indices against per-plane base pointers (one IMAD.WIDE per access instead of 64-bit adds);
+//   * plain streaming cache operators (ld.global.nc / st.global.cs): no createpolicy register to shuttle through
+//     the uniform datapath on every access.
+// The arithmetic is exactly that of k_map_vec (Appendix A.2/A.3), hence bit-identical output.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint8_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_cs_f4(float* p, float a, float b, float c, float d)
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Pipe budget notes (ncu, profiles/r1_clahe_full.md): the first-generation kernel was bound by the 16-lane ALU
+// pipe (72 % busy: SHF/LOP3/LEA/IADD3/PRMT/VIMNMX/ISETP) while the FMA pipe idled at 36 % and the conversion
+// pipe at 1 %.  Hence: table records with a 12-byte stride (address = index*12 + base is an IMAD, not a LEA),
+// unpacked {quad, A, y} records (no LOP/SHF to split a packed word), all four LUT bytes converted by I2F.U8,
+// shift+add pairs expressed so that they become one LEA.HI.SX32, and IMAD.WIDE global addressing.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32_off(uint32_t addr, int off)
+{
+    int v;
+    if (off == 4) asm("ld.shared.s32 %0, [%1+4];" : "=r"(v) : "r"(addr));
+    else asm("ld.shared.s32 %0, [%1+8];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// base + idx*scale as ONE IMAD.WIDE on the FMA pipe.  `scale` is a run-time register (4 or 16 plus blockIdx.z == 0):
+// with an immediate power of two ptxas lowers the same PTX to LEA + LEA.HI.X, two instructions on the ALU pipe,
+// which is the pipe these kernels saturate.
+__device__ __forceinline__ const void* wide_addr(const void* base, uint32_t idx, uint32_t scale)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "r"(scale), "l"(base));
+    return reinterpret_cast<const void*>(r);
+}
+
+// abToXZ (Appendix A.2): i <= 3390 ? trunc(i*108/841) - 290 : ((i*i >> 14) * i) >> 14
+__device__ __forceinline__ int ab_to_xz2(int i)
+{
+    const int lin = i * 108 / 841 - 290;
+    const int cub = (((i * i) >> 14) * i) >> 14;
+    return i <= 3390 ? lin : cub;
+}
+
+constexpr int kRecStride = 12;   // bytes per grey-level record {quad u32, A s32, y s32}
+
+struct MapTables {
+    uint32_t four;     // 4, opaque to ptxas (see wide_addr)
+    uint32_t rec;      // shared address of the record table
+    uint32_t rec_lp;   // rec - 0x4B400000*12 (mod 2^32): record address of L' straight from the magic-add bits
+    uint32_t outf;     // shared address of float[4096] invgamma[c] / 255.f
+};
+
+__device__ __forceinline__ void map_pixel(uint32_t Lv, int av, int bv, float xa, float xa1, float ya, float ya1,
+                                          const MapTables& t, float& r, float& g, float& b)
+{
+    const uint32_t q = lds_u32(Lv * kRecStride + t.rec);
+    const float l11 = float(q & 0xffu), l12 = float((q >> 8) & 0xffu), l21 = float((q >> 16) & 0xffu), l22 = float(q >> 24);
+    const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+    const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+    // rint via 1.5*2^23 (round-half-even == cvRound); 0 <= res < 255.5, so the sum's bits are 0x4B400000 + L'
+    const uint32_t ra = __float_as_uint(__fadd_rn(res, 12582912.0f)) * kRecStride + t.rec_lp;
+    const int A = lds_s32_off(ra, 4);    // ify(L') - 4194
+    const int y = lds_s32_off(ra, 8);
+    // ix = ify + adiv(a);  iz = ify - bdiv(b) = A + 14678 - ((b*41943+16) >> 9)  with  -(t >> 9) == (511 - t) >> 9
+    const int x = ab_to_xz2(A + ((av * 268435 + 128) >> 13));
+    const int z = ab_to_xz2(A + ((bv * -41943 + (495 + 14678 * 512)) >> 9));
+    const int ro = __vimin_s32_relu((12615 * x - 6296 * y - 2223 * z + 8192) >> 14, 4095);
+    const int go = __vimin_s32_relu((-3773 * x + 7684 * y + 185 * z + 8192) >> 14, 4095);
+    const int bo = __vimin_s32_relu((217 * x - 836 * y + 4715 * z + 8192) >> 14, 4095);
+    r = lds_f32(uint32_t(ro) * t.four + t.outf);
+    g = lds_f32(uint32_t(go) * t.four + t.outf);
+    b = lds_f32(uint32_t(bo) * t.four + t.outf);
+}
+
+__global__ void __launch_bounds__(kK3Threads, 4)
+k_map_vec2(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out, const MapGeom g)
+{
+    __shared__ __align__(16) uint32_t s_rec[256 * kRecStride / 4];
+    __shared__ __align__(16) float s_outf[4096];
+
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x % g.nstrips;
+    const int cell = blockIdx.x / g.nstrips;
+    const int cy = cell / (g.tiles_x + 1), cx = cell - cy * (g.tiles_x + 1);
+    const int f = blockIdx.y;
+
+    const int x0 = g.bx[cx], x1 = g.bx[cx + 1];
+    const int rows_cell = g.by[cy + 1] - g.by[cy];
+    const int srows = (rows_cell + g.nstrips - 1) / g.nstrips;
+    const int y0 = g.by[cy] + strip * srows;
+    const int y1 = min(y0 + srows, g.by[cy + 1]);
+    if (x0 >= x1 || y0 >= y1) return;
+
+    {
+        const int ty1 = max(cy - 1, 0), ty2 = min(cy, g.tiles_y - 1);
+        const int tx1 = max(cx - 1, 0), tx2 = min(cx, g.tiles_x - 1);
+        const uint8_t* lf = lut_g + size_t(f) * g.tiles_x * g.tiles_y * 256 + tid;
+        const uint32_t yf = d_labyf[tid];
+        s_rec[tid * 3 + 0] = uint32_t(lf[(ty1 * g.tiles_x + tx1) * 256]) | (uint32_t(lf[(ty1 * g.tiles_x + tx2) * 256]) << 8) |
+                             (uint32_t(lf[(ty2 * g.tiles_x + tx1) * 256]) << 16) | (uint32_t(lf[(ty2 * g.tiles_x + tx2) * 256]) << 24);
+        s_rec[tid * 3 + 1] = uint32_t(int(yf & 0xffffu) - 4194);
+        s_rec[tid * 3 + 2] = yf >> 16;
+#pragma unroll
+        for (int i = 0; i < 4096 / 4 / kK3Threads; ++i)
+            reinterpret_cast<uint4*>(s_outf)[tid + i * kK3Threads] = reinterpret_cast<const uint4*>(d_outf_bits)[tid + i * kK3Threads];
+    }
+    __syncthreads();
+
+    MapTables t;
+    t.rec = uint32_t(__cvta_generic_to_shared(s_rec));
+    // + blockIdx.z (always 0): keeps the constant a run-time register value, so that the L' record address stays
+    // ONE IMAD (bits*12 + reg) instead of an IMAD plus one wide-immediate add per load
+    t.rec_lp = t.rec - 0x4B400000u * uint32_t(kRecStride) + blockIdx.z;
+    t.outf = uint32_t(__cvta_generic_to_shared(s_outf));
+    t.four = 4u + blockIdx.z;
+    const uint32_t sixteen = 16u + blockIdx.z;
+
+    // word (4 px) indices against per-plane bases: one IMAD.WIDE per access; fast path guarantees 3*plane < 2^32
+    const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;
+    const uint32_t* labL = reinterpret_cast<const uint32_t*>(lab) + size_t(f) * 3 * plane4;
+    float4* outR = reinterpret_cast<float4*>(out) + size_t(f) * 3 * plane4;
+    const float txbase = float(cx - 1), tybase = float(cy - 1);
+    const int cw4 = (x1 - x0) >> 2;
+    const uint32_t w4 = uint32_t(g.w) >> 2;
+
+    for (int xc = 0; xc < cw4; xc += kK3Threads) {
+        const int cwc = min(kK3Threads, cw4 - xc);
+        const int rpi = kK3Threads / cwc;  // rows per iteration
+        const int lr = tid / cwc, lc = tid - lr * cwc;
+        if (lr >= rpi) continue;
+        const int x = x0 + (xc + lc) * 4;
+        float xa[4], xa1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float txf = __fadd_rn(__fmul_rn(float(x + k), g.inv_tw), -0.5f);
+            xa[k] = __fsub_rn(txf, txbase);
+            xa1[k] = __fsub_rn(1.0f, xa[k]);
+        }
+        // three running word offsets (L/R, a/G, b/B planes) against ONE base each for lab and out: every access is a
+        // single IMAD.WIDE on the FMA pipe (distinct offset registers keep ptxas from splitting them into 64-bit adds)
+        // (the column goes into per-thread bases: a uniform base would be added with a separate 64-bit IADD3 pair)
+        const uint32_t* labC = labL + (uint32_t(x) >> 2);
+        float4* outC = outR + (uint32_t(x) >> 2);
+        uint32_t o0 = uint32_t(y0 + lr) * w4, o1 = o0 + plane4, o2 = o1 + plane4;
+        const uint32_t doff = uint32_t(rpi) * w4;
+        for (int y = y0 + lr; y < y1; y += rpi, o0 += doff, o1 += doff, o2 += doff) {
+            const uint32_t wl = __ldg(static_cast<const uint32_t*>(wide_addr(labC, o0, t.four)));
+            const uint32_t wa = __ldg(static_cast<const uint32_t*>(wide_addr(labC, o1, t.four)));
+            const uint32_t wb = __ldg(static_cast<const uint32_t*>(wide_addr(labC, o2, t.four)));
+            const float tyf = __fadd_rn(__fmul_rn(float(y), g.inv_th), -0.5f);
+            const float ya = __fsub_rn(tyf, tybase);
+            const float ya1 = __fsub_rn(1.0f, ya);
+            float o[3][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                map_pixel(__byte_perm(wl, 0u, 0x4440u | uint32_t(k)), int(__byte_perm(wa, 0u, 0x4440u | uint32_t(k))),
+                          int(__byte_perm(wb, 0u, 0x4440u | uint32_t(k))), xa[k], xa1[k], ya, ya1, t, o[0][k], o[1][k], o[2][k]);
+            __stcs(static_cast<float4*>(const_cast<void*>(wide_addr(outC, o0, sixteen))), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
+            __stcs(static_cast<float4*>(const_cast<void*>(wide_addr(outC, o1, sixteen))), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
+            __stcs(static_cast<float4*>(const_cast<void*>(wide_addr(outC, o2, sixteen))), make_float4(o[2][0], o[2][1], o[2][2], o[2][3]));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3 generic path: one thread per pixel, LUTs read through L1/L2.
 // ---------------------------------------------------------------------------------------------
@@ -498,6 +689,13 @@ static bool valid_shape(int n, int h, int w, int tiles_x, int tiles_y)
            size_t(h) * w <= (size_t(1) << 30);
 }
 
+// development switch (A/B timing on the GPU box): UPR_CLAHE_VARIANT bit 0 = first-generation K3, bit 1 = first-generation K1
+static int variant()
+{
+    static const int v = [] { const char* e = std::getenv("UPR_CLAHE_VARIANT"); return e ? std::atoi(e) : 0; }();
+    return v;
+}
+
 // raw tile coordinate of OpenCV's interpolation: floor(p * inv - 0.5f), fp32, separately rounded
 static inline int raw_tile(int p, float inv)
 {
@@ -538,7 +736,8 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
 
     // interpolation cell boundaries from the exact fp32 recipe (monotone in p)
     MapGeom m{};
-    bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && aligned16(in) && aligned16(out);
+    bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && aligned16(in) && aligned16(out) &&
+                size_t(h) * w * 3 < (size_t(1) << 32);
     if (fast) {
         m.n = n; m.h = h; m.w = w; m.tiles_x = tiles_x; m.tiles_y = tiles_y; m.inv_tw = inv_tw; m.inv_th = inv_th;
         int c = 0;
@@ -597,7 +796,10 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             ks = std::min(std::max(ks, want3), std::max(cell_rows / 4, 1));
             m.nstrips = ks;
             if (stage_mask & 2) {
-                k_map_vec<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
+                if (variant() & 1)
+                    k_map_vec<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
+                else
+                    k_map_vec2<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
                 UPR_LAUNCH_CHECK();
             }
         } else {
