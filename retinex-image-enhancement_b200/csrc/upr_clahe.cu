@@ -6,16 +6,16 @@
 //   -> LAB2BGR -> BGR2RGB -> /255
 // with two kernels per batch and a 3 B/px u8 Lab intermediate:
 //
-//   K1  k_hist_lab_*   one CTA per (frame, tile, row-strip): planar f32 RGB -> u8 quantise ->
-//                      OpenCV fixed-point Lab; stores L,a,b (u8 planes); per-THREAD private byte
-//                      counters in shared memory build the tile histogram without atomics
-//                      (shared atomics cost ~1-2 cycles/lane on this part: slower than the whole
-//                      budget of the kernel); the CTA (or the last strip CTA of the tile) then does
-//                      clip -> redistribute -> prefix scan -> LUT in place.
-//   K3  k_map_*        one CTA per (frame, interpolation cell, row-strip): the four tile LUTs that
-//                      surround a cell are interleaved into one 32-bit word per grey level, so the
-//                      bilinear LUT interpolation costs ONE shared-memory lookup per pixel; fused
-//                      with Lab -> sRGB (integer path) and the /255 de-quantisation.
+//   K1  k_hist_lab_vec2  one CTA per (frame, tile, row-strip): planar f32 RGB -> u8 quantise -> OpenCV fixed-point
+//                        Lab; stores L,a,b (u8 planes); per-THREAD private byte counters in shared memory build the
+//                        tile histogram without atomics; the CTA (or the last strip CTA of the tile) then does
+//                        clip -> redistribute -> prefix scan -> LUT in place.
+//   K3  k_map_vec5       persistent CTAs pulling (frame, interpolation cell, row-strip) items: the four tile LUTs
+//                        that surround a cell are interleaved into one 32-bit word per grey level, so the bilinear
+//                        LUT interpolation costs ONE shared-memory lookup per pixel; fused with Lab -> sRGB (integer
+//                        path) and the /255 de-quantisation.
+//   (k_hist_lab_vec / k_map_vec are the first generations, kept behind UPR_CLAHE_VARIANT for A/B timing;
+//    k_*_generic handle ragged shapes incl. OpenCV's padding quirk.)
 //
 // All fixed-point recipes follow SURVEY.md Appendix A (pinned against the cv2 binary by the
 // oracle tests).  fp32 products/sums of the interpolation use __fmul_rn/__fadd_rn so that ptxas
@@ -37,6 +37,7 @@ __device__ const uint16_t d_gamma[UPR_TAB_GAMMA_LEN] = UPR_TAB_GAMMA_INIT;
 __device__ const uint16_t d_cbrt[UPR_TAB_CBRT_LEN] = UPR_TAB_CBRT_INIT;
 __device__ const uint32_t d_labyf[UPR_TAB_LABYF_LEN] = UPR_TAB_LABYF_INIT;
 __device__ const uint32_t d_outf_bits[UPR_TAB_INVGAMMA_F32BITS_LEN] = UPR_TAB_INVGAMMA_F32BITS_INIT;
+__device__ __align__(16) const int16_t d_xzlin[UPR_TAB_XZLIN_LEN + 8] = UPR_TAB_XZLIN_INIT;   // padded to a multiple of 16 bytes
 
 static const uint16_t h_gamma[UPR_TAB_GAMMA_LEN] = UPR_TAB_GAMMA_INIT;
 static const uint16_t h_cbrt[UPR_TAB_CBRT_LEN] = UPR_TAB_CBRT_INIT;
@@ -65,6 +66,54 @@ struct MapGeom {
     int bx[kMaxTiles + 2];  // cell c covers x in [bx[c], bx[c+1]); raw tile index of the cell is c-1
     int by[kMaxTiles + 2];
 };
+
+// ---------------------------------------------------------------------------------------------
+// raw shared/global access helpers of the second-generation kernels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint8_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_cs_f4(float* p, float a, float b, float c, float d)
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Pipe budget notes (ncu, profiles/r1_clahe_full.md): the first-generation kernel was bound by the 16-lane ALU
+// pipe (72 % busy: SHF/LOP3/LEA/IADD3/PRMT/VIMNMX/ISETP) while the FMA pipe idled at 36 % and the conversion
+// pipe at 1 %.  Hence: table records with a 12-byte stride (address = index*12 + base is an IMAD, not a LEA),
+// unpacked {quad, A, y} records (no LOP/SHF to split a packed word), all four LUT bytes converted by I2F.U8,
+// shift+add pairs expressed so that they become one LEA.HI.SX32, and IMAD.WIDE global addressing.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32_off(uint32_t addr, int off)
+{
+    int v;
+    if (off == 4) asm("ld.shared.s32 %0, [%1+4];" : "=r"(v) : "r"(addr));
+    else asm("ld.shared.s32 %0, [%1+8];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// base + idx*scale as ONE IMAD.WIDE on the FMA pipe.  `scale` is a run-time register (4 or 16 plus blockIdx.z == 0):
+// with an immediate power of two ptxas lowers the same PTX to LEA + LEA.HI.X, two instructions on the ALU pipe,
+// which is the pipe these kernels saturate.
+__device__ __forceinline__ const void* wide_addr(const void* base, uint32_t idx, uint32_t scale)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "r"(scale), "l"(base));
+    return reinterpret_cast<const void*>(r);
+}
 
 // ---------------------------------------------------------------------------------------------
 // device arithmetic (Appendix A.1 / A.2)
@@ -282,6 +331,270 @@ k_hist_lab_vec(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t*
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1 fast path, second generation ("instruction diet": the first one ran 80 SASS instructions per pixel at 64 % issue
+// utilisation, and the ncu source view put 28 % of its stalls on the first use of loads issued only 0.6 iterations
+// ahead).  Same arithmetic (Appendix A.1), hence bit-identical Lab planes / histograms / LUTs:
+//   * quantisation on the FMA pipe: for 0 <= x <= 1 (checked once per 12 values with three-input integer maxima on
+//     the raw bit patterns) trunc(x*255) is the low mantissa of  RZ(x*255 + 2^23);  those bits times four plus a
+//     constant IS the shared address of the gamma entry.  Anything else (negative, > 1, NaN, inf) takes the exact
+//     general path (numpy's wrap-around semantics, see quantize_u8);
+//   * the gamma table is stored as fp32 and the three 3x3 dot products run as FFMA chains (every partial sum is an
+//     integer < 2^24, hence exact); floor(S / 4096) falls out of one more FFMA.RZ against 2^23, again as address bits;
+//   * L, a, b are produced pre-scaled so that the result sits in byte 2 of a register: one PRMT assembles a Lab word,
+//     no shifts, no masks;
+//   * the private-counter address ((L >> 2) << 10 | (L & 3)) is (L * 257) & 0xFC03: one IMAD, one LOP3 (which also ORs
+//     in the thread's column);
+//   * two explicit register sets: the twelve floats of item i+1 are in flight while item i is converted;
+//   * 32-bit item offsets against one base pointer per array (IMAD.WIDE), no L2 policy descriptors.
+// ---------------------------------------------------------------------------------------------
+// hides a value's provenance from ptxas (otherwise `bits*4 + (base - K)` is re-associated into two adds per use)
+__device__ __forceinline__ uint32_t opaque(uint32_t x)
+{
+    uint32_t y;
+    asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+// base + idx * K (K an immediate) as ONE IMAD.WIDE.U32 with a 64-bit addend: nothing 64-bit to keep live but the base
+template <uint32_t K>
+__device__ __forceinline__ const char* wide_imm(const char* base, uint32_t idx)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "n"(K), "l"(base));
+    return reinterpret_cast<const char*>(r);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void st_global_u32(const void* p, uint32_t v)
+{
+    // no "memory" clobber: the Lab words are never read back by the storing kernel, and a clobber would pin every
+    // shared-memory access of the surrounding code in program order
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v));
+}
+__device__ __forceinline__ float4 ld_nc_f4(const void* p)
+{
+    float4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+struct K1Tables {
+    uint32_t gam_q;    // &s_gammaf[0] - 4 * 0x4B000000: address of gamma[q] from the magic-add bits of q
+    uint32_t gam;      // &s_gammaf[0]
+    uint32_t cbr_q;    // &s_cbrt[0] - 2 * 0x4B000000
+    uint32_t four, sixteen;
+};
+
+// 12 floats (4 px x RGB) -> three Lab words + four counter increments
+__device__ __forceinline__ void k1_item(const float4 vr, const float4 vg, const float4 vb, const K1Tables& t,
+                                        unsigned char* s_cnt, uint32_t tid4, uint32_t& wl, uint32_t& wa, uint32_t& wb)
+{
+    const float pr[4] = {vr.x, vr.y, vr.z, vr.w};
+    const float pg[4] = {vg.x, vg.y, vg.z, vg.w};
+    const float pb[4] = {vb.x, vb.y, vb.z, vb.w};
+    uint32_t m0 = __vimax3_u32(__float_as_uint(pr[0]), __float_as_uint(pr[1]), __float_as_uint(pr[2]));
+    uint32_t m1 = __vimax3_u32(__float_as_uint(pr[3]), __float_as_uint(pg[0]), __float_as_uint(pg[1]));
+    uint32_t m2 = __vimax3_u32(__float_as_uint(pg[2]), __float_as_uint(pg[3]), __float_as_uint(pb[0]));
+    uint32_t m3 = __vimax3_u32(__float_as_uint(pb[1]), __float_as_uint(pb[2]), __float_as_uint(pb[3]));
+    m0 = __vimax3_u32(m0, m1, m2);
+    m0 = max(m0, m3);
+    float R[4], G[4], B[4];
+    if (m0 <= 0x3F800000u) {   // every value in [+0, 1]: as unsigned integers, positive floats order like their values
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            R[k] = lds_f32(__float_as_uint(__fadd_rz(__fmul_rn(pr[k], 255.0f), 8388608.0f)) * 4u + t.gam_q);
+            G[k] = lds_f32(__float_as_uint(__fadd_rz(__fmul_rn(pg[k], 255.0f), 8388608.0f)) * 4u + t.gam_q);
+            B[k] = lds_f32(__float_as_uint(__fadd_rz(__fmul_rn(pb[k], 255.0f), 8388608.0f)) * 4u + t.gam_q);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            R[k] = lds_f32(uint32_t(quantize_u8(pr[k])) * 4u + t.gam);
+            G[k] = lds_f32(uint32_t(quantize_u8(pg[k])) * 4u + t.gam);
+            B[k] = lds_f32(uint32_t(quantize_u8(pb[k])) * 4u + t.gam);
+        }
+    }
+    int vL[4], vA[4], vB[4], fY[4];
+    // Y first: L only needs fY, and the four dependent read-modify-writes of the private counters then overlap the
+    // X/Z arithmetic instead of trailing it
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // S = c0 R + c1 G + c2 B + 2048 is an exact integer < 2^24; RZ(S / 4096 + 2^23) carries floor(S / 4096)
+        const float sy = __fmaf_rn(B[k], 296.0f, __fmaf_rn(G[k], 2929.0f, __fmaf_rn(R[k], 871.0f, 2048.0f)));
+        fY[k] = int(lds_u16(__float_as_uint(__fmaf_rz(sy, 0.000244140625f, 8388608.0f)) * 2u + t.cbr_q));
+        // twice the Appendix A.1 expressions: the u8 result is byte 2 (L 0..255, a 42..226, b 20..223, never negative)
+        vL[k] = fY[k] * 592 - 2641100;                 // 2 * (296 fY - 1336934 + 16384)
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t L = uint32_t(vL[k]) >> 16;
+        unsigned char* c = s_cnt + (((L * 257u) & 0xFC03u) | tid4);   // bits 2..9 of the offset are the thread's column
+        *c = static_cast<unsigned char>(*c + 1);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float sx = __fmaf_rn(B[k], 778.0f, __fmaf_rn(G[k], 1541.0f, __fmaf_rn(R[k], 1777.0f, 2048.0f)));
+        const float sz = __fmaf_rn(B[k], 3575.0f, __fmaf_rn(G[k], 448.0f, __fmaf_rn(R[k], 73.0f, 2048.0f)));
+        const int fX = int(lds_u16(__float_as_uint(__fmaf_rz(sx, 0.000244140625f, 8388608.0f)) * 2u + t.cbr_q));
+        const int fZ = int(lds_u16(__float_as_uint(__fmaf_rz(sz, 0.000244140625f, 8388608.0f)) * 2u + t.cbr_q));
+        vA[k] = (fX - fY[k]) * 1000 + 8421376;         // 2 * (500 (fX - fY) + 128 * 32768 + 16384)
+        vB[k] = (fY[k] - fZ) * 400 + 8421376;
+    }
+    wl = __byte_perm(__byte_perm(uint32_t(vL[0]), uint32_t(vL[1]), 0x0062), __byte_perm(uint32_t(vL[2]), uint32_t(vL[3]), 0x0062), 0x5410);
+    wa = __byte_perm(__byte_perm(uint32_t(vA[0]), uint32_t(vA[1]), 0x0062), __byte_perm(uint32_t(vA[2]), uint32_t(vA[3]), 0x0062), 0x5410);
+    wb = __byte_perm(__byte_perm(uint32_t(vB[0]), uint32_t(vB[1]), 0x0062), __byte_perm(uint32_t(vB[2]), uint32_t(vB[3]), 0x0062), 0x5410);
+}
+
+__global__ void __launch_bounds__(kK1Threads, 3)
+k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
+                uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
+    float* s_gammaf = reinterpret_cast<float*>(smem + 256 * kK1Threads);           // 256 x f32
+    uint16_t* s_cbrt = reinterpret_cast<uint16_t*>(s_gammaf + UPR_TAB_GAMMA_LEN);  // 2048 x u16
+    __shared__ int s_tmp[8];
+    __shared__ int s_flag;
+
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x % g.nstrips;
+    const int tile = blockIdx.x / g.nstrips;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int f = blockIdx.y;
+    const int ntiles = g.tiles_x * g.tiles_y;
+
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cnt);
+#pragma unroll
+        for (int i = 0; i < 256 * kK1Threads / 16 / kK1Threads; ++i) z[tid + i * kK1Threads] = make_uint4(0, 0, 0, 0);
+        s_gammaf[tid] = float(d_gamma[tid]);
+        reinterpret_cast<uint4*>(s_cbrt)[tid] = reinterpret_cast<const uint4*>(d_cbrt)[tid];  // 256 x 16 B = 4 KB
+    }
+    __syncthreads();
+
+    const uint32_t zero = blockIdx.z;  // always 0: keeps the constants below in registers (see wide_addr)
+    K1Tables t;
+    t.gam = uint32_t(__cvta_generic_to_shared(s_gammaf));
+    t.gam_q = opaque(t.gam - 4u * 0x4B000000u);
+    t.cbr_q = opaque(uint32_t(__cvta_generic_to_shared(s_cbrt)) - 2u * 0x4B000000u);
+    t.four = opaque(4u + zero);
+    t.sixteen = opaque(16u + zero);
+
+    const int row0 = ty * g.th + strip * g.strip_rows;
+    const int row1 = min(row0 + g.strip_rows, (ty + 1) * g.th);
+    const int tw4 = g.tw >> 2;
+    const int nitems = max(row1 - row0, 0) * tw4;
+    const uint32_t w4 = uint32_t(g.w) >> 2;
+    const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;      // fast path: 3 * plane < 2^32
+    // item offsets count 4-pixel groups: a float4 of the input and a u32 word of the Lab planes share the same index
+    const float4* inT = reinterpret_cast<const float4*>(in) + size_t(f) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
+    uint32_t* labT = reinterpret_cast<uint32_t*>(lab) + size_t(f) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
+
+    const int dr = kK1Threads / tw4, dc = kK1Threads - dr * tw4;
+    const uint32_t dstep = uint32_t(dr) * w4 + uint32_t(dc), dwrap = w4 - uint32_t(tw4);
+    int c = tid % tw4;
+    // running 64-bit pointers (R plane of the input, L plane of the Lab intermediate); the other two planes are one
+    // 64-bit add away.  (IMAD.WIDE with a register multiplier is split by ptxas into IMAD.WIDE + a 64-bit add: 3 per
+    // address instead of 2.)
+    const char* pin = reinterpret_cast<const char*>(inT + (uint32_t(tid / tw4) * w4 + uint32_t(c)));
+    char* plab = reinterpret_cast<char*>(labT + (uint32_t(tid / tw4) * w4 + uint32_t(c)));
+    const uint32_t tid4 = uint32_t(tid) * 4u;
+
+    auto load = [&](const char* p, float4& r, float4& gch, float4& b) {
+        r = ld_nc_f4(p);
+        gch = ld_nc_f4(wide_imm<16>(p, plane4));
+        b = ld_nc_f4(wide_imm<32>(p, plane4));
+    };
+    auto store = [&](char* p, uint32_t wl, uint32_t wa, uint32_t wb) {
+        st_global_u32(p, wl);
+        st_global_u32(wide_imm<4>(p, plane4), wa);
+        st_global_u32(wide_imm<8>(p, plane4), wb);
+    };
+    // item i -> item i + 256 of the (rows x tw4) strip: returns the step in 4-pixel groups
+    auto advance = [&](int& cc) -> uint32_t {
+        cc += dc;
+        uint32_t st = dstep;
+        if (cc >= tw4) { cc -= tw4; st += dwrap; }
+        return st;
+    };
+
+    // L2 prefetch runs kPfAhead items (of 256 threads x 4 px) ahead of the register loads: the input is a pure stream
+    // (every byte read once), and with only one item of register prefetch the loads were exposed to the full DRAM
+    // latency (experiment: the kernel without its global loads ran in 0.26 ms instead of 0.44 ms).  Plain per-thread
+    // prefetch.global.L2 measured faster than cp.async.bulk.prefetch.L2 per row segment (0.402 vs 0.414 ms).
+    constexpr int kPfAhead = 6;
+    int cpf = c;
+    const char* ppf = pin;
+    int ipf = tid;
+    auto prefetch_next = [&]() {
+        ipf += kK1Threads;
+        cpf += dc;
+        uint32_t st = dstep;
+        if (cpf >= tw4) { cpf -= tw4; st += dwrap; }
+        ppf = wide_imm<16>(ppf, st);
+        if (ipf < nitems) {
+            prefetch_l2(ppf);
+            prefetch_l2(wide_imm<16>(ppf, plane4));
+            prefetch_l2(wide_imm<32>(ppf, plane4));
+        }
+    };
+#pragma unroll 1
+    for (int k = 0; k < kPfAhead; ++k) prefetch_next();
+
+    float4 ar, ag, ab, br, bg, bb;
+    int i = tid;
+    if (i < nitems) load(pin, ar, ag, ab);
+    while (i < nitems) {
+        const uint32_t st1 = advance(c);
+        const int i2 = i + kK1Threads;
+        if (i2 < nitems) load(wide_imm<16>(pin, st1), br, bg, bb);
+        prefetch_next();
+        uint32_t wl, wa, wb;
+        k1_item(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
+        store(plab, wl, wa, wb);
+        if (i2 >= nitems) break;
+        const uint32_t st2 = advance(c);
+        pin = wide_imm<16>(pin, st1 + st2);
+        i = i2 + kK1Threads;
+        if (i < nitems) load(pin, ar, ag, ab);
+        prefetch_next();
+        k1_item(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
+        store(const_cast<char*>(wide_imm<4>(plab, st1)), wl, wa, wb);
+        plab = const_cast<char*>(wide_imm<4>(plab, st1 + st2));
+    }
+    __syncthreads();
+
+    // thread `tid` sums bin `tid`: byte (tid&3) of the 256 words of row (tid>>2).  The four threads of a
+    // row read the same 16-byte chunks (broadcast); chunk order is rotated by the row so that the eight
+    // rows of a warp hit disjoint banks.
+    unsigned total_u = 0;
+    {
+        const uint4* row = reinterpret_cast<const uint4*>(s_cnt + (tid >> 2) * (kK1Threads * 4));
+        const unsigned sel = 1u << (8 * (tid & 3));
+#pragma unroll 8
+        for (int k = 0; k < kK1Threads / 4; ++k) {
+            const uint4 v = row[(k + (tid >> 2)) & (kK1Threads / 4 - 1)];
+            total_u = __dp4a(v.x, sel, total_u);
+            total_u = __dp4a(v.y, sel, total_u);
+            total_u = __dp4a(v.z, sel, total_u);
+            total_u = __dp4a(v.w, sel, total_u);
+        }
+    }
+    int total = int(total_u);
+    const size_t t_idx = size_t(f) * ntiles + tile;
+    if (!publish_hist(total, hist_g + t_idx * 256, tickets + t_idx, g.nstrips, &s_flag)) return;
+    tile_lut_256(total, g.clip, g.lut_scale, lut_g + t_idx * 256, s_tmp);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1 generic path: any size (including OpenCV's reflect-101 padding quirk, Appendix A.3 step 1).
 // One CTA per (frame, tile); per-warp shared histograms with atomics.  Correctness path for
 // ragged shapes -- the named workloads all take the vector path.
@@ -429,96 +742,54 @@ k_map_vec(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, fl
 
 
 // ---------------------------------------------------------------------------------------------
-// K3 fast path, second generation ("instruction diet", profiles/r1_clahe_full.md showed the first one issue-bound
-// at 94 SASS instructions per pixel):
-//   * clamp(v, 0, 4095) is ONE VIMNMX.RELU (__vimin_s32_relu);
-//   * the rounded L' is never masked/shifted: the fp32 magic-add leaves 0x4B400000 + L' in the register and the
-//     constant folds into the table address;
-//   * abToXZ selects with a predicated add instead of SEL and keeps the exact truncating division;
-//   * two of the four LUT bytes are converted by the conversion pipe (I2F.U8 with a byte selector, 1 instruction),
-//     two by PRMT+FADD on the ALU/FMA pipes, so neither pipe carries all four;
-//   * 32-bit element indices against per-plane base pointers (one IMAD.WIDE per access instead of 64-bit adds);
-//   * plain streaming cache operators (ld.global.nc / st.global.cs): no createpolicy register to shuttle through
-//     the uniform datapath on every access.
-// The arithmetic is exactly that of k_map_vec (Appendix A.2/A.3), hence bit-identical output.
+// K3 fast path, fifth generation.  Experiments on the third one (profiles/r2_*): with loads AND stores suppressed the
+// kernel still took 0.40 of 0.44 ms -- it is bound by instruction issue (94 executed instructions per pixel incl.
+// prologues and idle lanes), not by HBM or by shared-memory bank conflicts (constant frames are as slow as noise).
+// Hence a shorter instruction stream:
+//   * abToXZ: the cubic branch is 4 instructions; the linear branch (i <= 3390: C truncating division, 7 instructions
+//     plus a select) becomes a PREDICATED 16-bit table load (23 KB table; only dark pixels take it, so the gather is
+//     sparse);
+//   * {ify - 4194, y} of a grey level come from one 64-bit shared load, nothing to unpack;
+//   * the CTA has a multiple of the cell width in threads (240-px cell = 60 four-pixel columns -> 480 threads = 8 full
+//     rows): no idle lanes (first generations: 16 of 256);
+//   * persistent CTAs (2 per SM) pull (frame, cell, strip) items from an atomic counter: the 41 KB of tables are staged
+//     once per CTA instead of once per item, no tail wave; the quad table of the next item is built while the current
+//     one is mapped (one barrier per item).
+// Arithmetic identical to k_map_vec (Appendix A.2/A.3): bit-identical output.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ld_nc_u32(const uint8_t* p)
-{
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_cs_f4(float* p, float a, float b, float c, float d)
-{
-    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
+constexpr int kK5MaxThreads = 512;
+constexpr int kXzLinMin = -8145;
+constexpr int kXzLinBytes = (UPR_TAB_XZLIN_LEN * 2 + 15) / 16 * 16;
 
-// Pipe budget notes (ncu, profiles/r1_clahe_full.md): the first-generation kernel was bound by the 16-lane ALU
-// pipe (72 % busy: SHF/LOP3/LEA/IADD3/PRMT/VIMNMX/ISETP) while the FMA pipe idled at 36 % and the conversion
-// pipe at 1 %.  Hence: table records with a 12-byte stride (address = index*12 + base is an IMAD, not a LEA),
-// unpacked {quad, A, y} records (no LOP/SHF to split a packed word), all four LUT bytes converted by I2F.U8,
-// shift+add pairs expressed so that they become one LEA.HI.SX32, and IMAD.WIDE global addressing.
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
-{
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ int lds_s32_off(uint32_t addr, int off)
-{
-    int v;
-    if (off == 4) asm("ld.shared.s32 %0, [%1+4];" : "=r"(v) : "r"(addr));
-    else asm("ld.shared.s32 %0, [%1+8];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds_f32(uint32_t addr)
-{
-    float v;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-// base + idx*scale as ONE IMAD.WIDE on the FMA pipe.  `scale` is a run-time register (4 or 16 plus blockIdx.z == 0):
-// with an immediate power of two ptxas lowers the same PTX to LEA + LEA.HI.X, two instructions on the ALU pipe,
-// which is the pipe these kernels saturate.
-__device__ __forceinline__ const void* wide_addr(const void* base, uint32_t idx, uint32_t scale)
-{
-    unsigned long long r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "r"(scale), "l"(base));
-    return reinterpret_cast<const void*>(r);
-}
-
-// abToXZ (Appendix A.2): i <= 3390 ? trunc(i*108/841) - 290 : ((i*i >> 14) * i) >> 14
-__device__ __forceinline__ int ab_to_xz2(int i)
-{
-    const int lin = i * 108 / 841 - 290;
-    const int cub = (((i * i) >> 14) * i) >> 14;
-    return i <= 3390 ? lin : cub;
-}
-
-constexpr int kRecStride = 12;   // bytes per grey-level record {quad u32, A s32, y s32}
-
-struct MapTables {
-    uint32_t four;     // 4, opaque to ptxas (see wide_addr)
-    uint32_t rec;      // shared address of the record table
-    uint32_t rec_lp;   // rec - 0x4B400000*12 (mod 2^32): record address of L' straight from the magic-add bits
-    uint32_t outf;     // shared address of float[4096] invgamma[c] / 255.f
+struct Map5Tables {
+    uint32_t four;      // 4, opaque to ptxas
+    uint32_t quad;      // shared address of the current quad table (u32[256])
+    uint32_t ay_lp;     // &s_ay[0] - 0x4B400000*8: address of {A, y}[L'] straight from the magic-add bits
+    uint32_t outf;      // shared address of float[4096]
+    uint32_t lin;       // &s_lin[0] - 2*kXzLinMin
 };
 
-__device__ __forceinline__ void map_pixel(uint32_t Lv, int av, int bv, float xa, float xa1, float ya, float ya1,
-                                          const MapTables& t, float& r, float& g, float& b)
+__device__ __forceinline__ int ab_to_xz5(int i, uint32_t lin)
 {
-    const uint32_t q = lds_u32(Lv * kRecStride + t.rec);
+    int x = (((i * i) >> 14) * i) >> 14;
+    asm("{\n\t.reg .pred p;\n\tsetp.le.s32 p, %1, 3390;\n\t@p ld.shared.s16 %0, [%2];\n\t}" : "+r"(x) : "r"(i), "r"(uint32_t(i) * 2u + lin));
+    return x;
+}
+
+__device__ __forceinline__ void map_pixel5(uint32_t Lv, int av, int bv, float xa, float xa1, float ya, float ya1,
+                                           const Map5Tables& t, float& r, float& g, float& b)
+{
+    const uint32_t q = lds_u32(Lv * t.four + t.quad);
     const float l11 = float(q & 0xffu), l12 = float((q >> 8) & 0xffu), l21 = float((q >> 16) & 0xffu), l22 = float(q >> 24);
     const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
     const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
     const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
     // rint via 1.5*2^23 (round-half-even == cvRound); 0 <= res < 255.5, so the sum's bits are 0x4B400000 + L'
-    const uint32_t ra = __float_as_uint(__fadd_rn(res, 12582912.0f)) * kRecStride + t.rec_lp;
-    const int A = lds_s32_off(ra, 4);    // ify(L') - 4194
-    const int y = lds_s32_off(ra, 8);
-    // ix = ify + adiv(a);  iz = ify - bdiv(b) = A + 14678 - ((b*41943+16) >> 9)  with  -(t >> 9) == (511 - t) >> 9
-    const int x = ab_to_xz2(A + ((av * 268435 + 128) >> 13));
-    const int z = ab_to_xz2(A + ((bv * -41943 + (495 + 14678 * 512)) >> 9));
+    int A, y;
+    asm("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(A), "=r"(y) : "r"(__float_as_uint(__fadd_rn(res, 12582912.0f)) * 8u + t.ay_lp));
+    // ix = ify + adiv(a);  iz = ify - bdiv(b) = A + 14678 - ((b*41943+16) >> 9)  with  -(u >> 9) == (511 - u) >> 9
+    const int x = ab_to_xz5(A + ((av * 268435 + 128) >> 13), t.lin);
+    const int z = ab_to_xz5(A + ((bv * -41943 + (495 + 14678 * 512)) >> 9), t.lin);
     const int ro = __vimin_s32_relu((12615 * x - 6296 * y - 2223 * z + 8192) >> 14, 4095);
     const int go = __vimin_s32_relu((-3773 * x + 7684 * y + 185 * z + 8192) >> 14, 4095);
     const int bo = __vimin_s32_relu((217 * x - 836 * y + 4715 * z + 8192) >> 14, 4095);
@@ -527,94 +798,142 @@ __device__ __forceinline__ void map_pixel(uint32_t Lv, int av, int bv, float xa,
     b = lds_f32(uint32_t(bo) * t.four + t.outf);
 }
 
-__global__ void __launch_bounds__(kK3Threads, 4)
-k_map_vec2(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out, const MapGeom g)
+__global__ void __launch_bounds__(kK5MaxThreads, 2)
+k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out, const MapGeom g,
+           unsigned* __restrict__ work, int nitems)
 {
-    __shared__ __align__(16) uint32_t s_rec[256 * kRecStride / 4];
-    __shared__ __align__(16) float s_outf[4096];
+    extern __shared__ __align__(16) unsigned char smem5[];
+    int16_t* s_lin = reinterpret_cast<int16_t*>(smem5);
+    float* s_outf = reinterpret_cast<float*>(smem5 + kXzLinBytes);
+    int* s_ay = reinterpret_cast<int*>(s_outf + 4096);             // {A, y}[256]
+    uint32_t* s_quad = reinterpret_cast<uint32_t*>(s_ay + 512);    // [2][256]
+    __shared__ int s_nxt[2];
 
-    const int tid = threadIdx.x;
-    const int strip = blockIdx.x % g.nstrips;
-    const int cell = blockIdx.x / g.nstrips;
-    const int cy = cell / (g.tiles_x + 1), cx = cell - cy * (g.tiles_x + 1);
-    const int f = blockIdx.y;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int ncells = (g.tiles_x + 1) * (g.tiles_y + 1);
+    const int per_frame = ncells * g.nstrips;
 
-    const int x0 = g.bx[cx], x1 = g.bx[cx + 1];
-    const int rows_cell = g.by[cy + 1] - g.by[cy];
-    const int srows = (rows_cell + g.nstrips - 1) / g.nstrips;
-    const int y0 = g.by[cy] + strip * srows;
-    const int y1 = min(y0 + srows, g.by[cy + 1]);
-    if (x0 >= x1 || y0 >= y1) return;
-
-    {
+    auto build_quad = [&](int item, uint32_t* dst) {   // tid < 256
+        const int f = item / per_frame, rem = item - f * per_frame;
+        const int cell = rem / g.nstrips;
+        const int cy = cell / (g.tiles_x + 1), cx = cell - cy * (g.tiles_x + 1);
         const int ty1 = max(cy - 1, 0), ty2 = min(cy, g.tiles_y - 1);
         const int tx1 = max(cx - 1, 0), tx2 = min(cx, g.tiles_x - 1);
         const uint8_t* lf = lut_g + size_t(f) * g.tiles_x * g.tiles_y * 256 + tid;
-        const uint32_t yf = d_labyf[tid];
-        s_rec[tid * 3 + 0] = uint32_t(lf[(ty1 * g.tiles_x + tx1) * 256]) | (uint32_t(lf[(ty1 * g.tiles_x + tx2) * 256]) << 8) |
-                             (uint32_t(lf[(ty2 * g.tiles_x + tx1) * 256]) << 16) | (uint32_t(lf[(ty2 * g.tiles_x + tx2) * 256]) << 24);
-        s_rec[tid * 3 + 1] = uint32_t(int(yf & 0xffffu) - 4194);
-        s_rec[tid * 3 + 2] = yf >> 16;
-#pragma unroll
-        for (int i = 0; i < 4096 / 4 / kK3Threads; ++i)
-            reinterpret_cast<uint4*>(s_outf)[tid + i * kK3Threads] = reinterpret_cast<const uint4*>(d_outf_bits)[tid + i * kK3Threads];
+        dst[tid] = uint32_t(lf[(ty1 * g.tiles_x + tx1) * 256]) | (uint32_t(lf[(ty1 * g.tiles_x + tx2) * 256]) << 8) |
+                   (uint32_t(lf[(ty2 * g.tiles_x + tx1) * 256]) << 16) | (uint32_t(lf[(ty2 * g.tiles_x + tx2) * 256]) << 24);
+    };
+
+    int cur = blockIdx.x;
+    {
+        for (int i = tid; i < kXzLinBytes / 16; i += nthr) reinterpret_cast<uint4*>(s_lin)[i] = reinterpret_cast<const uint4*>(d_xzlin)[i];
+        for (int i = tid; i < 1024; i += nthr) reinterpret_cast<uint4*>(s_outf)[i] = reinterpret_cast<const uint4*>(d_outf_bits)[i];
+        if (tid < 256) {
+            const uint32_t yf = d_labyf[tid];
+            s_ay[tid * 2 + 0] = int(yf & 0xffffu) - 4194;
+            s_ay[tid * 2 + 1] = int(yf >> 16);
+            if (cur < nitems) build_quad(cur, s_quad);
+        }
+        if (tid == 0) s_nxt[0] = int(gridDim.x + atomicAdd(work, 1u));
     }
     __syncthreads();
 
-    MapTables t;
-    t.rec = uint32_t(__cvta_generic_to_shared(s_rec));
-    // + blockIdx.z (always 0): keeps the constant a run-time register value, so that the L' record address stays
-    // ONE IMAD (bits*12 + reg) instead of an IMAD plus one wide-immediate add per load
-    t.rec_lp = t.rec - 0x4B400000u * uint32_t(kRecStride) + blockIdx.z;
-    t.outf = uint32_t(__cvta_generic_to_shared(s_outf));
-    t.four = 4u + blockIdx.z;
-    const uint32_t sixteen = 16u + blockIdx.z;
+    Map5Tables t;
+    const uint32_t zero = blockIdx.z;  // always 0
+    t.four = opaque(4u + zero);
+    t.ay_lp = opaque(uint32_t(__cvta_generic_to_shared(s_ay)) - 0x4B400000u * 8u);
+    t.outf = opaque(uint32_t(__cvta_generic_to_shared(s_outf)));
+    t.lin = opaque(uint32_t(__cvta_generic_to_shared(s_lin)) - 2u * uint32_t(kXzLinMin));
+    const uint32_t sixteen = opaque(16u + zero);
+    const uint32_t quad0 = uint32_t(__cvta_generic_to_shared(s_quad));
 
-    // word (4 px) indices against per-plane bases: one IMAD.WIDE per access; fast path guarantees 3*plane < 2^32
     const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;
-    const uint32_t* labL = reinterpret_cast<const uint32_t*>(lab) + size_t(f) * 3 * plane4;
-    float4* outR = reinterpret_cast<float4*>(out) + size_t(f) * 3 * plane4;
-    const float txbase = float(cx - 1), tybase = float(cy - 1);
-    const int cw4 = (x1 - x0) >> 2;
     const uint32_t w4 = uint32_t(g.w) >> 2;
 
-    for (int xc = 0; xc < cw4; xc += kK3Threads) {
-        const int cwc = min(kK3Threads, cw4 - xc);
-        const int rpi = kK3Threads / cwc;  // rows per iteration
-        const int lr = tid / cwc, lc = tid - lr * cwc;
-        if (lr >= rpi) continue;
-        const int x = x0 + (xc + lc) * 4;
-        float xa[4], xa1[4];
+    for (int buf = 0; cur < nitems; buf ^= 1) {
+        const int nxt = s_nxt[buf];
+        if (nxt < nitems && tid < 256) build_quad(nxt, s_quad + (buf ^ 1) * 256);
+        if (tid == 0) s_nxt[buf ^ 1] = int(gridDim.x + atomicAdd(work, 1u));
+        t.quad = quad0 + uint32_t(buf) * 1024u;
+
+        const int f = cur / per_frame, rem = cur - f * per_frame;
+        const int cell = rem / g.nstrips, strip = rem - cell * g.nstrips;
+        const int cy = cell / (g.tiles_x + 1), cx = cell - cy * (g.tiles_x + 1);
+        const int x0 = g.bx[cx], x1 = g.bx[cx + 1];
+        const int rows_cell = g.by[cy + 1] - g.by[cy];
+        const int srows = (rows_cell + g.nstrips - 1) / g.nstrips;
+        const int y0 = g.by[cy] + strip * srows;
+        const int y1 = min(y0 + srows, g.by[cy + 1]);
+
+        const uint32_t* labL = reinterpret_cast<const uint32_t*>(lab) + size_t(f) * 3 * plane4;
+        float4* outR = reinterpret_cast<float4*>(out) + size_t(f) * 3 * plane4;
+        const float txbase = float(cx - 1), tybase = float(cy - 1);
+        const int cw4 = (x1 - x0) >> 2;
+
+        for (int xc = 0; xc < cw4; xc += nthr) {
+            const int cwc = min(nthr, cw4 - xc);
+            const int rpi = nthr / cwc;  // rows per iteration
+            const int lr = tid / cwc, lc = tid - lr * cwc;
+            if (lr >= rpi) continue;
+            const int x = x0 + (xc + lc) * 4;
+            float xa[4], xa1[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float txf = __fadd_rn(__fmul_rn(float(x + k), g.inv_tw), -0.5f);
-            xa[k] = __fsub_rn(txf, txbase);
-            xa1[k] = __fsub_rn(1.0f, xa[k]);
-        }
-        // three running word offsets (L/R, a/G, b/B planes) against ONE base each for lab and out: every access is a
-        // single IMAD.WIDE on the FMA pipe (distinct offset registers keep ptxas from splitting them into 64-bit adds)
-        // (the column goes into per-thread bases: a uniform base would be added with a separate 64-bit IADD3 pair)
-        const uint32_t* labC = labL + (uint32_t(x) >> 2);
-        float4* outC = outR + (uint32_t(x) >> 2);
-        uint32_t o0 = uint32_t(y0 + lr) * w4, o1 = o0 + plane4, o2 = o1 + plane4;
-        const uint32_t doff = uint32_t(rpi) * w4;
-        for (int y = y0 + lr; y < y1; y += rpi, o0 += doff, o1 += doff, o2 += doff) {
-            const uint32_t wl = __ldg(static_cast<const uint32_t*>(wide_addr(labC, o0, t.four)));
-            const uint32_t wa = __ldg(static_cast<const uint32_t*>(wide_addr(labC, o1, t.four)));
-            const uint32_t wb = __ldg(static_cast<const uint32_t*>(wide_addr(labC, o2, t.four)));
-            const float tyf = __fadd_rn(__fmul_rn(float(y), g.inv_th), -0.5f);
-            const float ya = __fsub_rn(tyf, tybase);
-            const float ya1 = __fsub_rn(1.0f, ya);
-            float o[3][4];
+            for (int k = 0; k < 4; ++k) {
+                const float txf = __fadd_rn(__fmul_rn(float(x + k), g.inv_tw), -0.5f);
+                xa[k] = __fsub_rn(txf, txbase);
+                xa1[k] = __fsub_rn(1.0f, xa[k]);
+            }
+            // per-thread 64-bit row pointers, advanced by a constant byte stride (2 instructions per plane and row)
+            const char* pl = reinterpret_cast<const char*>(labL + (uint32_t(y0 + lr) * w4 + (uint32_t(x) >> 2)));
+            char* po = reinterpret_cast<char*>(outR + (uint32_t(y0 + lr) * w4 + (uint32_t(x) >> 2)));
+            const uint32_t step4 = uint32_t(rpi) * w4;   // row stride of this thread in 4-pixel groups
+
+            auto load3 = [&](const char* p, uint32_t& l, uint32_t& a, uint32_t& b) {
+                l = __ldg(reinterpret_cast<const uint32_t*>(p));
+                a = __ldg(reinterpret_cast<const uint32_t*>(wide_imm<4>(p, plane4)));
+                b = __ldg(reinterpret_cast<const uint32_t*>(wide_imm<8>(p, plane4)));
+            };
+            auto map_row = [&](int y, char* p, uint32_t wl, uint32_t wa, uint32_t wb) {
+                const float tyf = __fadd_rn(__fmul_rn(float(y), g.inv_th), -0.5f);
+                const float ya = __fsub_rn(tyf, tybase);
+                const float ya1 = __fsub_rn(1.0f, ya);
+                float o[3][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                map_pixel(__byte_perm(wl, 0u, 0x4440u | uint32_t(k)), int(__byte_perm(wa, 0u, 0x4440u | uint32_t(k))),
-                          int(__byte_perm(wb, 0u, 0x4440u | uint32_t(k))), xa[k], xa1[k], ya, ya1, t, o[0][k], o[1][k], o[2][k]);
-            __stcs(static_cast<float4*>(const_cast<void*>(wide_addr(outC, o0, sixteen))), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
-            __stcs(static_cast<float4*>(const_cast<void*>(wide_addr(outC, o1, sixteen))), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
-            __stcs(static_cast<float4*>(const_cast<void*>(wide_addr(outC, o2, sixteen))), make_float4(o[2][0], o[2][1], o[2][2], o[2][3]));
+                for (int k = 0; k < 4; ++k)
+                    map_pixel5(__byte_perm(wl, 0u, 0x4440u | uint32_t(k)), int(__byte_perm(wa, 0u, 0x4440u | uint32_t(k))),
+                               int(__byte_perm(wb, 0u, 0x4440u | uint32_t(k))), xa[k], xa1[k], ya, ya1, t, o[0][k], o[1][k], o[2][k]);
+                __stcs(reinterpret_cast<float4*>(p), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
+                __stcs(reinterpret_cast<float4*>(const_cast<char*>(wide_imm<16>(p, plane4))), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
+                __stcs(reinterpret_cast<float4*>(const_cast<char*>(wide_imm<32>(p, plane4))), make_float4(o[2][0], o[2][1], o[2][2], o[2][3]));
+            };
+
+            // three register sets, loads two rows ahead of their use: the ncu source view of the one-row-ahead version
+            // still had 47 % of its stall samples on the first use of the Lab words (load-to-use > 1.5 us behind the
+            // kernel's own 12 B/px store stream)
+            int y = y0 + lr;
+            uint32_t al = 0, aa = 0, ab = 0, bl = 0, ba = 0, bb = 0, cl = 0, ca = 0, cb = 0;
+            if (y < y1) load3(pl, al, aa, ab);
+            if (y + rpi < y1) load3(wide_imm<4>(pl, step4), bl, ba, bb);
+            while (y < y1) {
+                if (y + 2 * rpi < y1) load3(wide_imm<8>(pl, step4), cl, ca, cb);
+                map_row(y, po, al, aa, ab);
+                y += rpi;
+                if (y >= y1) break;
+                if (y + 2 * rpi < y1) load3(wide_imm<12>(pl, step4), al, aa, ab);
+                map_row(y, const_cast<char*>(wide_imm<16>(po, step4)), bl, ba, bb);
+                y += rpi;
+                if (y >= y1) break;
+                if (y + 2 * rpi < y1) load3(wide_imm<16>(pl, step4), bl, ba, bb);
+                map_row(y, const_cast<char*>(wide_imm<32>(po, step4)), cl, ca, cb);
+                y += rpi;
+                pl = wide_imm<12>(pl, step4);
+                po = const_cast<char*>(wide_imm<48>(po, step4));
+            }
         }
+        __syncthreads();
+        cur = nxt;
     }
+    (void)sixteen;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -668,7 +987,7 @@ k_map_generic(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g
 // host side
 // ---------------------------------------------------------------------------------------------
 struct ClaheLayout {
-    size_t off_hist, off_lut, off_tickets, off_lab, total;
+    size_t off_hist, off_lut, off_tickets, off_work, off_lab, total;
 };
 
 static ClaheLayout clahe_layout(int n, int h, int w, int tiles_x, int tiles_y)
@@ -677,7 +996,8 @@ static ClaheLayout clahe_layout(int n, int h, int w, int tiles_x, int tiles_y)
     const size_t nt = size_t(n) * tiles_x * tiles_y;
     L.off_hist = 0;
     L.off_tickets = align_up(L.off_hist + nt * 256 * sizeof(int32_t), 256);
-    L.off_lut = align_up(L.off_tickets + nt * sizeof(unsigned), 256);
+    L.off_work = align_up(L.off_tickets + nt * sizeof(unsigned), 256);   // work-queue head of the persistent map kernel
+    L.off_lut = align_up(L.off_work + 256, 256);
     L.off_lab = align_up(L.off_lut + nt * 256, 256);
     L.total = align_up(L.off_lab + size_t(n) * 3 * h * w, 256);
     return L;
@@ -689,7 +1009,8 @@ static bool valid_shape(int n, int h, int w, int tiles_x, int tiles_y)
            size_t(h) * w <= (size_t(1) << 30);
 }
 
-// development switch (A/B timing on the GPU box): UPR_CLAHE_VARIANT bit 0 = first-generation K3, bit 1 = first-generation K1
+// development switch (A/B timing on the GPU box, profiles/r2_clahe.md): UPR_CLAHE_VARIANT bit 0 = first-generation
+// map kernel (k_map_vec), bit 1 = first-generation histogram kernel (k_hist_lab_vec).  Same results either way.
 static int variant()
 {
     static const int v = [] { const char* e = std::getenv("UPR_CLAHE_VARIANT"); return e ? std::atoi(e) : 0; }();
@@ -718,6 +1039,7 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
     auto* base = static_cast<unsigned char*>(ws);
     auto* hist = reinterpret_cast<int32_t*>(base + lay.off_hist);
     auto* tickets = reinterpret_cast<unsigned*>(base + lay.off_tickets);
+    auto* work = reinterpret_cast<unsigned*>(base + lay.off_work);
     auto* lut = base + lay.off_lut;
     auto* lab = base + lay.off_lab;
 
@@ -778,15 +1100,20 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                 UPR_CUDA_TRY(cudaMemsetAsync(hist + ftile * 256, 0, size_t(nf) * ntiles * 256 * sizeof(int32_t), stream));
                 UPR_CUDA_TRY(cudaMemsetAsync(tickets + ftile, 0, size_t(nf) * ntiles * sizeof(unsigned), stream));
             }
-            const size_t smem1 = size_t(256) * kK1Threads + UPR_TAB_GAMMA_LEN * 2 + UPR_TAB_CBRT_LEN * 2;
+            const size_t smem1 = size_t(256) * kK1Threads + UPR_TAB_GAMMA_LEN * 4 + UPR_TAB_CBRT_LEN * 2;
             static bool attr_set = false;  // benign race: idempotent
             if (!attr_set) {
                 UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
+                UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
                 attr_set = true;
             }
             if (stage_mask & 1) {
-                k_hist_lab_vec<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
-                                                                                            lut + ftile * 256, tickets + ftile, g);
+                if (variant() & 2)
+                    k_hist_lab_vec<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
+                                                                                                lut + ftile * 256, tickets + ftile, g);
+                else
+                    k_hist_lab_vec2<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
+                                                                                                 lut + ftile * 256, tickets + ftile, g);
                 UPR_LAUNCH_CHECK();
             }
             const int ncells = (tiles_x + 1) * (tiles_y + 1);
@@ -796,10 +1123,30 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             ks = std::min(std::max(ks, want3), std::max(cell_rows / 4, 1));
             m.nstrips = ks;
             if (stage_mask & 2) {
-                if (variant() & 1)
+                if (variant() & 1) {
                     k_map_vec<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
-                else
-                    k_map_vec2<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
+                } else {
+                    // thread count: the largest multiple of the interior cell width (in 4-px columns) <= 512
+                    const int cw4 = g.tw / 4;
+                    int nthr = cw4 <= kK5MaxThreads ? (kK5MaxThreads / cw4) * cw4 : kK5MaxThreads;
+                    if (nthr < 256) nthr = kK5MaxThreads;
+                    const size_t smem5 = size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4;
+                    static bool attr5 = false;
+                    if (!attr5) {
+                        UPR_CUDA_TRY(cudaFuncSetAttribute(k_map_vec5, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem5)));
+                        attr5 = true;
+                    }
+                    // items = (frame, cell, strip); enough strips for >= 16 items per resident CTA on small batches
+                    const int resident = 2 * kNumSMsB200;
+                    int ks5 = std::max(1, int((size_t(16) * resident + size_t(nf) * ncells - 1) / (size_t(nf) * ncells)));
+                    ks5 = std::min(ks5, std::max(cell_rows / 8, 1));
+                    m.nstrips = ks5;
+                    const long long nitems = (long long)nf * ncells * ks5;
+                    if (nitems > 0x7fffffffLL / 2) return UPR_E_SHAPE;
+                    UPR_CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(unsigned), stream));
+                    k_map_vec5<<<dim3(unsigned(std::min<long long>(nitems, resident))), nthr, smem5, stream>>>(
+                        lab + fplane, lut + ftile * 256, out + fplane, m, work, int(nitems));
+                }
                 UPR_LAUNCH_CHECK();
             }
         } else {
