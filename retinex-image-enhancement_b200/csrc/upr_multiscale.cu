@@ -17,6 +17,7 @@
 // Sums are fp64 per thread -> warp shuffle -> one partial per CTA -> the last CTA of the image adds the
 // partials in index order (deterministic) and writes the three means and the gain.
 #include <algorithm>
+#include <cstdlib>
 
 #include "upr_common.cuh"
 
@@ -287,6 +288,205 @@ k_ms_fused(const float* __restrict__ x, int h, int w, int tiles_x, double* __res
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// streaming path (replaces the tile kernel above for the named shapes): one warp per (frame, 120-column band, row
+// segment), no shared memory, no block barrier.  ncu on k_ms_fused: 288 executed instructions per pixel, 80 % issue
+// utilisation -- index arithmetic of three tile passes, 41 % halo re-staging, per-pixel luma and fp64 adds.  Here:
+//   * a lane owns 4 full-resolution columns = 2 half-resolution columns = 1 quarter-resolution column and walks down
+//     the segment one quarter row (4 image rows) at a time; the rows needed for vertical differences are carried in
+//     registers, horizontal neighbours come from the adjacent lanes by shuffle (lanes 0 and 31 are halo);
+//   * only what the means need is computed: sum(r+g+b+luma) is (1+w_c) * sum(channel c); the 2x2 block sums that give
+//     the channel sums ARE the (unscaled) half-resolution pixels, the centre 2x2 of a 4x4 block the quarter pixel;
+//     |grad| = 0.5 * sqrt(dx^2 + dy^2) with un-halved central differences (one-sided border differences doubled),
+//     and the constant factors (0.5, 0.25) are applied once per step to the partial sums -- powers of two, so every
+//     pixel value equals the reference's up to the approximate square root;
+//   * fp32 partial sums per 16 pixels, fp64 across steps, ordered (deterministic) reduction by the last warp.
+// Requires H % 4 == 0, W % 4 == 0, H/4 >= 2, W/4 >= 2 and 16-byte aligned rows.
+// -----------------------------------------------------------------------------------------
+constexpr int kMsBandCols = 120;
+
+__device__ __forceinline__ float ms_mag(float dx, float dy)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
+    return r;
+}
+
+// sum over the lane's pixels of sqrt(dx^2 + dy^2) for one row of 4 / 2 / 1 values; dy is already formed
+__device__ __forceinline__ float ms_edge4(const float v[4], const float dy[4], bool isL, bool isR)
+{
+    const float left = __shfl_up_sync(0xffffffffu, v[3], 1), right = __shfl_down_sync(0xffffffffu, v[0], 1);
+    const float d10 = __fsub_rn(v[1], v[0]), d32 = __fsub_rn(v[3], v[2]);
+    const float dx0 = isL ? __fadd_rn(d10, d10) : __fsub_rn(v[1], left);
+    const float dx3 = isR ? __fadd_rn(d32, d32) : __fsub_rn(right, v[2]);
+    return __fadd_rn(__fadd_rn(ms_mag(dx0, dy[0]), ms_mag(__fsub_rn(v[2], v[0]), dy[1])),
+                     __fadd_rn(ms_mag(__fsub_rn(v[3], v[1]), dy[2]), ms_mag(dx3, dy[3])));
+}
+__device__ __forceinline__ float ms_edge2(const float v[2], const float dy[2], bool isL, bool isR)
+{
+    const float left = __shfl_up_sync(0xffffffffu, v[1], 1), right = __shfl_down_sync(0xffffffffu, v[0], 1);
+    const float d = __fsub_rn(v[1], v[0]), d2 = __fadd_rn(d, d);
+    const float dx0 = isL ? d2 : __fsub_rn(v[1], left);
+    const float dx1 = isR ? d2 : __fsub_rn(right, v[0]);
+    return __fadd_rn(ms_mag(dx0, dy[0]), ms_mag(dx1, dy[1]));
+}
+__device__ __forceinline__ float ms_edge1(float v, float dy, bool isL, bool isR)
+{
+    const float left = __shfl_up_sync(0xffffffffu, v, 1), right = __shfl_down_sync(0xffffffffu, v, 1);
+    const float dr = __fsub_rn(right, v), dl = __fsub_rn(v, left);
+    const float dx = isL ? __fadd_rn(dr, dr) : (isR ? __fadd_rn(dl, dl) : __fsub_rn(right, left));
+    return ms_mag(dx, dy);
+}
+
+__global__ void __launch_bounds__(32)
+k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, double* __restrict__ partial,
+            unsigned* __restrict__ tickets, float* __restrict__ means, float* __restrict__ gain)
+{
+    const int lane = threadIdx.x;
+    const int band = blockIdx.x % bands, seg = blockIdx.x / bands;
+    const int f = blockIdx.y, parts = gridDim.x;
+    const int r0 = seg * seg_rows, r1 = min(r0 + seg_rows, h);
+    const int q0 = r0 >> 2, q1 = r1 >> 2, Q = h >> 2;
+    const int c0 = band * kMsBandCols - 4 + lane * 4;
+    const bool counted = lane >= 1 && lane <= 30 && c0 < w;
+    const bool isL = c0 == 0, isR = c0 + 4 == w;
+    const int cl = min(max(c0, 0), w - 4);
+    const long long plane = (long long)h * w;
+    const float* img = x + (long long)f * 3 * plane + cl;
+
+    float P2[3][4], P3[3][4], HB0[3][2], HB1[3][2], Q1[3], Q2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) P2[c][i] = P3[c][i] = 0.0f;
+        HB0[c][0] = HB0[c][1] = HB1[c][0] = HB1[c][1] = 0.0f;
+        Q1[c] = Q2[c] = 0.0f;
+    }
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+
+    if (r0 < h) {
+        for (int q = max(q0 - 1, 0); q <= q1; ++q) {
+            const bool have = q < Q;                 // image rows 4q .. 4q+3 exist
+            const bool inner = q >= q0 && q < q1;    // their statistics belong to this segment
+            const bool prev_in = q > q0;             // rows 4q-1 / 2q-1 / q-1 belong to this segment
+            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;   // this step's contribution to the three scale totals
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float wsum = c == 0 ? 1.299f : (c == 1 ? 1.587f : 1.114f);   // 1 + luma weight
+                float R[4][4];
+                if (have) {
+                    const float* p = img + c * plane + (long long)(4 * q) * w;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(p + (long long)j * w));
+                        R[j][0] = v.x; R[j][1] = v.y; R[j][2] = v.z; R[j][3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) R[j][0] = R[j][1] = R[j][2] = R[j][3] = 0.0f;
+                }
+                // 2x2 block sums (= 4 x half-resolution pixels) and the centre 2x2 (= 4 x quarter-resolution pixel)
+                float B0[2], B1[2];
+                B0[0] = __fadd_rn(__fadd_rn(R[0][0], R[0][1]), __fadd_rn(R[1][0], R[1][1]));
+                B0[1] = __fadd_rn(__fadd_rn(R[0][2], R[0][3]), __fadd_rn(R[1][2], R[1][3]));
+                B1[0] = __fadd_rn(__fadd_rn(R[2][0], R[2][1]), __fadd_rn(R[3][0], R[3][1]));
+                B1[1] = __fadd_rn(__fadd_rn(R[2][2], R[2][3]), __fadd_rn(R[3][2], R[3][3]));
+                const float Qc = __fadd_rn(__fadd_rn(R[1][1], R[1][2]), __fadd_rn(R[2][1], R[2][2]));
+                float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+                // ---- rows completed by this step: image row 4q-1, half row 2q-1, quarter row q-1 ----
+                if (q >= 1) {
+                    float dy4[4], dy2[2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float dlast = __fsub_rn(P3[c][i], P2[c][i]);
+                        dy4[i] = have ? __fsub_rn(R[0][i], P2[c][i]) : __fadd_rn(dlast, dlast);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float dlast = __fsub_rn(HB1[c][i], HB0[c][i]);
+                        dy2[i] = have ? __fsub_rn(B0[i], HB0[c][i]) : __fadd_rn(dlast, dlast);
+                    }
+                    float dy1;
+                    if (q == 1) { const float d = __fsub_rn(Qc, Q1[c]); dy1 = __fadd_rn(d, d); }       // quarter row 0: one-sided
+                    else if (have) dy1 = __fsub_rn(Qc, Q2[c]);
+                    else { const float d = __fsub_rn(Q1[c], Q2[c]); dy1 = __fadd_rn(d, d); }          // last quarter row
+                    const float a0 = ms_edge4(P3[c], dy4, isL, isR);
+                    const float a1 = ms_edge2(HB1[c], dy2, isL, isR);
+                    const float a2 = ms_edge1(Q1[c], dy1, isL, isR);
+                    if (prev_in) { e0 = a0; e1 = a1; e2 = a2; }
+                }
+                // ---- rows 4q .. 4q+2, half row 2q ----
+                if (have) {
+                    float dyA[4], dyB[4], dyC[4], dyH[2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float d01 = __fsub_rn(R[1][i], R[0][i]);
+                        dyA[i] = q == 0 ? __fadd_rn(d01, d01) : __fsub_rn(R[1][i], P3[c][i]);
+                        dyB[i] = __fsub_rn(R[2][i], R[0][i]);
+                        dyC[i] = __fsub_rn(R[3][i], R[1][i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float d01 = __fsub_rn(B1[i], B0[i]);
+                        dyH[i] = q == 0 ? __fadd_rn(d01, d01) : __fsub_rn(B1[i], HB1[c][i]);
+                    }
+                    const float a0 = __fadd_rn(__fadd_rn(ms_edge4(R[0], dyA, isL, isR), ms_edge4(R[1], dyB, isL, isR)),
+                                               ms_edge4(R[2], dyC, isL, isR));
+                    const float a1 = ms_edge2(B0, dyH, isL, isR);
+                    if (inner) {
+                        e0 = __fadd_rn(e0, a0);
+                        e1 = __fadd_rn(e1, a1);
+                        const float sfull = __fadd_rn(__fadd_rn(B0[0], B0[1]), __fadd_rn(B1[0], B1[1]));
+                        // channel sums: full = sum of the 16 pixels, half = 0.25 * the same, quarter = 0.25 * centre sum
+                        t0 = __fmaf_rn(wsum, sfull, t0);
+                        t1 = __fmaf_rn(wsum * 0.25f, sfull, t1);
+                        t2 = __fmaf_rn(wsum * 0.25f, Qc, t2);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { P2[c][i] = R[2][i]; P3[c][i] = R[3][i]; }
+                    HB0[c][0] = B0[0]; HB0[c][1] = B0[1]; HB1[c][0] = B1[0]; HB1[c][1] = B1[1];
+                    Q2[c] = Q1[c]; Q1[c] = Qc;
+                }
+                // |grad| = 0.5 * sqrt(.) of un-halved differences; half / quarter pixels carry their factor 0.25
+                t0 = __fmaf_rn(0.5f, e0, t0);
+                t1 = __fmaf_rn(0.125f, e1, t1);
+                t2 = __fmaf_rn(0.125f, e2, t2);
+            }
+            if (counted) { acc0 += double(t0); acc1 += double(t1); acc2 += double(t2); }
+        }
+    }
+    acc0 = warp_sum(acc0);
+    acc1 = warp_sum(acc1);
+    acc2 = warp_sum(acc2);
+    double* pp = partial + ((long long)f * parts + blockIdx.x) * 3;
+    int last = 0;
+    if (lane == 0) {
+        pp[0] = acc0; pp[1] = acc1; pp[2] = acc2;
+        __threadfence();
+        const unsigned t = atomicAdd(tickets + f, 1u);
+        last = (t == unsigned(parts - 1));
+        if (last) tickets[f] = 0;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    // last warp of the frame: ordered sum of the partials (lane-strided, then a fixed shuffle tree)
+    double sums[3] = {0.0, 0.0, 0.0};
+    for (int k = lane; k < parts; k += 32) {
+        const double* qd = partial + ((long long)f * parts + k) * 3;
+        sums[0] += __ldcg(qd);
+        sums[1] += __ldcg(qd + 1);
+        sums[2] += __ldcg(qd + 2);
+    }
+    sums[0] = warp_sum(sums[0]);
+    sums[1] = warp_sum(sums[1]);
+    sums[2] = warp_sum(sums[2]);
+    if (lane == 0) {
+        const double counts[3] = {double(h) * w, double(h / 2) * (w / 2), double(h / 4) * (w / 4)};
+        ms_finalize(sums, counts, means + 3 * f, gain + f, nullptr);
+    }
+}
+
 struct MsLayout {
     size_t off_partial, off_tickets, off_half, off_quar, total;
     int oh2, ow2, oh4, ow4;
@@ -333,6 +533,22 @@ static int ms_run(const float* x, int n, int h, int w, float* means, float* gain
     const bool fused = allow_fused && !want_feat && h % 4 == 0 && w % 4 == 0 && aligned16(x) &&
                        (long long)tiles_x * tiles_y <= kMsMaxParts * 16LL;
     if (fused) {
+        static const int variant = [] { const char* e = std::getenv("UPR_MS_VARIANT"); return e ? std::atoi(e) : 0; }();
+        if (!(variant & 1) && h / 4 >= 2 && w / 4 >= 2) {
+            // streaming kernel: one warp per (band, row segment, frame); ~6 warps per resident slot, segments >= 64 rows
+            const int bands = (w + kMsBandCols - 1) / kMsBandCols;
+            const long long slots = 24LL * kNumSMsB200;
+            long long nseg = (6 * slots + (long long)n * bands - 1) / ((long long)n * bands);
+            nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
+            int seg_rows = int((h + nseg - 1) / nseg);
+            seg_rows = (seg_rows + 3) / 4 * 4;
+            const int segs = (h + seg_rows - 1) / seg_rows;
+            if ((long long)bands * segs <= kMsMaxParts) {
+                k_ms_stream<<<dim3(bands * segs, n), 32, 0, s>>>(x, h, w, bands, seg_rows, partial, tickets, means, gain);
+                UPR_LAUNCH_CHECK();
+                return UPR_OK;
+            }
+        }
         const int parts = tiles_x * tiles_y;
         // partial holds 3 doubles per CTA; the generic layout reserves kMsMaxParts*3 per image
         if (parts <= kMsMaxParts) {

@@ -17,6 +17,9 @@
 // K7 k_normalize: (v - min) / (max - min + 1e-8) in place (used for both maps).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+
+#include <cuda_fp16.h>
 
 #include "upr_common.cuh"
 
@@ -150,8 +153,199 @@ k_saliency_blur(const float* __restrict__ x, int h, int w, int tiles_x, float* _
     }
 }
 
-// sal = float((double(blur) - min) / (max - min + 1e-8)); optional attention raw value + its fp32 min/max
-template <bool kAttention>
+// ---------------------------------------------------------------------------------------------
+// K5s k_saliency_stream: the same chain as k_saliency_blur as a row-streaming, one-warp-per-CTA kernel.
+//   The tile kernel above executes 271 SASS instructions per pixel (ncu, profiles/r2_c5.md): 56 % halo re-computation
+//   of the gray stage (80x80 per 64x64), scalar reflect-indexed loads, 15 shared loads per output and pass, an fp64
+//   FMA chain.  Here a warp owns a band of 256 columns (lane = 8 columns; lanes 0 and 31 are the +-8 halo, 240 columns
+//   are written) and marches down a row segment:
+//     load row k (two 128-bit loads per plane and lane) -> quantise/gray on the FMA pipe (exact integer arithmetic in
+//     fp32, see upr_clahe.cu) -> |lap| of row k-1 (vertical neighbours from registers, the two horizontal ones by
+//     shuffle) -> fp16 ring of the last 16 |lap| rows in shared memory (integers <= 1020, and their pair sums <= 2040,
+//     are exact in fp16; the ring is private per lane and column, so it needs no synchronisation) -> VERTICAL 15-tap
+//     pass of row k-8 (symmetric taps paired) -> one fp32 row exchanged through a per-warp buffer (__syncwarp only) ->
+//     HORIZONTAL pass -> un-normalised blur (fp32) + running min/max.
+//   Vertical-then-horizontal and fp32 accumulation differ from OpenCV's fp64 rows-then-columns by ~2e-7 relative --
+//   the same order as the fp32 store of the tile kernel, and far inside the stated 1e-4 bound.
+//   Row segments overlap by 16 rows, bands by 16 columns (amplification ~1.07 x 1.06 instead of 1.56).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSsLaneCols = 8;
+constexpr int kSsBandCols = 30 * kSsLaneCols;      // 240 written columns per warp
+constexpr int kSsRingRows = 16;                    // power of two: slot offsets wrap with a mask
+constexpr int kSsRingRowBytes = 32 * kSsLaneCols * 2;   // 512
+constexpr int kSsRingBytes = kSsRingRows * kSsRingRowBytes;   // 8192
+
+struct GaussTapsF {
+    float t[8];
+};
+
+__device__ __forceinline__ void ss_load8(const float* __restrict__ row, int c0, int w, bool vec, float v[8])
+{
+    if (vec) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(row + c0));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(row + c0 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(row + reflect101_s(c0 + i, w));
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, float* __restrict__ blur_out,
+                  SalMinMax* __restrict__ mm, const GaussTapsF taps)
+{
+    __shared__ __align__(16) unsigned char s_ring[kSsRingBytes];
+    __shared__ __align__(16) float s_row[2][32 * kSsLaneCols + 16];
+
+    const int lane = threadIdx.x;
+    const int band = blockIdx.x % bands, seg = blockIdx.x / bands;
+    const int f = blockIdx.y;
+    const int r0 = seg * seg_rows, r1 = min(r0 + seg_rows, h);
+    if (r0 >= h) return;
+    const int c0 = band * kSsBandCols - kSsLaneCols + lane * kSsLaneCols;   // plane column of this lane's first pixel
+    const long long plane = (long long)h * w;
+    const float* img = x + (long long)f * 3 * plane;
+    const bool vec = (w % 4 == 0) && c0 >= 0 && c0 + kSsLaneCols <= w && aligned16(x);
+    const bool writer = lane >= 1 && lane <= 30 && c0 < w;
+    const bool vec_out = vec && aligned16(blur_out);
+
+    const uint32_t ring_lane = uint32_t(__cvta_generic_to_shared(s_ring)) + uint32_t(lane) * 16u;
+    float g0[8], g1[8], g2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g0[i] = g1[i] = g2[i] = 0.0f;
+    float mn = INFINITY, mx = -INFINITY;
+    uint32_t slot = 0;   // byte offset of the ring row that receives the next |lap| row
+
+    for (int k = r0 - 8; k < r1 + 8; ++k) {
+        // ---- gray(k) ----
+        {
+            const int gy = reflect101_s(k, h);
+            const float* rowp = img + (long long)gy * w;
+            float r[8], g[8], b[8];
+            ss_load8(rowp, c0, w, vec, r);
+            ss_load8(rowp + plane, c0, w, vec, g);
+            ss_load8(rowp + 2 * plane, c0, w, vec, b);
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m = __vimax3_u32(m, __float_as_uint(r[i]), __vimax3_u32(__float_as_uint(g[i]), __float_as_uint(b[i]), 0u));
+            if (m <= 0x3F800000u) {   // all in [+0, 1]: trunc(v*255) == RZ(v*255 + 2^23) - 2^23
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float qr = __fsub_rn(__fadd_rz(__fmul_rn(r[i], 255.0f), 8388608.0f), 8388608.0f);
+                    const float qg = __fsub_rn(__fadd_rz(__fmul_rn(g[i], 255.0f), 8388608.0f), 8388608.0f);
+                    const float qb = __fsub_rn(__fadd_rz(__fmul_rn(b[i], 255.0f), 8388608.0f), 8388608.0f);
+                    // (9798 R + 19235 G + 3735 B + 16384) >> 15: every partial sum is an integer < 2^24
+                    const float sgr = __fmaf_rn(qb, 3735.0f, __fmaf_rn(qg, 19235.0f, __fmaf_rn(qr, 9798.0f, 16384.0f)));
+                    g2[i] = __fsub_rn(__fmaf_rz(sgr, 0.000030517578125f, 8388608.0f), 8388608.0f);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    g2[i] = float((quantize_u8(r[i]) * 9798 + quantize_u8(g[i]) * 19235 + quantize_u8(b[i]) * 3735 + 16384) >> 15);
+            }
+        }
+        // ---- |lap|(k-1) -> ring ----
+        if (k >= r0 - 6) {
+            const float left = __shfl_up_sync(0xffffffffu, g1[7], 1), right = __shfl_down_sync(0xffffffffu, g1[0], 1);
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float l = i == 0 ? left : g1[i - 1], rr = i == 7 ? right : g1[i + 1];
+                a[i] = fabsf(__fmaf_rn(g1[i], -4.0f, __fadd_rn(__fadd_rn(g0[i], g2[i]), __fadd_rn(l, rr))));
+            }
+            const __half2 h01 = __floats2half2_rn(a[0], a[1]), h23 = __floats2half2_rn(a[2], a[3]);
+            const __half2 h45 = __floats2half2_rn(a[4], a[5]), h67 = __floats2half2_rn(a[6], a[7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ring_lane + slot), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&h23)), "r"(*reinterpret_cast<const uint32_t*>(&h45)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&h67)) : "memory");
+            // ---- vertical pass of row k-8, horizontal pass, output ----
+            if (k >= r0 + 8) {
+                // rows k-1-i live at (slot - i*512) & 8191; centre i = 7
+                auto ring_row = [&](int i, __half2 v[4]) {
+                    const uint32_t a4 = ring_lane + ((slot - uint32_t(i) * kSsRingRowBytes) & uint32_t(kSsRingBytes - 1));
+                    uint32_t u0, u1, u2, u3;
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(a4));
+                    v[0] = *reinterpret_cast<__half2*>(&u0); v[1] = *reinterpret_cast<__half2*>(&u1);
+                    v[2] = *reinterpret_cast<__half2*>(&u2); v[3] = *reinterpret_cast<__half2*>(&u3);
+                };
+                float vsum[8];
+                {
+                    __half2 c[4];
+                    ring_row(7, c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 cf = __half22float2(c[j]);
+                        vsum[2 * j] = __fmul_rn(taps.t[0], cf.x);
+                        vsum[2 * j + 1] = __fmul_rn(taps.t[0], cf.y);
+                    }
+                }
+#pragma unroll
+                for (int d = 1; d <= 7; ++d) {
+                    __half2 p[4], q[4];
+                    ring_row(7 - d, p);
+                    ring_row(7 + d, q);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 sf = __half22float2(__hadd2(p[j], q[j]));   // integers <= 2040: exact in fp16
+                        vsum[2 * j] = __fmaf_rn(taps.t[d], sf.x, vsum[2 * j]);
+                        vsum[2 * j + 1] = __fmaf_rn(taps.t[d], sf.y, vsum[2 * j + 1]);
+                    }
+                }
+                float* rowbuf = s_row[k & 1];
+                *reinterpret_cast<float4*>(rowbuf + 8 + lane * 8) = make_float4(vsum[0], vsum[1], vsum[2], vsum[3]);
+                *reinterpret_cast<float4*>(rowbuf + 8 + lane * 8 + 4) = make_float4(vsum[4], vsum[5], vsum[6], vsum[7]);
+                __syncwarp();
+                float bwin[24];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(rowbuf + lane * 8 + 4 * j);
+                    bwin[4 * j] = t4.x; bwin[4 * j + 1] = t4.y; bwin[4 * j + 2] = t4.z; bwin[4 * j + 3] = t4.w;
+                }
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float acc = __fmul_rn(taps.t[0], bwin[8 + i]);
+#pragma unroll
+                    for (int d = 1; d <= 7; ++d) acc = __fmaf_rn(taps.t[d], __fadd_rn(bwin[8 + i - d], bwin[8 + i + d]), acc);
+                    o[i] = acc;
+                }
+                const int m = k - 8;   // output row
+                if (writer) {
+                    float* dst = blur_out + (long long)f * plane + (long long)m * w + c0;
+                    if (vec_out) {
+                        __stcg(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+                        __stcg(reinterpret_cast<float4*>(dst + 4), make_float4(o[4], o[5], o[6], o[7]));
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { mn = fminf(mn, o[i]); mx = fmaxf(mx, o[i]); }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (c0 + i >= 0 && c0 + i < w) { dst[i] = o[i]; mn = fminf(mn, o[i]); mx = fmaxf(mx, o[i]); }
+                    }
+                }
+            }
+            slot = (slot + kSsRingRowBytes) & uint32_t(kSsRingBytes - 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { g0[i] = g1[i]; g1[i] = g2[i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0 && mn <= mx) {
+        atomicMin(&mm[f].blur_min, dbl_key(double(mn)));
+        atomicMax(&mm[f].blur_max, dbl_key(double(mx)));
+    }
+}
+
+// sal = float((blur - min) / (max - min + 1e-8)); optional attention raw value + its fp32 min/max.
+// blur is held in fp32 (so min and max are fp32 values): the subtraction is done exactly in fp64, the quotient in fp32
+// (IEEE division) -- within 1 ulp of the reference's fp64 quotient rounded to fp32, without a 30-instruction fp64 divide
+// per pixel (the first version of this kernel ran at 2.4 TB/s because of it).  VEC = 4 pixels per thread.
+template <bool kAttention, int VEC>
 __global__ void __launch_bounds__(kSalThreads)
 k_sal_normalize(const float* __restrict__ blur, const float* __restrict__ x, float* __restrict__ out, long long plane,
                 SalMinMax* __restrict__ mm)
@@ -159,50 +353,86 @@ k_sal_normalize(const float* __restrict__ blur, const float* __restrict__ x, flo
     __shared__ float s_mn[kSalThreads / 32], s_mx[kSalThreads / 32];
     const int f = blockIdx.y;
     const double bmn = key_dbl(mm[f].blur_min), bmx = key_dbl(mm[f].blur_max);
-    const double den = bmx - bmn + 1e-8;
+    const float den = float(bmx - bmn + 1e-8);
     const float* img = x + (long long)f * 3 * plane;
+    const float* bl = blur + (long long)f * plane;
+    float* o = out + (long long)f * plane;
     float mn = INFINITY, mx = -INFINITY;
+    const long long nvec = plane / VEC;
     const long long stride = (long long)gridDim.x * kSalThreads;
-    for (long long i = (long long)blockIdx.x * kSalThreads + threadIdx.x; i < plane; i += stride) {
-        const float s = float((double(blur[(long long)f * plane + i]) - bmn) / den);
-        if (kAttention) {
-            const float lum = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, __ldg(img + i)), __fmul_rn(0.587f, __ldg(img + plane + i))),
-                                        __fmul_rn(0.114f, __ldg(img + 2 * plane + i)));
-            const float a = __fmul_rn(s, __fdiv_rn(1.0f, __fadd_rn(lum, 0.1f)));
-            out[(long long)f * plane + i] = a;
-            mn = fminf(mn, a);
-            mx = fmaxf(mx, a);
+    for (long long i = (long long)blockIdx.x * kSalThreads + threadIdx.x; i < nvec; i += stride) {
+        float b[VEC], r[VEC], g[VEC], bb[VEC], res[VEC];
+        if (VEC == 4) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(bl) + i);
+            b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
+            if (kAttention) {
+                const float4 tr = __ldg(reinterpret_cast<const float4*>(img) + i);
+                const float4 tg = __ldg(reinterpret_cast<const float4*>(img + plane) + i);
+                const float4 tb = __ldg(reinterpret_cast<const float4*>(img + 2 * plane) + i);
+                r[0] = tr.x; r[1] = tr.y; r[2] = tr.z; r[3] = tr.w;
+                g[0] = tg.x; g[1] = tg.y; g[2] = tg.z; g[3] = tg.w;
+                bb[0] = tb.x; bb[1] = tb.y; bb[2] = tb.z; bb[3] = tb.w;
+            }
         } else {
-            out[(long long)f * plane + i] = s;
+            b[0] = bl[i];
+            if (kAttention) { r[0] = __ldg(img + i); g[0] = __ldg(img + plane + i); bb[0] = __ldg(img + 2 * plane + i); }
         }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float sal = __fdiv_rn(float(double(b[k]) - bmn), den);
+            if (kAttention) {
+                const float lum = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r[k]), __fmul_rn(0.587f, g[k])), __fmul_rn(0.114f, bb[k]));
+                const float a = __fmul_rn(sal, __fdiv_rn(1.0f, __fadd_rn(lum, 0.1f)));
+                res[k] = a;
+                mn = fminf(mn, a);
+                mx = fmaxf(mx, a);
+            } else {
+                res[k] = sal;
+            }
+        }
+        if (VEC == 4) reinterpret_cast<float4*>(o)[i] = make_float4(res[0], res[1], res[2], res[3]);
+        else o[i] = res[0];
     }
     if constexpr (kAttention) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int sh = 16; sh > 0; sh >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, sh));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
     }
     if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 1; k < kSalThreads / 32; ++k) { mn = fminf(mn, s_mn[k]); mx = fmaxf(mx, s_mx[k]); }
-        atomicMin(&mm[f].att_min, flt_key(mn));
-        atomicMax(&mm[f].att_max, flt_key(mx));
+        if (mn <= mx) {
+            atomicMin(&mm[f].att_min, flt_key(mn));
+            atomicMax(&mm[f].att_max, flt_key(mx));
+        }
     }
     }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(kSalThreads)
 k_att_normalize(float* __restrict__ att, long long plane, const SalMinMax* __restrict__ mm)
 {
     const int f = blockIdx.y;
     const float mn = key_flt(mm[f].att_min), mx = key_flt(mm[f].att_max);
     const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-8f);
+    const long long nvec = plane / VEC;
     const long long stride = (long long)gridDim.x * kSalThreads;
-    for (long long i = (long long)blockIdx.x * kSalThreads + threadIdx.x; i < plane; i += stride) {
-        float* p = att + (long long)f * plane + i;
-        *p = __fdiv_rn(__fsub_rn(*p, mn), den);
+    float* base = att + (long long)f * plane;
+    for (long long i = (long long)blockIdx.x * kSalThreads + threadIdx.x; i < nvec; i += stride) {
+        if (VEC == 4) {
+            float4 v = reinterpret_cast<float4*>(base)[i];
+            v.x = __fdiv_rn(__fsub_rn(v.x, mn), den);
+            v.y = __fdiv_rn(__fsub_rn(v.y, mn), den);
+            v.z = __fdiv_rn(__fsub_rn(v.z, mn), den);
+            v.w = __fdiv_rn(__fsub_rn(v.w, mn), den);
+            reinterpret_cast<float4*>(base)[i] = v;
+        } else {
+            base[i] = __fdiv_rn(__fsub_rn(base[i], mn), den);
+        }
     }
 }
 
@@ -217,9 +447,24 @@ static GaussTaps sal_taps()
     return g;
 }
 
+static GaussTapsF sal_taps_f()
+{
+    const GaussTaps g = sal_taps();
+    GaussTapsF r;
+    for (int d = 0; d < 8; ++d) r.t[d] = float(g.t[d]);
+    return r;
+}
+
 static size_t sal_ws_bytes(int n, int h, int w)
 {
     return align_up(size_t(n) * sizeof(SalMinMax), 256) + align_up(size_t(n) * h * w * sizeof(float), 256);
+}
+
+// development switch: UPR_SAL_VARIANT=1 selects the first-generation tile kernel (fp64 blur) for A/B runs
+static int sal_variant()
+{
+    static const int v = [] { const char* e = std::getenv("UPR_SAL_VARIANT"); return e ? std::atoi(e) : 0; }();
+    return v;
 }
 
 // mode 0: saliency only -> out ; mode 1: attention -> out (saliency is an internal temporary)
@@ -229,30 +474,49 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
     if (n == 0) return UPR_OK;
     if (!x || !out || !ws) return UPR_E_NULL;
     if (ws_bytes < sal_ws_bytes(n, h, w) || (reinterpret_cast<uintptr_t>(ws) & 255u)) return UPR_E_WORKSPACE;
-    static const GaussTaps taps = sal_taps();
     auto* mm = static_cast<SalMinMax*>(ws);
     auto* blur = reinterpret_cast<float*>(static_cast<unsigned char*>(ws) + align_up(size_t(n) * sizeof(SalMinMax), 256));
     const long long plane = (long long)h * w;
     k_sal_reset<<<(n + 127) / 128, 128, 0, s>>>(mm, n);
     UPR_LAUNCH_CHECK();
-    const int tiles_x = (w + kSalTile - 1) / kSalTile, tiles_y = (h + kSalTile - 1) / kSalTile;
-    const size_t smem = size_t(kRH) * kSalTile * sizeof(double) + size_t(kLW) * kLW * 2 + size_t(kGW) * kGW;
-    static bool attr_set = false;
-    if (!attr_set) {
-        UPR_CUDA_TRY(cudaFuncSetAttribute(k_saliency_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        attr_set = true;
+    if (sal_variant() & 1) {
+        static const GaussTaps taps = sal_taps();
+        const int tiles_x = (w + kSalTile - 1) / kSalTile, tiles_y = (h + kSalTile - 1) / kSalTile;
+        const size_t smem = size_t(kRH) * kSalTile * sizeof(double) + size_t(kLW) * kLW * 2 + size_t(kGW) * kGW;
+        static bool attr_set = false;
+        if (!attr_set) {
+            UPR_CUDA_TRY(cudaFuncSetAttribute(k_saliency_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            attr_set = true;
+        }
+        k_saliency_blur<<<dim3(tiles_x * tiles_y, n), kSalThreads, smem, s>>>(x, h, w, tiles_x, blur, mm, taps);
+    } else {
+        static const GaussTapsF taps = sal_taps_f();
+        const int bands = (w + kSsBandCols - 1) / kSsBandCols;
+        // one warp per (band, row segment, frame): aim at ~6 warps per resident slot (20 warps/SM) for balance, but keep
+        // segments >= 64 rows (16 of every segment's rows are re-computed halo)
+        const long long slots = 20LL * kNumSMsB200;
+        long long nseg = (6 * slots + (long long)n * bands - 1) / ((long long)n * bands);
+        nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
+        const int seg_rows = int((h + nseg - 1) / nseg);
+        const int segs = (h + seg_rows - 1) / seg_rows;
+        if ((long long)bands * segs > 0x7fffffffLL) return UPR_E_SHAPE;
+        k_saliency_stream<<<dim3(unsigned(bands * segs), n), 32, 0, s>>>(x, h, w, bands, seg_rows, blur, mm, taps);
     }
-    k_saliency_blur<<<dim3(tiles_x * tiles_y, n), kSalThreads, smem, s>>>(x, h, w, tiles_x, blur, mm, taps);
     UPR_LAUNCH_CHECK();
-    const int parts = int(std::max<long long>(1, std::min<long long>((plane + kSalThreads * 4 - 1) / (kSalThreads * 4),
-                                                                     (8LL * kNumSMsB200 + n - 1) / n)));
+    const bool v4 = plane % 4 == 0 && aligned16(x) && aligned16(out);
+    const long long work = v4 ? plane / 4 : plane;
+    const int parts = int(std::max<long long>(1, std::min<long long>((work + kSalThreads * 2 - 1) / (kSalThreads * 2),
+                                                                     (16LL * kNumSMsB200 + n - 1) / n)));
     if (mode == 0) {
-        k_sal_normalize<false><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
+        if (v4) k_sal_normalize<false, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
+        else k_sal_normalize<false, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
         UPR_LAUNCH_CHECK();
     } else {
-        k_sal_normalize<true><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
+        if (v4) k_sal_normalize<true, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
+        else k_sal_normalize<true, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
         UPR_LAUNCH_CHECK();
-        k_att_normalize<<<dim3(parts, n), kSalThreads, 0, s>>>(out, plane, mm);
+        if (v4) k_att_normalize<4><<<dim3(parts, n), kSalThreads, 0, s>>>(out, plane, mm);
+        else k_att_normalize<1><<<dim3(parts, n), kSalThreads, 0, s>>>(out, plane, mm);
         UPR_LAUNCH_CHECK();
     }
     return UPR_OK;

@@ -128,8 +128,10 @@ def test_content_golden(native, golden, small_cases):
         assert abs(float(att.astype(np.float64).mean()) - rec["att_mean"]) <= 1e-7
         assert int(att.argmax()) == rec["att_argmax"] and int(sal.argmax()) == rec["sal_argmax"]
         if f"sal_{rec['seed']}" in small_cases:
-            np.testing.assert_allclose(sal[0, 0], small_cases[f"sal_{rec['seed']}"], rtol=0, atol=2e-7)
-            np.testing.assert_allclose(att[0, 0], small_cases[f"att_{rec['seed']}"], rtol=0, atol=4e-7)
+            # fp32 blur (the reference blurs in fp64 and rounds the normalised map to fp32): a few 1e-7 absolute on [0,1]
+            # maps; the stated bound for a6/a7 is 1e-4 relative
+            np.testing.assert_allclose(sal[0, 0], small_cases[f"sal_{rec['seed']}"], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(att[0, 0], small_cases[f"att_{rec['seed']}"], rtol=0, atol=2e-6)
 
 
 @pytest.mark.parametrize("shape,kind", [((64, 96), "uniform"), ((67, 93), "dark"), ((130, 70), "ramp"), ((9, 11), "uniform"),
