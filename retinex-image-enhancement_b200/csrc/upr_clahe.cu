@@ -1013,8 +1013,8 @@ static bool valid_shape(int n, int h, int w, int tiles_x, int tiles_y)
 // map kernel (k_map_vec), bit 1 = first-generation histogram kernel (k_hist_lab_vec).  Same results either way.
 static int variant()
 {
-    static const int v = [] { const char* e = std::getenv("UPR_CLAHE_VARIANT"); return e ? std::atoi(e) : 0; }();
-    return v;
+    const char* e = std::getenv("UPR_CLAHE_VARIANT");   // read per call so that tests can A/B within one process
+    return e ? std::atoi(e) : 0;
 }
 
 // raw tile coordinate of OpenCV's interpolation: floor(p * inv - 0.5f), fp32, separately rounded

@@ -364,7 +364,16 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
     }
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
 
+    float4 N[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) N[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    auto load_rows = [&](int q, int c) {
+        const float* p = img + c * plane + (long long)(4 * q) * w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) N[j] = __ldg(reinterpret_cast<const float4*>(p + (long long)j * w));
+    };
     if (r0 < h) {
+        if (max(q0 - 1, 0) < Q) load_rows(max(q0 - 1, 0), 0);
         for (int q = max(q0 - 1, 0); q <= q1; ++q) {
             const bool have = q < Q;                 // image rows 4q .. 4q+3 exist
             const bool inner = q >= q0 && q < q1;    // their statistics belong to this segment
@@ -373,18 +382,13 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float wsum = c == 0 ? 1.299f : (c == 1 ? 1.587f : 1.114f);   // 1 + luma weight
+                // software pipeline: the four rows of the NEXT (step, channel) are requested before this one is reduced
+                // (ncu: 54 % of the stall samples of the un-pipelined kernel sat on the first use of these loads)
                 float R[4][4];
-                if (have) {
-                    const float* p = img + c * plane + (long long)(4 * q) * w;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(p + (long long)j * w));
-                        R[j][0] = v.x; R[j][1] = v.y; R[j][2] = v.z; R[j][3] = v.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) R[j][0] = R[j][1] = R[j][2] = R[j][3] = 0.0f;
-                }
+                for (int j = 0; j < 4; ++j) { R[j][0] = N[j].x; R[j][1] = N[j].y; R[j][2] = N[j].z; R[j][3] = N[j].w; }
+                if (c < 2) { if (have) load_rows(q, c + 1); }
+                else if (q + 1 <= q1 && q + 1 < Q) load_rows(q + 1, 0);
                 // 2x2 block sums (= 4 x half-resolution pixels) and the centre 2x2 (= 4 x quarter-resolution pixel)
                 float B0[2], B1[2];
                 B0[0] = __fadd_rn(__fadd_rn(R[0][0], R[0][1]), __fadd_rn(R[1][0], R[1][1]));
@@ -533,7 +537,9 @@ static int ms_run(const float* x, int n, int h, int w, float* means, float* gain
     const bool fused = allow_fused && !want_feat && h % 4 == 0 && w % 4 == 0 && aligned16(x) &&
                        (long long)tiles_x * tiles_y <= kMsMaxParts * 16LL;
     if (fused) {
-        static const int variant = [] { const char* e = std::getenv("UPR_MS_VARIANT"); return e ? std::atoi(e) : 0; }();
+        // development switch, read per call: UPR_MS_VARIANT=1 selects the first-generation tile kernel (A/B runs, tests)
+        const char* ev = std::getenv("UPR_MS_VARIANT");
+        const int variant = ev ? std::atoi(ev) : 0;
         if (!(variant & 1) && h / 4 >= 2 && w / 4 >= 2) {
             // streaming kernel: one warp per (band, row segment, frame); ~6 warps per resident slot, segments >= 64 rows
             const int bands = (w + kMsBandCols - 1) / kMsBandCols;

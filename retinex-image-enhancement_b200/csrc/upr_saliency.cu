@@ -196,7 +196,7 @@ k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_
                   SalMinMax* __restrict__ mm, const GaussTapsF taps)
 {
     __shared__ __align__(16) unsigned char s_ring[kSsRingBytes];
-    __shared__ __align__(16) float s_row[2][32 * kSsLaneCols + 16];
+    __shared__ __align__(16) float s_row[2][2 * 34 * 4];
 
     const int lane = threadIdx.x;
     const int band = blockIdx.x % bands, seg = blockIdx.x / bands;
@@ -217,15 +217,22 @@ k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_
     float mn = INFINITY, mx = -INFINITY;
     uint32_t slot = 0;   // byte offset of the ring row that receives the next |lap| row
 
+    float nr[8], ng[8], nb[8];
+    auto load_row = [&](int k) {
+        const float* rowp = img + (long long)reflect101_s(k, h) * w;
+        ss_load8(rowp, c0, w, vec, nr);
+        ss_load8(rowp + plane, c0, w, vec, ng);
+        ss_load8(rowp + 2 * plane, c0, w, vec, nb);
+    };
+    load_row(r0 - 8);
     for (int k = r0 - 8; k < r1 + 8; ++k) {
         // ---- gray(k) ----
         {
-            const int gy = reflect101_s(k, h);
-            const float* rowp = img + (long long)gy * w;
+            // software pipeline: row k+1 is requested before row k is converted
             float r[8], g[8], b[8];
-            ss_load8(rowp, c0, w, vec, r);
-            ss_load8(rowp + plane, c0, w, vec, g);
-            ss_load8(rowp + 2 * plane, c0, w, vec, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { r[i] = nr[i]; g[i] = ng[i]; b[i] = nb[i]; }
+            if (k + 1 < r1 + 8) load_row(k + 1);
             uint32_t m = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) m = __vimax3_u32(m, __float_as_uint(r[i]), __vimax3_u32(__float_as_uint(g[i]), __float_as_uint(b[i]), 0u));
@@ -292,15 +299,22 @@ k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_
                         vsum[2 * j + 1] = __fmaf_rn(taps.t[d], sf.y, vsum[2 * j + 1]);
                     }
                 }
-                float* rowbuf = s_row[k & 1];
-                *reinterpret_cast<float4*>(rowbuf + 8 + lane * 8) = make_float4(vsum[0], vsum[1], vsum[2], vsum[3]);
-                *reinterpret_cast<float4*>(rowbuf + 8 + lane * 8 + 4) = make_float4(vsum[4], vsum[5], vsum[6], vsum[7]);
+                // exchange buffer: first halves (columns 0..3) of all lanes, then second halves -- every 128-bit access of
+                // the warp is contiguous (an interleaved [lane][8] layout costs 8 wavefronts per access instead of 4)
+                float4* rowA = reinterpret_cast<float4*>(s_row[k & 1]) + 1;      // slot -1 and slot 32 are padding
+                float4* rowB = rowA + 34;
+                rowA[lane] = make_float4(vsum[0], vsum[1], vsum[2], vsum[3]);
+                rowB[lane] = make_float4(vsum[4], vsum[5], vsum[6], vsum[7]);
                 __syncwarp();
                 float bwin[24];
+                {
+                    const float4 t0 = rowA[lane - 1], t1 = rowB[lane - 1], t4 = rowA[lane + 1], t5 = rowB[lane + 1];
+                    bwin[0] = t0.x; bwin[1] = t0.y; bwin[2] = t0.z; bwin[3] = t0.w;
+                    bwin[4] = t1.x; bwin[5] = t1.y; bwin[6] = t1.z; bwin[7] = t1.w;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(rowbuf + lane * 8 + 4 * j);
-                    bwin[4 * j] = t4.x; bwin[4 * j + 1] = t4.y; bwin[4 * j + 2] = t4.z; bwin[4 * j + 3] = t4.w;
+                    for (int i = 0; i < 8; ++i) bwin[8 + i] = vsum[i];
+                    bwin[16] = t4.x; bwin[17] = t4.y; bwin[18] = t4.z; bwin[19] = t4.w;
+                    bwin[20] = t5.x; bwin[21] = t5.y; bwin[22] = t5.z; bwin[23] = t5.w;
                 }
                 float o[8];
 #pragma unroll
@@ -463,8 +477,8 @@ static size_t sal_ws_bytes(int n, int h, int w)
 // development switch: UPR_SAL_VARIANT=1 selects the first-generation tile kernel (fp64 blur) for A/B runs
 static int sal_variant()
 {
-    static const int v = [] { const char* e = std::getenv("UPR_SAL_VARIANT"); return e ? std::atoi(e) : 0; }();
-    return v;
+    const char* e = std::getenv("UPR_SAL_VARIANT");   // read per call so that tests can A/B within one process
+    return e ? std::atoi(e) : 0;
 }
 
 // mode 0: saliency only -> out ; mode 1: attention -> out (saliency is an internal temporary)

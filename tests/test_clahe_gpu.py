@@ -133,3 +133,31 @@ def test_full_size_properties(native):
         assert torch.equal(native.clahe_lab(x[i:i + 1].clone()), out[i:i + 1])
     assert float(out[3].std()) == 0.0
     assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+
+
+# ---- kernel generations ----------------------------------------------------------------------------------
+def test_kernel_generations_bit_identical(native, monkeypatch):
+    """UPR_CLAHE_VARIANT selects the first-generation kernels (k_hist_lab_vec / k_map_vec); the production pair
+    (k_hist_lab_vec2 + k_map_vec5) must give the same Lab planes, histograms, LUTs and output, bit for bit, on the named
+    shapes, on a batch, and on inputs that leave [0,1] (slow quantisation path of the new histogram kernel)."""
+    rng = np.random.default_rng(7)
+    cases = [O.kat_input(3, 1080, 1920, "uniform"), O.kat_input(6, 2160, 3840, "dark"),
+             np.concatenate([O.kat_input(20 + i, 400, 600, k) for i, k in enumerate(["uniform", "dark", "ramp", "const"])]),
+             (rng.random((2, 3, 240, 320), dtype=np.float32) * 3.0 - 1.0).astype(np.float32)]
+    cases[3][0, 0, 5, 7] = np.nan
+    cases[3][1, 2, 9, 3] = np.inf
+    for x in cases:
+        res = {}
+        for v in ("0", "3"):
+            monkeypatch.setenv("UPR_CLAHE_VARIANT", v)
+            res[v] = run_clahe(native, x)
+        for a, b in zip(res["0"], res["3"]):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,h,w,tiles", [(1, 1080, 1920, (8, 8)), (3, 480, 640, (8, 8)), (2, 256, 1024, (4, 2)), (5, 64, 64, (8, 8)),
+                                          (1, 2160, 3840, (16, 16)), (2, 96, 2048, (1, 3))])
+def test_persistent_map_kernel_shapes(native, n, h, w, tiles):
+    """Work-queue geometry of the persistent map kernel: cells narrower/wider than the CTA, single-row cells, strips."""
+    x = np.concatenate([O.kat_input(300 + i, h, w, ("uniform", "dark", "ramp")[i % 3]) for i in range(n)])
+    compare(native, x, 2.0, tiles)

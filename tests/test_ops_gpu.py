@@ -249,3 +249,50 @@ def test_clahe_host_entry(native):
         ref = O.clahe_lab(xs[i])
         assert np.array_equal(out[i].numpy(), ref[0]) and np.array_equal(out_pageable[i].numpy(), ref[0])
     assert native.lib().upr_host_pool_release() == 0
+
+
+# ---- streaming kernels vs the first-generation tile kernels ----------------------------------------------
+@pytest.mark.parametrize("n,h,w", [(1, 2160, 3840), (2, 1080, 1920), (3, 400, 600), (1, 64, 120), (1, 8, 8), (2, 68, 244), (1, 128, 4096)])
+def test_multiscale_stream_vs_tile_kernel(native, monkeypatch, n, h, w):
+    """k_ms_stream (warp per band/segment) against k_ms_fused (tile kernel, UPR_MS_VARIANT=1) and, for small shapes, the oracle:
+    band edges (w not a multiple of 120), segment edges, one-sided differences on all four borders, batches."""
+    x = np.concatenate([O.kat_input(500 + i, h, w, ("uniform", "dark", "ramp")[i % 3]) for i in range(n)])
+    xd = dev(x)
+    monkeypatch.setenv("UPR_MS_VARIANT", "0")
+    m0, g0 = native.multiscale_stats(xd)
+    monkeypatch.setenv("UPR_MS_VARIANT", "1")
+    m1, g1 = native.multiscale_stats(xd)
+    np.testing.assert_allclose(m0.cpu().numpy(), m1.cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(g0.cpu().numpy(), g1.cpu().numpy(), rtol=2e-7)
+    if h * w <= 400 * 600:
+        for i in range(n):
+            m_ref, f_ref = O.multiscale_means(x[i:i + 1])
+            np.testing.assert_allclose(m0.cpu().numpy()[i], m_ref, rtol=2e-6)
+            assert abs(float(g0[i]) - f_ref) <= 2e-7
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 2160, 3840), (2, 1080, 1920), (2, 70, 250), (1, 33, 481), (1, 3, 9), (1, 600, 17), (1, 20, 243)])
+def test_saliency_stream_vs_tile_kernel(native, monkeypatch, n, h, w):
+    """k_saliency_stream (fp32, vertical-then-horizontal) against k_saliency_blur (fp64 tile kernel, UPR_SAL_VARIANT=1):
+    band edges (w not a multiple of 240, lanes that straddle the right border), reflect-101 on narrow/short images,
+    row segments, batches.  Same bound as against the oracle."""
+    x = np.concatenate([O.kat_input(600 + i, h, w, ("uniform", "dark")[i % 2]) for i in range(n)])
+    xd = dev(x)
+    monkeypatch.setenv("UPR_SAL_VARIANT", "0")
+    s0, a0 = native.saliency(xd).cpu().numpy(), native.attention(xd).cpu().numpy()
+    monkeypatch.setenv("UPR_SAL_VARIANT", "1")
+    s1, a1 = native.saliency(xd).cpu().numpy(), native.attention(xd).cpu().numpy()
+    np.testing.assert_allclose(s0, s1, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(a0, a1, rtol=0, atol=2e-6)
+    if h * w <= 70 * 250:
+        for i in range(n):
+            np.testing.assert_allclose(s0[i], O.saliency(x[i:i + 1])[0], rtol=0, atol=1e-6)
+
+
+def test_saliency_out_of_range_inputs(native):
+    """Values outside [0,1], NaN and inf take the exact numpy-semantics quantisation path of the streaming kernel."""
+    rng = np.random.default_rng(9)
+    x = (rng.random((1, 3, 40, 300), dtype=np.float32) * 4.0 - 1.5).astype(np.float32)
+    x[0, 1, 3, 4] = np.nan
+    x[0, 2, 30, 250] = -np.inf
+    np.testing.assert_allclose(native.saliency(dev(x)).cpu().numpy(), O.saliency(x), rtol=0, atol=1e-6)
