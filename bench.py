@@ -127,7 +127,10 @@ def make_frames(torch, n, h, w, seed, device):
 
 
 def event_time_ms(torch, fn, iters):
-    """Per-iteration CUDA-event durations (ms) of fn on the current stream."""
+    """Per-iteration CUDA-event durations (ms) of fn on the current stream, after two untimed calls (allocator, caches)."""
+    fn()
+    fn()
+    torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     for s, e in evs:
         s.record()
@@ -303,7 +306,7 @@ def bench_c2(torch, dist, rank, world, local, args):
     achieved = alg_bytes / (dom_ms / 1e3) / 1e9
     op_achieved = 24.0 * px / (ms_step / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": args.traffic, "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
+                "traffic": args.traffic if args.traffic is not None else committed_traffic(dom_name), "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernels_ms": {"k_hist_lab_vec2": k1, "k_map_vec5": k3},
                 "op": {"algorithmic_bytes_per_px": 24, "achieved": op_achieved, "frac": op_achieved / peak,
@@ -312,7 +315,7 @@ def bench_c2(torch, dist, rank, world, local, args):
     # the Retinex arithmetic of the same configuration (a8, models/model.py:405-413,442), reported separately:
     # R = x / (illu + 1e-6), enh = R*e + (1-R)*e^2 without materialising R: 12 + 4 + 12 read, 12 written = 40 B/px
     illu = (x[:, :1] * 0.5 + 0.25).contiguous()
-    k8 = statistics.mean(event_time_ms(torch, lambda: native.retinex_recombine(x, illu, out, want_reflectance=False), 5))
+    k8 = statistics.median(event_time_ms(torch, lambda: native.retinex_recombine(x, illu, out, want_reflectance=False), 9))
     roofline["retinex_recombine"] = {"kernel": "k_recombine_vec", "kernel_ms": k8, "algorithmic_bytes_per_px": 40,
                                      "achieved": 40.0 * px / (k8 / 1e3) / 1e9, "frac": 40.0 * px / (k8 / 1e3) / 1e9 / peak}
     del illu
@@ -484,8 +487,6 @@ def main():
     import __graft_entry__ as entry
     entry.ensure_built()
     dist, rank, world, local = dist_setup(torch, args.gpus)
-    if args.traffic is None:
-        args.traffic = committed_traffic()
     try:
         line = WORKLOADS[args.workload](torch, dist, rank, world, local, args)
         if rank == 0:
@@ -496,11 +497,14 @@ def main():
     return 0
 
 
-def committed_traffic():
-    """dram bytes per launch of the dominant kernel, read from the committed ncu summary (profiles/), or None."""
+def committed_traffic(kernel=None):
+    """dram bytes per launch of a kernel (default: the dominant one), read from the committed ncu summary (profiles/), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return float(json.load(f)["dominant_kernel_dram_bytes_per_launch"])
+            d = json.load(f)
+        if kernel is not None and kernel in d.get("kernels", {}):
+            return float(d["kernels"][kernel])
+        return float(d["dominant_kernel_dram_bytes_per_launch"])
     except Exception:
         return None
 
