@@ -125,6 +125,12 @@ UPR_API int upr_attention_f32(const float* x_nchw, int n, int h, int w, float* a
                               size_t workspace_bytes, upr_stream_t stream);
 UPR_API int upr_attention_apply_f32(const float* enh, const float* att_n1hw, float* out, int n, int c, int h, int w,
                                     upr_stream_t stream);
+/* The whole of apply_content_aware_enhancement's arithmetic after the CNN (content_aware.py:105-120) in three passes:
+ * saliency blur -> raw attention + its min/max -> out = clamp(enh * (1 + 0.2*att), 0, 1).  att_n1hw may be NULL (the
+ * reference discards the map); enh/out are [n][3][h][w].  Same workspace as upr_saliency_f32.  Results are identical to
+ * upr_attention_f32 followed by upr_attention_apply_f32. */
+UPR_API int upr_content_aware_apply_f32(const float* x_nchw, const float* enh_nchw, float* out_nchw, float* att_n1hw, int n,
+                                        int h, int w, void* workspace, size_t workspace_bytes, upr_stream_t stream);
 
 /* ---- a8: Retinex decomposition / recombination ------------------------------------------
  * models/model.py:405-413 (R = x / (illu + eps), illu broadcast over the 3 channels) and :442

@@ -450,6 +450,59 @@ k_att_normalize(float* __restrict__ att, long long plane, const SalMinMax* __res
     }
 }
 
+// a7 in one pass over the raw attention: att = (raw - min) / (max - min + 1e-8); out = clamp(enh * (1 + 0.2 att), 0, 1)
+// (content_aware.py:88-90 and :119-120).  One item = 4 pixels of one frame, all three channels: the raw attention is read
+// once instead of being normalised in place (8 B/px) and then re-read per channel by the gain kernel.
+__device__ __forceinline__ float sal_clamp01_keep_nan(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+
+template <bool kWriteAtt, int VEC>
+__global__ void __launch_bounds__(kSalThreads)
+k_att_gain(const float* __restrict__ raw, const float* __restrict__ enh, float* __restrict__ out, float* __restrict__ att_out,
+           long long plane, const SalMinMax* __restrict__ mm)
+{
+    const int f = blockIdx.y;
+    const float mn = key_flt(mm[f].att_min), mx = key_flt(mm[f].att_max);
+    const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-8f);
+    const float* r = raw + (long long)f * plane;
+    const float* e = enh + (long long)f * 3 * plane;
+    float* o = out + (long long)f * 3 * plane;
+    float* ao = kWriteAtt ? att_out + (long long)f * plane : nullptr;
+    const long long nvec = plane / VEC;
+    const long long stride = (long long)gridDim.x * kSalThreads;
+    for (long long i = (long long)blockIdx.x * kSalThreads + threadIdx.x; i < nvec; i += stride) {
+        float a[VEC], g[VEC];
+        if (VEC == 4) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(r) + i);
+            a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+        } else {
+            a[0] = r[i];
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            a[k] = __fdiv_rn(__fsub_rn(a[k], mn), den);
+            g[k] = __fadd_rn(1.0f, __fmul_rn(0.2f, a[k]));
+        }
+        if (kWriteAtt) {
+            if (VEC == 4) reinterpret_cast<float4*>(ao)[i] = make_float4(a[0], a[1], a[2], a[3]);
+            else ao[i] = a[0];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (VEC == 4) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(e + c * plane) + i);
+                float4 w;
+                w.x = sal_clamp01_keep_nan(__fmul_rn(v.x, g[0]));
+                w.y = sal_clamp01_keep_nan(__fmul_rn(v.y, g[1]));
+                w.z = sal_clamp01_keep_nan(__fmul_rn(v.z, g[2]));
+                w.w = sal_clamp01_keep_nan(__fmul_rn(v.w, g[3]));
+                __stcs(reinterpret_cast<float4*>(o + c * plane) + i, w);
+            } else {
+                o[c * plane + i] = sal_clamp01_keep_nan(__fmul_rn(e[c * plane + i], g[0]));
+            }
+        }
+    }
+}
+
 static GaussTaps sal_taps()
 {
     // cv2.getGaussianKernel(15, sigma=0.3*((15-1)*0.5-1)+0.8 = 2.6), fp64
@@ -481,12 +534,14 @@ static int sal_variant()
     return e ? std::atoi(e) : 0;
 }
 
-// mode 0: saliency only -> out ; mode 1: attention -> out (saliency is an internal temporary)
-static int sal_run(int mode, const float* x, int n, int h, int w, float* out, void* ws, size_t ws_bytes, cudaStream_t s)
+// mode 0: saliency only -> out ; mode 1: attention -> out (saliency is an internal temporary);
+// mode 2: out = clamp(enh * (1 + 0.2 attention), 0, 1) with the attention map optional (att_out)
+static int sal_run(int mode, const float* x, int n, int h, int w, float* out, void* ws, size_t ws_bytes, cudaStream_t s,
+                   const float* enh = nullptr, float* att_out = nullptr)
 {
     if (n < 0 || n > 65535 || h <= 0 || w <= 0) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
-    if (!x || !out || !ws) return UPR_E_NULL;
+    if (!x || !out || !ws || (mode == 2 && !enh)) return UPR_E_NULL;
     if (ws_bytes < sal_ws_bytes(n, h, w) || (reinterpret_cast<uintptr_t>(ws) & 255u)) return UPR_E_WORKSPACE;
     auto* mm = static_cast<SalMinMax*>(ws);
     auto* blur = reinterpret_cast<float*>(static_cast<unsigned char*>(ws) + align_up(size_t(n) * sizeof(SalMinMax), 256));
@@ -517,13 +572,26 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
         k_saliency_stream<<<dim3(unsigned(bands * segs), n), 32, 0, s>>>(x, h, w, bands, seg_rows, blur, mm, taps);
     }
     UPR_LAUNCH_CHECK();
-    const bool v4 = plane % 4 == 0 && aligned16(x) && aligned16(out);
+    const bool v4 = plane % 4 == 0 && aligned16(x) && aligned16(out) && (mode != 2 || (aligned16(enh) && (!att_out || aligned16(att_out))));
     const long long work = v4 ? plane / 4 : plane;
     const int parts = int(std::max<long long>(1, std::min<long long>((work + kSalThreads * 2 - 1) / (kSalThreads * 2),
                                                                      (16LL * kNumSMsB200 + n - 1) / n)));
     if (mode == 0) {
         if (v4) k_sal_normalize<false, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
         else k_sal_normalize<false, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
+        UPR_LAUNCH_CHECK();
+    } else if (mode == 2) {
+        // raw attention over the blur plane in place (each element is read and written by the same thread)
+        if (v4) k_sal_normalize<true, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, blur, plane, mm);
+        else k_sal_normalize<true, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, blur, plane, mm);
+        UPR_LAUNCH_CHECK();
+        if (att_out) {
+            if (v4) k_att_gain<true, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, enh, out, att_out, plane, mm);
+            else k_att_gain<true, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, enh, out, att_out, plane, mm);
+        } else {
+            if (v4) k_att_gain<false, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, enh, out, nullptr, plane, mm);
+            else k_att_gain<false, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, enh, out, nullptr, plane, mm);
+        }
         UPR_LAUNCH_CHECK();
     } else {
         if (v4) k_sal_normalize<true, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
@@ -556,6 +624,13 @@ int upr_attention_f32(const float* x_nchw, int n, int h, int w, float* att_n1hw,
                       upr_stream_t stream)
 {
     return upr::sal_run(1, x_nchw, n, h, w, att_n1hw, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int upr_content_aware_apply_f32(const float* x_nchw, const float* enh_nchw, float* out_nchw, float* att_n1hw, int n, int h,
+                                int w, void* workspace, size_t workspace_bytes, upr_stream_t stream)
+{
+    return upr::sal_run(2, x_nchw, n, h, w, out_nchw, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), enh_nchw,
+                        att_n1hw);
 }
 
 }  // extern "C"

@@ -34,7 +34,7 @@ class ContentAwareEnhancer:
 
     def apply_content_aware_enhancement(self, model, image_tensor, device):
         image_tensor = _to_device(_as_batch(image_tensor), device)
-        attention_map = native.attention(image_tensor)
         with torch.no_grad():
             enhanced_img, _reflectance, illu_map = model(image_tensor)
-        return native.attention_apply(enhanced_img, attention_map), illu_map
+        # attention map + gain + clamp in three passes over the frame (the map itself is not materialised)
+        return native.content_aware_apply(image_tensor, enhanced_img.contiguous()), illu_map

@@ -67,6 +67,8 @@ def _declare(lib):
     lib.upr_attention_f32.argtypes = [vp, i32, i32, i32, vp, vp, sz, vp]
     lib.upr_attention_apply_f32.restype = i32
     lib.upr_attention_apply_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.upr_content_aware_apply_f32.restype = i32
+    lib.upr_content_aware_apply_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
     lib.upr_retinex_recombine_f32.restype = i32
     lib.upr_retinex_recombine_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
     lib.upr_retinex_decompose_f32.restype = i32
@@ -337,6 +339,24 @@ def attention_apply(enh: torch.Tensor, att: torch.Tensor, out: Optional[torch.Te
 # ------------------------------------------------------------------------------------------------
 # a8: Retinex decomposition / recombination
 # ------------------------------------------------------------------------------------------------
+def content_aware_apply(x: torch.Tensor, enh: torch.Tensor, out: Optional[torch.Tensor] = None, want_attention: bool = False):
+    """clamp(enh * (1 + 0.2 * attention(x)), 0, 1) in three passes (upr_content_aware_apply_f32); returns out, or
+    (out, attention) with want_attention.  Identical to attention() followed by attention_apply()."""
+    x = _require_cuda_f32(x, "x")
+    enh = _require_cuda_f32(enh, "enh")
+    n, c, h, w = x.shape
+    if c != 3 or enh.shape != x.shape:
+        raise ValueError("expected x, enh [N,3,H,W]")
+    out = torch.empty_like(enh) if out is None else out
+    att = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device) if want_attention else None
+    L = lib()
+    with torch.cuda.device(x.device):
+        ws = workspace(L.upr_saliency_workspace_bytes(n, h, w), x.device)
+        check(L.upr_content_aware_apply_f32(x.data_ptr(), enh.data_ptr(), out.data_ptr(), att.data_ptr() if att is not None else None,
+                                            n, h, w, ws.data_ptr(), ws.numel(), _stream()), "upr_content_aware_apply_f32")
+    return (out, att) if want_attention else out
+
+
 def retinex_recombine(x: torch.Tensor, illu: torch.Tensor, e: torch.Tensor, want_reflectance: bool = True,
                       eps: float = 1e-6):
     """(reflectance | None, enhanced) for x,e [N,3,H,W] and illu [N,1,H,W]."""

@@ -296,3 +296,15 @@ def test_saliency_out_of_range_inputs(native):
     x[0, 1, 3, 4] = np.nan
     x[0, 2, 30, 250] = -np.inf
     np.testing.assert_allclose(native.saliency(dev(x)).cpu().numpy(), O.saliency(x), rtol=0, atol=1e-6)
+
+
+def test_content_aware_apply_fused(native):
+    """upr_content_aware_apply_f32 == upr_attention_f32 followed by upr_attention_apply_f32, bit for bit (vector and scalar paths)."""
+    for h, w in ((96, 160), (33, 51)):
+        xs = np.concatenate([O.kat_input(700 + i, h, w, k) for i, k in enumerate(["uniform", "dark", "ramp"])])
+        enh = np.random.default_rng(701).random((3, 3, h, w), dtype=np.float32) * 1.3
+        att = native.attention(dev(xs))
+        ref = native.attention_apply(dev(enh), att)
+        out, att2 = native.content_aware_apply(dev(xs), dev(enh), want_attention=True)
+        assert torch.equal(out, ref) and torch.equal(att2, att)
+        assert torch.equal(native.content_aware_apply(dev(xs), dev(enh)), ref)
