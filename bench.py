@@ -318,7 +318,15 @@ def bench_c2(torch, dist, rank, world, local, args):
     k8 = statistics.median(event_time_ms(torch, lambda: native.retinex_recombine(x, illu, out, want_reflectance=False), 9))
     roofline["retinex_recombine"] = {"kernel": "k_recombine_vec", "kernel_ms": k8, "algorithmic_bytes_per_px": 40,
                                      "achieved": 40.0 * px / (k8 / 1e3) / 1e9, "frac": 40.0 * px / (k8 / 1e3) / 1e9 / peak}
-    del illu
+    # the enhance path after the CNN in ONE call (upr_retinex_clahe_f32): recombination in the registers of the histogram
+    # kernel + CLAHE; 40 B/px (x 12 + illu 4 + e 12 read, out 12 written) instead of 64 B/px for the two ops back to back
+    e_map = torch.rand((n, 3, h, w), device=dev, generator=torch.Generator(device=dev).manual_seed(7000 + rank))
+    kf = statistics.median(event_time_ms(torch, lambda: native.retinex_clahe(x, illu, e_map, out=out), 9))
+    roofline["fused_enhance"] = {"api": "upr_retinex_clahe_f32 (k_hist_lab_vec2<fused> + k_map_vec5)", "ms": kf,
+                                 "mpix_s": px / 1e6 / (kf / 1e3), "algorithmic_bytes_per_px": 40,
+                                 "achieved": 40.0 * px / (kf / 1e3) / 1e9, "frac": 40.0 * px / (kf / 1e3) / 1e9 / peak,
+                                 "unfused_ms": k8 + ms_step}
+    del illu, e_map
 
     # end to end through the reference-facing API with host tensors
     adj = AdaptiveParameterAdjuster()

@@ -65,6 +65,16 @@ UPR_API int upr_clahe_lab_f32(const float* in_nchw, float* out_nchw, int n, int 
 /* Profiling hook: runs only the selected stages of upr_clahe_lab_f32 on a workspace that a full call has
  * already populated.  stage_mask bit 0 = K1 (quantise + Lab + tile histograms + clip/LUT), bit 1 = K3
  * (bilinear LUT map + Lab->RGB); bench.py uses it to time each kernel with CUDA events. */
+/* The enhance path after the CNN in one call: enhanced = R*e + (1-R)*e^2 with R = x/(illu+eps)
+ * (models/model.py:405-413, :442) followed by apply_clahe_enhancement(enhanced) (adaptive_params.py:195,
+ * :121-169).  x, e: [n][3][h][w]; illu: [n][1][h][w]; out: [n][3][h][w].  The recombined frame is formed in the
+ * registers of the histogram kernel and never stored: 40 B/px (x 12 + illu 4 + e 12 read, out 12 written) instead
+ * of 64 B/px for upr_retinex_recombine_f32 + upr_clahe_lab_f32.  Bit-identical to those two calls.  Same
+ * workspace as upr_clahe_lab_f32. */
+UPR_API int upr_retinex_clahe_f32(const float* x_nchw, const float* illu_n1hw, const float* e_nchw, float* out_nchw,
+                                  int n, int h, int w, float eps, double clip_limit, int tiles_x, int tiles_y,
+                                  void* workspace, size_t workspace_bytes, upr_stream_t stream);
+
 UPR_API int upr_clahe_lab_stages_f32(const float* in_nchw, float* out_nchw, int n, int h, int w, double clip_limit,
                                      int tiles_x, int tiles_y, void* workspace, size_t workspace_bytes, int stage_mask,
                                      upr_stream_t stream);

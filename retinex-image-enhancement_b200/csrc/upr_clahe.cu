@@ -453,9 +453,26 @@ __device__ __forceinline__ void k1_item(const float4 vr, const float4 vg, const 
     wb = __byte_perm(__byte_perm(uint32_t(vB[0]), uint32_t(vB[1]), 0x0062), __byte_perm(uint32_t(vB[2]), uint32_t(vB[3]), 0x0062), 0x5410);
 }
 
+// kFused: the CLAHE input is the Retinex recombination of the CNN outputs (models/model.py:405-413,442 followed by
+// adaptive_params.py:195): enhanced = R*e + (1-R)*e^2 with R = x / (illu + eps), evaluated in registers with exactly the
+// arithmetic of k_recombine_vec (IEEE division, separately rounded products) -- the 12 B/px `enhanced` frame is never
+// written nor re-read (x 12 + illu 4 + e 12 B/px are read instead).
+__device__ __forceinline__ void recombine_px(float x, float d, float e, float& r, float& o)
+{
+    r = __fdiv_rn(x, d);
+    o = __fadd_rn(__fmul_rn(r, e), __fmul_rn(__fsub_rn(1.0f, r), __fmul_rn(e, e)));
+}
+
+struct RetinexIn {
+    const float* illu;   // [n][1][h][w]
+    const float* e;      // [n][3][h][w]
+    float eps;
+};
+
+template <bool kFused>
 __global__ void __launch_bounds__(kK1Threads, 3)
 k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
-                uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g)
+                uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g, const RetinexIn rx)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
@@ -546,9 +563,70 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
             prefetch_l2(wide_imm<32>(ppf, plane4));
         }
     };
+    if constexpr (!kFused) {
 #pragma unroll 1
-    for (int k = 0; k < kPfAhead; ++k) prefetch_next();
+        for (int k = 0; k < kPfAhead; ++k) prefetch_next();
+    }
 
+    if constexpr (kFused) {
+        // one raw register set (x, e: 3 planes each, illu: 1) requested one item ahead, L2 prefetch kPfAhead items ahead
+        const long long e_delta = reinterpret_cast<const char*>(rx.e) - reinterpret_cast<const char*>(in);
+        const float4* ilT = reinterpret_cast<const float4*>(rx.illu) + size_t(f) * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
+        const char* pil = reinterpret_cast<const char*>(ilT + (uint32_t(tid / tw4) * w4 + uint32_t(tid % tw4)));
+        const char* pilf = pil;   // runs with ppf
+        // L2 prefetch of x, e, illu, kPfAhead items ahead
+        auto prefetch7 = [&]() {
+            ipf += kK1Threads;
+            cpf += dc;
+            uint32_t st = dstep;
+            if (cpf >= tw4) { cpf -= tw4; st += dwrap; }
+            ppf = wide_imm<16>(ppf, st);
+            pilf = wide_imm<16>(pilf, st);
+            if (ipf < nitems) {
+                prefetch_l2(ppf);
+                prefetch_l2(wide_imm<16>(ppf, plane4));
+                prefetch_l2(wide_imm<32>(ppf, plane4));
+                prefetch_l2(ppf + e_delta);
+                prefetch_l2(wide_imm<16>(ppf + e_delta, plane4));
+                prefetch_l2(wide_imm<32>(ppf + e_delta, plane4));
+                prefetch_l2(pilf);
+            }
+        };
+#pragma unroll 1
+        for (int k = 0; k < kPfAhead; ++k) prefetch7();
+        float4 X[3], E[3], IL;
+        auto load7 = [&](const char* px, const char* pi) {
+            X[0] = ld_nc_f4(px); X[1] = ld_nc_f4(wide_imm<16>(px, plane4)); X[2] = ld_nc_f4(wide_imm<32>(px, plane4));
+            const char* pe = px + e_delta;
+            E[0] = ld_nc_f4(pe); E[1] = ld_nc_f4(wide_imm<16>(pe, plane4)); E[2] = ld_nc_f4(wide_imm<32>(pe, plane4));
+            IL = ld_nc_f4(pi);
+        };
+        auto recombine4 = [&](const float4 xv, const float4 ev, const float d[4]) {
+            float4 o;
+            float r;
+            recombine_px(xv.x, d[0], ev.x, r, o.x);
+            recombine_px(xv.y, d[1], ev.y, r, o.y);
+            recombine_px(xv.z, d[2], ev.z, r, o.z);
+            recombine_px(xv.w, d[3], ev.w, r, o.w);
+            return o;
+        };
+        int i = tid;
+        if (i < nitems) load7(pin, pil);
+        while (i < nitems) {
+            const float d[4] = {__fadd_rn(IL.x, rx.eps), __fadd_rn(IL.y, rx.eps), __fadd_rn(IL.z, rx.eps), __fadd_rn(IL.w, rx.eps)};
+            const float4 er = recombine4(X[0], E[0], d), eg = recombine4(X[1], E[1], d), eb = recombine4(X[2], E[2], d);
+            const uint32_t st1 = advance(c);
+            i += kK1Threads;
+            pin = wide_imm<16>(pin, st1);
+            pil = wide_imm<16>(pil, st1);
+            if (i < nitems) load7(pin, pil);
+            prefetch7();
+            uint32_t wl, wa, wb;
+            k1_item(er, eg, eb, t, s_cnt, tid4, wl, wa, wb);
+            store(plab, wl, wa, wb);
+            plab = const_cast<char*>(wide_imm<4>(plab, st1));
+        }
+    } else {
     float4 ar, ag, ab, br, bg, bb;
     int i = tid;
     if (i < nitems) load(pin, ar, ag, ab);
@@ -569,6 +647,7 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
         k1_item(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
         store(const_cast<char*>(wide_imm<4>(plab, st1)), wl, wa, wb);
         plab = const_cast<char*>(wide_imm<4>(plab, st1 + st2));
+    }
     }
     __syncthreads();
 
@@ -1026,8 +1105,10 @@ static inline int raw_tile(int p, float inv)
 }
 
 // stage_mask: bit 0 = K1 (Lab + histograms + LUTs), bit 1 = K3 (map); 3 = the whole op
+constexpr int kNeedUnfused = -100;   // internal: the fused Retinex prologue exists on the vector path only
+
 static int clahe_run(const float* in, float* out, int n, int h, int w, double clip_limit, int tiles_x, int tiles_y,
-                     void* ws, size_t ws_bytes, cudaStream_t stream, int stage_mask = 3)
+                     void* ws, size_t ws_bytes, cudaStream_t stream, int stage_mask = 3, const RetinexIn* rx = nullptr)
 {
     if (!valid_shape(n, h, w, tiles_x, tiles_y)) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
@@ -1059,7 +1140,7 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
     // interpolation cell boundaries from the exact fp32 recipe (monotone in p)
     MapGeom m{};
     bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && aligned16(in) && aligned16(out) &&
-                size_t(h) * w * 3 < (size_t(1) << 32);
+                size_t(h) * w * 3 < (size_t(1) << 32) && (!rx || (aligned16(rx->illu) && aligned16(rx->e)));
     if (fast) {
         m.n = n; m.h = h; m.w = w; m.tiles_x = tiles_x; m.tiles_y = tiles_y; m.inv_tw = inv_tw; m.inv_th = inv_th;
         int c = 0;
@@ -1081,6 +1162,7 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
         for (int i = 0; i <= tiles_x + 1 && fast; ++i) fast = (m.bx[i] % 4 == 0);
     }
 
+    if (rx && !fast) return kNeedUnfused;
     const int ntiles = tiles_x * tiles_y;
     // a frame index rides in gridDim.y (<= 65535): run long batches in slices
     for (int f0 = 0; f0 < n; f0 += 65535) {
@@ -1104,16 +1186,22 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             static bool attr_set = false;  // benign race: idempotent
             if (!attr_set) {
                 UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
-                UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
+                UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
+                UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
                 attr_set = true;
             }
             if (stage_mask & 1) {
-                if (variant() & 2)
+                if (rx) {
+                    const RetinexIn rxf{rx->illu + size_t(f0) * h * w, rx->e + fplane, rx->eps};
+                    k_hist_lab_vec2<true><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
+                        in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
+                } else if (variant() & 2) {
                     k_hist_lab_vec<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
                                                                                                 lut + ftile * 256, tickets + ftile, g);
-                else
-                    k_hist_lab_vec2<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
-                                                                                                 lut + ftile * 256, tickets + ftile, g);
+                } else {
+                    k_hist_lab_vec2<false><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
+                        in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, RetinexIn{nullptr, nullptr, 0.0f});
+                }
                 UPR_LAUNCH_CHECK();
             }
             const int ncells = (tiles_x + 1) * (tiles_y + 1);
@@ -1183,6 +1271,22 @@ int upr_clahe_lab_f32(const float* in_nchw, float* out_nchw, int n, int h, int w
                       int tiles_y, void* workspace, size_t workspace_bytes, upr_stream_t stream)
 {
     return upr::clahe_run(in_nchw, out_nchw, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int upr_retinex_clahe_f32(const float* x, const float* illu, const float* e, float* out_nchw, int n, int h, int w, float eps,
+                          double clip_limit, int tiles_x, int tiles_y, void* workspace, size_t workspace_bytes,
+                          upr_stream_t stream)
+{
+    if (!x || !illu || !e) return (n == 0 && upr::valid_shape(n, h, w, tiles_x, tiles_y)) ? UPR_OK : UPR_E_NULL;
+    const upr::RetinexIn rx{illu, e, eps};
+    int rc = upr::clahe_run(x, out_nchw, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
+                            static_cast<cudaStream_t>(stream), 3, &rx);
+    if (rc != upr::kNeedUnfused) return rc;
+    // ragged shapes: the two ops back to back (recombination into `out`, CLAHE in place) -- same results
+    rc = upr_retinex_recombine_f32(x, illu, e, nullptr, out_nchw, n, h, w, eps, stream);
+    if (rc) return rc;
+    return upr::clahe_run(out_nchw, out_nchw, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
                           static_cast<cudaStream_t>(stream));
 }
 

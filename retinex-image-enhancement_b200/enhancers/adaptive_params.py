@@ -96,6 +96,13 @@ class AdaptiveParameterAdjuster:
         image_tensor = _to_device(_as_batch(image_tensor), device)
         self.adjust_parameters(image_tensor)
         with torch.no_grad():
+            if hasattr(model, "forward_maps") and not getattr(model, "training", False):
+                # recombination (models/model.py:405-413,442) fused into the CLAHE histogram kernel: the `enhanced` frame
+                # is never materialised; bit-identical to model(x)[0] -> apply_clahe_enhancement
+                illu_map, e_map = model.forward_maps(image_tensor)
+                enhanced_img = native.retinex_clahe(image_tensor.contiguous(), illu_map.contiguous(), e_map.contiguous(),
+                                                    self.CLIP_LIMIT, self.TILE_GRID)
+                return enhanced_img, illu_map
             enhanced_img, _reflectance, illu_map = model(image_tensor)
         enhanced_img = native.clahe_lab(enhanced_img, self.CLIP_LIMIT, self.TILE_GRID)
         return enhanced_img, illu_map

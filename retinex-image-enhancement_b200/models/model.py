@@ -82,9 +82,14 @@ class MultiScaleUP_Retinex(nn.Module):
         f3 = F.interpolate(f3, size=size, mode="bilinear", align_corners=False)
         return torch.sigmoid(self.output_layer(torch.cat([f1, f2, f3], dim=1)))
 
+    def forward_maps(self, x):
+        """The two CNN outputs the Retinex arithmetic consumes: (illumination [B,1,H,W], enhancement map [B,3,H,W]).
+        Inference drivers that only need the CLAHE'd result hand them to the fused ``native.retinex_clahe`` instead of
+        materialising reflectance and enhanced (``AdaptiveParameterAdjuster.apply_adaptive_enhancement``)."""
+        return torch.sigmoid(self.ie_net(x)), self.enhancement_map(x)
+
     def forward(self, x):
-        illu = torch.sigmoid(self.ie_net(x))
-        e = self.enhancement_map(x)
+        illu, e = self.forward_maps(x)
         reflectance, enhanced = retinex_recombine(x.contiguous(), illu.contiguous(), e.contiguous())
         return enhanced, reflectance, illu
 

@@ -39,6 +39,8 @@ def _declare(lib):
     lib.upr_clahe_workspace_bytes.argtypes = [i32] * 5
     lib.upr_clahe_lab_f32.restype = i32
     lib.upr_clahe_lab_f32.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, vp, sz, vp]
+    lib.upr_retinex_clahe_f32.restype = i32
+    lib.upr_retinex_clahe_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, C.c_float, f64, i32, i32, vp, sz, vp]
     lib.upr_clahe_lab_stages_f32.restype = i32
     lib.upr_clahe_lab_stages_f32.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, vp, sz, i32, vp]
     lib.upr_clahe_debug_dump.restype = i32
@@ -296,6 +298,30 @@ def scale_clamp(enh: torch.Tensor, gain: torch.Tensor, out: Optional[torch.Tenso
     with torch.cuda.device(enh.device):
         check(lib().upr_scale_clamp_f32(enh.data_ptr(), gain.data_ptr(), out.data_ptr(), n, c, h, w, _stream()),
               "upr_scale_clamp_f32")
+    return out
+
+
+def retinex_clahe(x: torch.Tensor, illu: torch.Tensor, e: torch.Tensor, clip_limit: float = 2.0,
+                  tiles: Tuple[int, int] = (8, 8), eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CLAHE-in-Lab of the Retinex recombination R*e + (1-R)*e^2, R = x/(illu+eps), in one call (upr_retinex_clahe_f32):
+    the recombined frame is never materialised.  Bit-identical to retinex_recombine(...)[1] -> clahe_lab(...)."""
+    x = _require_cuda_f32(x, "x"); illu = _require_cuda_f32(illu, "illu"); e = _require_cuda_f32(e, "e")
+    n, c, h, w = x.shape
+    if c != 3 or e.shape != x.shape or illu.numel() != n * h * w:
+        raise ValueError("expected x,e [N,3,H,W] and illu [N,1,H,W]")
+    tx, ty = int(tiles[0]), int(tiles[1])
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 CUDA tensor shaped like x")
+    L = lib()
+    with torch.cuda.device(x.device):
+        nbytes = L.upr_clahe_workspace_bytes(n, h, w, tx, ty)
+        if nbytes == 0:
+            raise UprError(-2, "upr_clahe_workspace_bytes")
+        ws = workspace(nbytes, x.device)
+        check(L.upr_retinex_clahe_f32(x.data_ptr(), illu.data_ptr(), e.data_ptr(), out.data_ptr(), n, h, w, float(eps),
+                                      float(clip_limit), tx, ty, ws.data_ptr(), ws.numel(), _stream()), "upr_retinex_clahe_f32")
     return out
 
 

@@ -161,3 +161,23 @@ def test_persistent_map_kernel_shapes(native, n, h, w, tiles):
     """Work-queue geometry of the persistent map kernel: cells narrower/wider than the CTA, single-row cells, strips."""
     x = np.concatenate([O.kat_input(300 + i, h, w, ("uniform", "dark", "ramp")[i % 3]) for i in range(n)])
     compare(native, x, 2.0, tiles)
+
+
+# ---- fused Retinex recombination + CLAHE -----------------------------------------------------------------
+@pytest.mark.parametrize("n,h,w,tiles", [(2, 1080, 1920, (8, 8)), (3, 400, 600, (8, 8)), (1, 403, 601, (8, 8)), (2, 64, 96, (4, 2)),
+                                          (1, 2160, 3840, (8, 8))])
+def test_retinex_clahe_fused_equals_composition(native, n, h, w, tiles):
+    """upr_retinex_clahe_f32 == upr_retinex_recombine_f32 -> upr_clahe_lab_f32, bit for bit (vector path, ragged fallback),
+    and == the oracle's recombination + CLAHE on a small case."""
+    rng = np.random.default_rng(h + w)
+    x = np.concatenate([O.kat_input(800 + i, h, w, ("dark", "uniform")[i % 2]) for i in range(n)])
+    e = rng.random((n, 3, h, w), dtype=np.float32)
+    illu = (rng.random((n, 1, h, w), dtype=np.float32) * 0.9 + 0.05).astype(np.float32)
+    xd, ed, id_ = (torch.from_numpy(a).cuda() for a in (x, e, illu))
+    _, enh = native.retinex_recombine(xd, id_, ed, want_reflectance=False)
+    ref = native.clahe_lab(enh, 2.0, tiles)
+    got = native.retinex_clahe(xd, id_, ed, 2.0, tiles)
+    assert torch.equal(got, ref)
+    if h * w <= 400 * 600:
+        _, e_ref = O.retinex_recombine(x[:1], illu[:1], e[:1])
+        assert np.array_equal(got[:1].cpu().numpy(), O.clahe_lab(e_ref, 2.0, tiles))

@@ -101,3 +101,24 @@ def test_model_inference_uses_fused_recombine(cuda):
     r_ref = x / (illu + 1e-6)
     assert torch.equal(reflectance, r_ref)
     assert torch.allclose(enhanced, r_ref * e + (1 - r_ref) * e ** 2, rtol=3e-7, atol=1e-30)
+
+
+def test_apply_adaptive_enhancement_fused_path_matches_unfused(cuda):
+    """With a model that exposes forward_maps() the adjuster takes the fused recombination+CLAHE kernel; the result must equal
+    model(x)[0] -> apply_clahe_enhancement bit for bit, and the oracle's recombination + CLAHE."""
+    from retinex_image_enhancement_b200 import native
+    from retinex_image_enhancement_b200.enhancers.adaptive_params import AdaptiveParameterAdjuster
+    from retinex_image_enhancement_b200.models.model import UP_Retinex
+    torch.manual_seed(5)
+    model = UP_Retinex().to(cuda).eval()
+    x = torch.from_numpy(O.kat_input(2, 400, 600, "dark"))
+    adj = AdaptiveParameterAdjuster()
+    out, illu = adj.apply_adaptive_enhancement(model, x, cuda)
+    with torch.no_grad():
+        enhanced, _r, illu2 = model(x.to(cuda))
+    ref = native.clahe_lab(enhanced.contiguous())
+    assert torch.equal(out, ref) and torch.equal(illu, illu2)
+    with torch.no_grad():
+        il, e = model.forward_maps(x.to(cuda))
+    _, e_ref = O.retinex_recombine(x.numpy(), il.cpu().numpy(), e.cpu().numpy())
+    assert np.array_equal(out.cpu().numpy(), O.clahe_lab(e_ref))
