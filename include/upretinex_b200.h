@@ -168,6 +168,25 @@ UPR_API int upr_texture_edge_density_f32(const float* x, int n, int c, int h, in
 UPR_API int upr_dynamic_smooth_weight_f32(const float* batch_stats2, float weight_smooth, float* weight_out,
                                           upr_stream_t stream);
 
+/* ---- EXTENSION ops: not present in the reference, no reference parity target ------------------
+ * The north-star names a Gaussian pyramid, log-domain SSR/MSR and gamma; the reference contains none of them
+ * (SURVEY 8a "ABSENT").  These entry points implement them against OpenCV / NumPy semantics and are NOT called by
+ * any reference-facing entry point.  planes = n*c; all tensors are [planes][h][w] f32.
+ *   upr_ext_gaussian_blur_f32 : cv2.GaussianBlur(src, (ksize,ksize), sigma, borderType=BORDER_REFLECT_101), odd
+ *                               ksize <= 31 (sigma <= 0: OpenCV's rule, incl. its fixed tables for ksize <= 7).
+ *                               The input tile is staged by TMA (cp.async.bulk.tensor) when rows are 16-byte aligned.
+ *   upr_ext_msr_f32           : sum_s weights[s] * (log(x + eps) - log(GaussianBlur_s(x) + eps)), 1 <= nscales <= 4
+ *                               (nscales == 1: single-scale Retinex); one staged tile serves all scales.
+ *   upr_ext_pyr_down_f32      : cv2.pyrDown(src) -> [planes][(h+1)/2][(w+1)/2].
+ *   upr_ext_gamma_f32         : pow(clamp(x, 0, 1), gamma).
+ * out must not alias x for the two filters. */
+UPR_API int upr_ext_gaussian_blur_f32(const float* x, float* out, int planes, int h, int w, int ksize, double sigma,
+                                      upr_stream_t stream);
+UPR_API int upr_ext_msr_f32(const float* x, float* out, int planes, int h, int w, int nscales, const int* ksizes,
+                            const double* sigmas, const float* weights, float eps, upr_stream_t stream);
+UPR_API int upr_ext_pyr_down_f32(const float* x, float* out, int planes, int h, int w, upr_stream_t stream);
+UPR_API int upr_ext_gamma_f32(const float* x, float* out, long long count, float gamma, upr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
