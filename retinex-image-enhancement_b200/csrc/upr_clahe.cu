@@ -1183,13 +1183,10 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                 UPR_CUDA_TRY(cudaMemsetAsync(tickets + ftile, 0, size_t(nf) * ntiles * sizeof(unsigned), stream));
             }
             const size_t smem1 = size_t(256) * kK1Threads + UPR_TAB_GAMMA_LEN * 4 + UPR_TAB_CBRT_LEN * 2;
-            static bool attr_set = false;  // benign race: idempotent
-            if (!attr_set) {
-                UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
-                UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
-                UPR_CUDA_TRY(cudaFuncSetAttribute(k_hist_lab_vec2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
-                attr_set = true;
-            }
+            static unsigned long long m1 = 0, m2 = 0, m3 = 0;
+            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec, smem1, m1));
+            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<false>, smem1, m2));
+            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<true>, smem1, m3));
             if (stage_mask & 1) {
                 if (rx) {
                     const RetinexIn rxf{rx->illu + size_t(f0) * h * w, rx->e + fplane, rx->eps};
@@ -1219,11 +1216,8 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                     int nthr = cw4 <= kK5MaxThreads ? (kK5MaxThreads / cw4) * cw4 : kK5MaxThreads;
                     if (nthr < 256) nthr = kK5MaxThreads;
                     const size_t smem5 = size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4;
-                    static bool attr5 = false;
-                    if (!attr5) {
-                        UPR_CUDA_TRY(cudaFuncSetAttribute(k_map_vec5, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem5)));
-                        attr5 = true;
-                    }
+                    static unsigned long long m5 = 0;
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5, smem5, m5));
                     // items = (frame, cell, strip); enough strips for >= 16 items per resident CTA on small batches
                     const int resident = 2 * kNumSMsB200;
                     int ks5 = std::max(1, int((size_t(16) * resident + size_t(nf) * ncells - 1) / (size_t(nf) * ncells)));

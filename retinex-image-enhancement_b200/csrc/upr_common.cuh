@@ -28,6 +28,21 @@ constexpr int kNumSMsB200 = 148;
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs must set it
+// on each of them.  `mask` is one bit per device ordinal (benign race: the call is idempotent).
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, unsigned long long& mask)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (e == cudaSuccess) mask |= bit;
+    return e;
+}
+
 // ---------------------------------------------------------------------------------------
 // streaming global accesses: every f32 pixel is touched exactly once, so keep it out of L1
 // and mark it evict-first in L2; the u8 Lab intermediate is what should stay L2-resident.

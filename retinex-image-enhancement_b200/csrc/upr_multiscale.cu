@@ -559,11 +559,8 @@ static int ms_run(const float* x, int n, int h, int w, float* means, float* gain
         // partial holds 3 doubles per CTA; the generic layout reserves kMsMaxParts*3 per image
         if (parts <= kMsMaxParts) {
             const size_t smem = size_t(3) * (kFH * kFW + kHH * kHW + kQH * kQW) * sizeof(float);
-            static bool attr_set = false;
-            if (!attr_set) {
-                UPR_CUDA_TRY(cudaFuncSetAttribute(k_ms_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                attr_set = true;
-            }
+            static unsigned long long mask = 0;
+            UPR_CUDA_TRY(ensure_dynamic_smem(k_ms_fused, smem, mask));
             k_ms_fused<<<dim3(parts, n), kMsThreads, smem, s>>>(x, h, w, tiles_x, partial, tickets, means, gain);
             UPR_LAUNCH_CHECK();
             return UPR_OK;

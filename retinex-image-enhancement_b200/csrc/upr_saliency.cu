@@ -552,11 +552,8 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
         static const GaussTaps taps = sal_taps();
         const int tiles_x = (w + kSalTile - 1) / kSalTile, tiles_y = (h + kSalTile - 1) / kSalTile;
         const size_t smem = size_t(kRH) * kSalTile * sizeof(double) + size_t(kLW) * kLW * 2 + size_t(kGW) * kGW;
-        static bool attr_set = false;
-        if (!attr_set) {
-            UPR_CUDA_TRY(cudaFuncSetAttribute(k_saliency_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            attr_set = true;
-        }
+        static unsigned long long mask = 0;
+        UPR_CUDA_TRY(ensure_dynamic_smem(k_saliency_blur, smem, mask));
         k_saliency_blur<<<dim3(tiles_x * tiles_y, n), kSalThreads, smem, s>>>(x, h, w, tiles_x, blur, mm, taps);
     } else {
         static const GaussTapsF taps = sal_taps_f();

@@ -181,3 +181,18 @@ def test_retinex_clahe_fused_equals_composition(native, n, h, w, tiles):
     if h * w <= 400 * 600:
         _, e_ref = O.retinex_recombine(x[:1], illu[:1], e[:1])
         assert np.array_equal(got[:1].cpu().numpy(), O.clahe_lab(e_ref, 2.0, tiles))
+
+
+def test_second_device_same_process(native):
+    """One process driving two GPUs: per-device kernel attributes (dynamic shared memory) and workspaces."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    x = torch.from_numpy(O.kat_input(2, 400, 600, "dark"))
+    a = native.clahe_lab(x.to("cuda:0"))
+    with torch.cuda.device(1):
+        b = native.clahe_lab(x.to("cuda:1"))
+        m1, g1 = native.multiscale_stats(x.to("cuda:1"))
+        att1 = native.attention(x.to("cuda:1"))
+    assert torch.equal(a.cpu(), b.cpu())
+    m0, g0 = native.multiscale_stats(x.to("cuda:0"))
+    assert torch.equal(m0.cpu(), m1.cpu()) and torch.equal(native.attention(x.to("cuda:0")).cpu(), att1.cpu())
