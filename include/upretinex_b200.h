@@ -168,6 +168,17 @@ UPR_API int upr_texture_edge_density_f32(const float* x, int n, int c, int h, in
 UPR_API int upr_dynamic_smooth_weight_f32(const float* batch_stats2, float weight_smooth, float* weight_out,
                                           upr_stream_t stream);
 
+/* ---- letterbox pre-processing of the enhance drivers ---------------------------------------------
+ * utils/letterbox.py:9-102 as called by enhancers/simple_enhance.py:43-58: quantise to u8, cv2.resize INTER_LINEAR
+ * (8-bit fixed point) to (rh, rw) when that differs from (h, w), constant border (default 114) to (oh, ow) with the
+ * image at (top, left), then /255.  The geometry (ratio, mod-32 padding, rounding) is computed by the caller exactly
+ * as the reference does.  Down-scaling only (rh <= h, rw <= w; bit-exact against cv2); up-scaling returns
+ * UPR_E_PARAM.  pad_value: c bytes or NULL (114).  The _u8 variant takes the decoded file (u8 HWC) directly. */
+UPR_API int upr_letterbox_f32(const float* in_nchw, float* out_nchw, int n, int c, int h, int w, int rh, int rw, int top,
+                              int left, int oh, int ow, const unsigned char* pad_value, upr_stream_t stream);
+UPR_API int upr_letterbox_u8_f32(const unsigned char* in_nhwc, float* out_nchw, int n, int c, int h, int w, int rh, int rw,
+                                 int top, int left, int oh, int ow, const unsigned char* pad_value, upr_stream_t stream);
+
 /* ---- EXTENSION ops: not present in the reference, no reference parity target ------------------
  * The north-star names a Gaussian pyramid, log-domain SSR/MSR and gamma; the reference contains none of them
  * (SURVEY 8a "ABSENT").  These entry points implement them against OpenCV / NumPy semantics and are NOT called by

@@ -45,3 +45,69 @@ def clahe_lab_batch(frames: np.ndarray, workers: int = 1) -> list:
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=workers) as ex:
         return list(ex.map(clahe_lab_frame, frames))
+
+
+# ---------------------------------------------------------------------------------------------------
+# letterbox: the reference's utils/letterbox.py:9-102 call sequence, and the pinned fixed-point recipe
+# ---------------------------------------------------------------------------------------------------
+def letterbox_ref(chw: np.ndarray, new_shape, color=(114, 114, 114), auto=True, scale_fill=False, scaleup=True):
+    """utils/letterbox.py letterbox_tensor on a [C,H,W] f32 array, OpenCV doing the pixels: -> ([C,H',W'] f32, ratio, (dw, dh))."""
+    import cv2
+    img = (np.transpose(chw, (1, 2, 0)) * 255).astype(np.uint8)
+    shape = img.shape[:2]
+    if isinstance(new_shape, int):
+        new_shape = (new_shape, new_shape)
+    r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
+    if not scaleup:
+        r = min(r, 1.0)
+    ratio = r, r
+    new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
+    dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if auto:
+        dw, dh = np.mod(dw, 32), np.mod(dh, 32)
+    elif scale_fill:
+        dw, dh = 0.0, 0.0
+        new_unpad = (new_shape[1], new_shape[0])
+        ratio = new_shape[1] / shape[1], new_shape[0] / shape[0]
+    dw /= 2
+    dh /= 2
+    if shape[::-1] != new_unpad:
+        img = cv2.resize(img, new_unpad, interpolation=cv2.INTER_LINEAR)
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    img = cv2.copyMakeBorder(img, top, bottom, left, right, cv2.BORDER_CONSTANT, value=color)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    return np.ascontiguousarray(np.transpose(img.astype(np.float32) / 255.0, (2, 0, 1))), ratio, (dw, dh)
+
+
+def resize_linear_u8_fixed(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src u8 [H,W,C], (dw, dh), INTER_LINEAR) restated (8-bit fixed point, 11-bit coefficients); pinned against
+    the binary for down-scaling (tests/test_oracle_pin.py) -- the specification the GPU kernel implements."""
+    sh, sw = src.shape[:2]
+
+    def coeffs(dn, sn, scale):
+        idx = np.empty(dn, np.int64)
+        a0 = np.empty(dn, np.int64)
+        a1 = np.empty(dn, np.int64)
+        for d in range(dn):
+            f = np.float32((d + 0.5) * scale - 0.5)
+            s = int(np.floor(f))
+            f = np.float32(f - np.float32(s))
+            if s < 0:
+                f, s = np.float32(0), 0
+            if s >= sn - 1:
+                f, s = np.float32(0), sn - 1
+            idx[d] = s
+            a0[d] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))))
+            a1[d] = int(np.rint(np.float32(f * np.float32(2048))))
+        return idx, a0, a1
+
+    xi, xa0, xa1 = coeffs(dw, sw, sw / dw)
+    yi, ya0, ya1 = coeffs(dh, sh, sh / dh)
+    s64 = src.reshape(sh, sw, -1).astype(np.int64)
+    x1 = np.minimum(xi + 1, sw - 1)
+    rows = s64[:, xi, :] * xa0[None, :, None] + s64[:, x1, :] * xa1[None, :, None]
+    y1 = np.minimum(yi + 1, sh - 1)
+    out = (((ya0[:, None, None] * (rows[yi] >> 4)) >> 16) + ((ya1[:, None, None] * (rows[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8).reshape((dh, dw) + src.shape[2:])

@@ -32,11 +32,27 @@ from .multi_scale import MultiScaleEnhancer
 VALID_EXTENSIONS = {".jpg", ".jpeg", ".png", ".bmp", ".tif", ".tiff"}
 
 
-def load_image(image_path, max_size=None):
-    """-> ([1,3,H,W] f32 host tensor in [0,1], (W, H) of the file)."""
+def load_image(image_path, max_size=None, device=None):
+    """-> ([1,3,H,W] f32 tensor in [0,1], (W, H) of the file).  Host tensor like the reference's by default.  With a CUDA
+    ``device`` (what the drivers below pass) the decoded uint8 frame is uploaded as is -- 3 instead of 12 bytes per pixel
+    over PCIe -- and de-quantised / letterboxed on the device (upr_letterbox_u8_f32; same values, bit for bit)."""
     from PIL import Image
     img = Image.open(image_path).convert("RGB")
     original_size = img.size
+    if device is not None and torch.device(device).type == "cuda":
+        from .. import native
+        from ..utils.letterbox import letterbox_geometry
+        u8 = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).unsqueeze(0)
+        h, w = u8.shape[1], u8.shape[2]
+        if max_size is None:
+            (rh, rw), (top, bottom, left, right) = (h, w), (0, 0, 0, 0)
+        else:
+            (rh, rw), (top, bottom, left, right), _, _ = letterbox_geometry(h, w, max_size, auto=True, scaleup=False)
+        dev = torch.device(device)
+        with torch.cuda.device(dev):
+            t = native.letterbox(u8.pin_memory().to(dev, non_blocking=True), (rh, rw), top, left,
+                                 (rh + top + bottom, rw + left + right))
+        return t, original_size
     t = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).to(torch.float32) / 255.0
     if max_size is not None:
         t, _, _ = letterbox_tensor(t, new_shape=max_size, auto=True, scaleup=False)
@@ -86,7 +102,7 @@ def _write_outputs(img_low, img_enhanced, illu_map, image_path, output_dir):
 def enhance_single_image(model, image_path, output_dir, device, max_size=None, enable_multi_scale=False,
                          enable_content_aware=False, adjuster=None):
     print(f"正在处理: {os.path.basename(image_path)}")
-    img_low, _original_size = load_image(image_path, max_size)
+    img_low, _original_size = load_image(image_path, max_size, device=device)
     start = time.time()
     img_enhanced, illu_map = _enhance_tensor(model, img_low, device, enable_multi_scale, enable_content_aware, adjuster)
     if img_enhanced.is_cuda:
@@ -135,7 +151,7 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
         pending.clear()
 
     for path in mine:
-        low, _ = load_image(path, max_size)
+        low, _ = load_image(path, max_size, device=device)
         if pending and (pending[0][1].shape != low.shape or len(pending) >= batch_size):
             flush()
         pending.append((path, low))

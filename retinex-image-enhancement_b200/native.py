@@ -75,6 +75,10 @@ def _declare(lib):
     lib.upr_retinex_recombine_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
     lib.upr_retinex_decompose_f32.restype = i32
     lib.upr_retinex_decompose_f32.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp]
+    lib.upr_letterbox_f32.restype = i32
+    lib.upr_letterbox_f32.argtypes = [vp, vp] + [i32] * 10 + [vp, vp]
+    lib.upr_letterbox_u8_f32.restype = i32
+    lib.upr_letterbox_u8_f32.argtypes = [vp, vp] + [i32] * 10 + [vp, vp]
     lib.upr_texture_workspace_bytes.restype = sz
     lib.upr_texture_workspace_bytes.argtypes = [i32]
     lib.upr_texture_workspace_init.restype = i32
@@ -451,4 +455,30 @@ def dynamic_smooth_weight(batch_stats2: torch.Tensor, weight_smooth: float = 1.0
     with torch.cuda.device(s.device):
         check(lib().upr_dynamic_smooth_weight_f32(s.data_ptr(), float(weight_smooth), out.data_ptr(), _stream()),
               "upr_dynamic_smooth_weight_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# N2: letterbox (utils/letterbox.py) -- geometry by the caller, pixels on the device
+# ------------------------------------------------------------------------------------------------
+def letterbox(x: torch.Tensor, resized_hw, top: int, left: int, out_hw, pad_value=(114, 114, 114)) -> torch.Tensor:
+    """x: [N,C,H,W] f32 CUDA in [0,1]  or  [N,H,W,C] u8 CUDA (decoded files) -> [N,C,oh,ow] f32 CUDA.
+    Down-scaling only (bit-exact against cv2.resize INTER_LINEAR on uint8); raises UprError(UPR_E_PARAM) for up-scaling."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError("x must live on a CUDA device (upretinex-b200 has no CPU path)")
+    x = x.contiguous()
+    if x.dtype == torch.uint8:
+        n, h, w, c = x.shape
+        fn, name = lib().upr_letterbox_u8_f32, "upr_letterbox_u8_f32"
+    elif x.dtype == torch.float32:
+        n, c, h, w = x.shape
+        fn, name = lib().upr_letterbox_f32, "upr_letterbox_f32"
+    else:
+        raise TypeError(f"x must be float32 [N,C,H,W] or uint8 [N,H,W,C], got {x.dtype}")
+    rh, rw = int(resized_hw[0]), int(resized_hw[1])
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+    pad = (C.c_ubyte * 4)(*([int(v) for v in pad_value] + [114] * 4)[:4])
+    with torch.cuda.device(x.device):
+        check(fn(x.data_ptr(), out.data_ptr(), n, c, h, w, rh, rw, int(top), int(left), oh, ow, pad, _stream()), name)
     return out

@@ -25,7 +25,7 @@ def create_comparison(img_low, img_enhanced, illu_map, save_path):
 
 
 def predict_single_image(model, image_path, output_dir, device, max_size=None, save_comparison=True):
-    img_low, _ = load_image(image_path, max_size)
+    img_low, _ = load_image(image_path, max_size, device=device)
     img_low = img_low.to(device)
     start = time.time()
     with torch.no_grad():

@@ -167,3 +167,39 @@ def test_cv2_chain_matches_oracle():
     xs = np.concatenate([O.kat_input(40 + i, 64, 96, "uniform") for i in range(4)])
     for got, x in zip(cv2_chain.clahe_lab_batch(xs, workers=3), xs):
         assert np.array_equal(np.ascontiguousarray(got), O.clahe_lab(x)[0])
+
+
+# ---- letterbox: the fixed-point bilinear recipe against the cv2 binary ---------------------------
+@pytest.mark.parametrize("sh,sw,dh,dw", [(480, 640, 240, 320), (1000, 1024, 640, 655), (1080, 1920, 360, 640), (123, 457, 77, 301),
+                                          (99, 101, 98, 100), (500, 333, 499, 332), (301, 301, 150, 150), (64, 64, 63, 1), (200, 300, 1, 1),
+                                          (1080, 1920, 1078, 1917), (777, 1333, 389, 667), (1024, 1000, 625, 640)])
+def test_resize_linear_u8_recipe_matches_cv2_downscale(sh, sw, dh, dw):
+    cv2 = pytest.importorskip("cv2")
+    from oracle import cv2_chain
+    src = np.random.default_rng(sh * 7 + dw).integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+    for ipp in (True, False):
+        if hasattr(cv2, "ipp"):
+            cv2.ipp.setUseIPP(ipp)
+        ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(cv2_chain.resize_linear_u8_fixed(src, dw, dh), ref)
+    if hasattr(cv2, "ipp"):
+        cv2.ipp.setUseIPP(True)
+
+
+def test_letterbox_ref_is_the_reference_function():
+    """oracle/cv2_chain.letterbox_ref against the unmodified reference (when its tree is mounted)."""
+    import os, sys
+    if not os.path.isdir("/root/reference/utils"):
+        pytest.skip("reference tree not mounted")
+    pytest.importorskip("cv2")
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("ref_letterbox", "/root/reference/utils/letterbox.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from oracle import cv2_chain
+    x = np.random.default_rng(3).random((3, 300, 517), dtype=np.float32)
+    for new_shape, scaleup in ((256, False), (640, False), ((200, 333), True)):
+        got, ratio, pad = cv2_chain.letterbox_ref(x, new_shape, auto=True, scaleup=scaleup)
+        exp, ratio2, pad2 = ref.letterbox_tensor(torch.from_numpy(x), new_shape=new_shape, auto=True, scaleup=scaleup)
+        assert np.array_equal(got, exp.numpy()) and ratio == ratio2 and tuple(pad) == tuple(pad2)
