@@ -61,10 +61,20 @@ def load_image(image_path, max_size=None, device=None):
 
 
 def _to_u8_hwc(tensor):
+    """[1,C,H,W] / [C,H,W] f32 -> [H,W,3] uint8 array: (clip(x,0,1)*255).astype(uint8) as in the reference's save_image
+    (enhancers/simple_enhance.py:65-80).  A CUDA tensor is clipped, quantised and interleaved on the device, so only 3 bytes
+    per pixel cross PCIe (the same truncating cast; uint8 arrays pass through)."""
+    if isinstance(tensor, np.ndarray):
+        return tensor
     if tensor.dim() == 4:
         tensor = tensor.squeeze(0)
-    a = tensor.detach().to("cpu", torch.float32).numpy()
-    a = (np.clip(a, 0, 1) * 255).astype(np.uint8)
+    t = tensor.detach().to(torch.float32)
+    if t.is_cuda:
+        q = (t.clamp(0, 1) * 255).to(torch.uint8)
+        if q.shape[0] == 1:
+            q = q.expand(3, -1, -1)
+        return q.permute(1, 2, 0).contiguous().cpu().numpy()
+    a = (np.clip(t.numpy(), 0, 1) * 255).astype(np.uint8)
     if a.shape[0] == 1:
         return np.stack([a[0]] * 3, axis=2)
     return np.transpose(a, (1, 2, 0))
@@ -91,12 +101,23 @@ def _enhance_tensor(model, img_low, device, enable_multi_scale, enable_content_a
     return (adjuster or AdaptiveParameterAdjuster()).apply_adaptive_enhancement(model, img_low, device)
 
 
-def _write_outputs(img_low, img_enhanced, illu_map, image_path, output_dir):
+def _write_outputs(img_low, img_enhanced, illu_map, image_path, output_dir, pool=None):
+    """The reference's three files per image (enhancers/simple_enhance.py:177-195).  Quantisation happens here (on the
+    device for CUDA tensors); with ``pool`` (a ThreadPoolExecutor) the PNG encoding runs on host threads while the GPU
+    works on the next batch."""
     os.makedirs(output_dir, exist_ok=True)
     stem = os.path.splitext(os.path.basename(image_path))[0]
-    save_image(img_enhanced, os.path.join(output_dir, f"{stem}_enhanced.png"))
-    save_image(illu_map, os.path.join(output_dir, f"{stem}_illumination.png"))
-    create_comparison(img_low, img_enhanced, os.path.join(output_dir, f"{stem}_comparison.png"))
+    low, enh, illu = _to_u8_hwc(img_low), _to_u8_hwc(img_enhanced), _to_u8_hwc(illu_map)
+
+    def write():
+        save_image(enh, os.path.join(output_dir, f"{stem}_enhanced.png"))
+        save_image(illu, os.path.join(output_dir, f"{stem}_illumination.png"))
+        create_comparison(low, enh, os.path.join(output_dir, f"{stem}_comparison.png"))
+
+    if pool is None:
+        write()
+        return None
+    return pool.submit(write)
 
 
 def enhance_single_image(model, image_path, output_dir, device, max_size=None, enable_multi_scale=False,
@@ -139,23 +160,30 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
     print(f"找到 {len(files)} 个图像文件 (本进程处理 {len(mine)} 个)")
     t0 = time.time()
     pending = []   # consecutive same-shape images form one device batch
+    from concurrent.futures import ThreadPoolExecutor
+    writers = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
+    futures = []
 
     def flush():
         if not pending:
             return
         batch = torch.cat([p[1] for p in pending], dim=0)
         enhanced, illu = _enhance_tensor(model, batch, device, enable_multi_scale, enable_content_aware)
-        enhanced, illu = enhanced.cpu(), illu.cpu()
         for i, (path, low) in enumerate(pending):
-            _write_outputs(low, enhanced[i:i + 1], illu[i:i + 1], path, output_dir)
+            futures.append(_write_outputs(low, enhanced[i:i + 1], illu[i:i + 1], path, output_dir, pool=writers))
         pending.clear()
 
-    for path in mine:
-        low, _ = load_image(path, max_size, device=device)
-        if pending and (pending[0][1].shape != low.shape or len(pending) >= batch_size):
-            flush()
-        pending.append((path, low))
-    flush()
+    try:
+        for path in mine:
+            low, _ = load_image(path, max_size, device=device)
+            if pending and (pending[0][1].shape != low.shape or len(pending) >= batch_size):
+                flush()
+            pending.append((path, low))
+        flush()
+        for fut in futures:
+            fut.result()
+    finally:
+        writers.shutdown(wait=True)
     total = time.time() - t0
     print("=" * 50)
     print(f"总共处理了 {len(mine)} 张图像")
