@@ -1218,10 +1218,12 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                     const size_t smem5 = size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4;
                     static unsigned long long m5 = 0;
                     UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5, smem5, m5));
-                    // items = (frame, cell, strip); enough strips for >= 16 items per resident CTA on small batches
+                    // items = (frame, cell, strip): ~4 items per resident CTA on small batches, strips of >= 16 rows (every item
+                    // costs a barrier and a quad-table build: with 16 items per CTA and 8-row strips a 3-frame call took 99 us
+                    // instead of 78 us for the first-generation kernel)
                     const int resident = 2 * kNumSMsB200;
-                    int ks5 = std::max(1, int((size_t(16) * resident + size_t(nf) * ncells - 1) / (size_t(nf) * ncells)));
-                    ks5 = std::min(ks5, std::max(cell_rows / 8, 1));
+                    int ks5 = std::max(1, int((size_t(4) * resident + size_t(nf) * ncells - 1) / (size_t(nf) * ncells)));
+                    ks5 = std::min(ks5, std::max(cell_rows / 16, 1));
                     m.nstrips = ks5;
                     const long long nitems = (long long)nf * ncells * ks5;
                     if (nitems > 0x7fffffffLL / 2) return UPR_E_SHAPE;
