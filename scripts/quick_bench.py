@@ -59,6 +59,11 @@ def main():
             x *= 0.3
         elif a.kinds == "const":
             x.fill_(0.3)
+        elif a.kinds == "smooth":
+            # natural-image-like content: low-pass noise (16x bilinear up-sampling of coarse noise) + 2 % fine noise
+            coarse = torch.rand((a.n, 3, a.h // 16 + 1, a.w // 16 + 1), device="cuda", generator=g)
+            x = torch.nn.functional.interpolate(coarse, size=(a.h, a.w), mode="bicubic", align_corners=False).clamp_(0, 1)
+            x = (x * 0.98 + 0.02 * torch.rand(x.shape, device="cuda", generator=g)).contiguous()
     out = torch.empty_like(x)
     med, best = time_op(lambda: native.clahe_lab(x, out=out), a.iters)
     px = a.n * a.h * a.w
