@@ -417,6 +417,14 @@ def bench_c4(torch, dist, rank, world, local, args):
         del wgt
     except Exception as e:  # pragma: no cover
         graph_us = f"graph capture failed: {e!r}"
+    # one kernel per rank: statistics + [sum, count] exchange over NVLink peer memory + weight (no NCCL call)
+    fused_us = None
+    try:
+        dsw = L.DynamicSmoothWeight(1.0, True, "tv", fused_collective=True)
+        dsw(x)
+        fused_us = timed_steps(torch, dist, lambda: dsw(x), args.steps, args.warmup) / args.steps * 1e3
+    except Exception as e:  # pragma: no cover
+        fused_us = f"fused path failed: {e!r}"
     k_tv = statistics.mean(event_time_ms(torch, lambda: native.texture_complexity(x, "tv"), 20))
     k_ed = statistics.mean(event_time_ms(torch, lambda: native.texture_complexity(x, "edge_density"), 20))
     px = b * h * w
@@ -424,7 +432,8 @@ def bench_c4(torch, dist, rank, world, local, args):
     achieved = 12.0 * px / (k_tv / 1e3) / 1e9
     return {"metric": "Mpix/s, texture statistics + dynamic smoothness weight (losses/loss.py:523-583,704-720)",
             "value": world * px / 1e6 / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "us_per_step": ms_step * 1e3, "us_per_step_cuda_graph": graph_us, "higher_is_better": True,
+            "ms_per_step": ms_step, "us_per_step": ms_step * 1e3, "us_per_step_cuda_graph": graph_us,
+            "us_per_step_fused_peer_kernel": fused_us, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp64 accumulators)", "data": "synthetic",
             "config": {"workload": f"c4: upr_texture_tv_f32 on {b}x{c}x{h}x{w} per rank + all-reduce(SUM) of [sum, count] + weight kernel",
                        "l2": "latency-bound config (6.3 MB input is L2 resident by construction); reported in us/step"},

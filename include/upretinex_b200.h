@@ -167,6 +167,19 @@ UPR_API int upr_texture_edge_density_f32(const float* x, int n, int c, int h, in
                                          upr_stream_t stream);
 UPR_API int upr_dynamic_smooth_weight_f32(const float* batch_stats2, float weight_smooth, float* weight_out,
                                           upr_stream_t stream);
+/* a9 + the data-parallel batch mean + a10 in ONE kernel per rank: the texture statistics kernel exchanges its
+ * [sum c, B] pair with every peer through NVLink-mapped symmetric memory (P2P stores + system-scope flags) and writes
+ * the all-rank statistics and the dynamic smoothness weight itself -- no NCCL call, no second launch.
+ * peer_buffers_dev: device array of `world` addresses, entry r = rank r's buffer of upr_peer_stats_buffer_bytes()
+ * bytes (zero-filled once before the first call; allocated with torch.distributed._symmetric_memory or any CUDA IPC /
+ * VMM mapping); NULL = single process (then this is upr_texture_*_f32 + upr_dynamic_smooth_weight_f32).  seq: call
+ * counter >= 1, the same on every rank, strictly increasing.  method: 0 = 'tv', 1 = 'edge_density'.  All ranks must
+ * call it (collective); a peer that never arrives traps the kernel after ~1 s instead of hanging. */
+UPR_API size_t upr_peer_stats_buffer_bytes(void);
+UPR_API int upr_texture_weight_peer_f32(const float* x, int n, int c, int h, int w, int method, float* per_image,
+                                        float* batch_stats2, void* workspace, size_t workspace_bytes,
+                                        const unsigned long long* peer_buffers_dev, int rank, int world, unsigned seq,
+                                        float weight_smooth, float* weight_out, upr_stream_t stream);
 
 /* ---- letterbox pre-processing of the enhance drivers ---------------------------------------------
  * utils/letterbox.py:9-102 as called by enhancers/simple_enhance.py:43-58: quantise to u8, cv2.resize INTER_LINEAR

@@ -50,10 +50,73 @@ __device__ __forceinline__ bool last_cta_of(unsigned* ticket, unsigned nparts, i
     return last;
 }
 
+// Data-parallel exchange of the batch statistics over NVLink peer memory, fused into the statistics kernel (the
+// "compute step followed by a collective" of this path: losses/loss.py:710 needs the batch mean over ALL ranks).
+// Every rank owns one symmetric-memory buffer (torch.distributed._symmetric_memory; peers[] holds the W mapped base
+// addresses, identical layout everywhere):
+//     float    slot[2][kPeerMax][2]   [parity][source rank] = {sum of complexity, image count}
+//     unsigned flag[2][kPeerMax]      [parity][source rank] = sequence number of the call that wrote the slot
+// The thread that finishes the local batch stores its pair into slot[seq & 1][rank] of EVERY rank (P2P stores), fences
+// system-wide, raises the flags, then waits for the W flags of its own buffer and adds the W pairs in rank order -- all
+// ranks add the same numbers in the same order, so every rank derives the bit-identical weight.  Two parities: a rank can
+// be at most one call ahead of its slowest peer (it needs that peer's flag of the current call to finish).
+constexpr int kPeerMax = 64;
+constexpr size_t kPeerBufBytes = size_t(2) * kPeerMax * 2 * sizeof(float) + size_t(2) * kPeerMax * sizeof(unsigned);
+
+struct PeerXchg {
+    const unsigned long long* peers;   // device array [world] of peer buffer addresses; nullptr = single process
+    int rank, world;
+    unsigned seq;                      // >= 1, strictly increasing per call on this buffer set
+    float w0;                          // weight_smooth
+    float* weight_out;                 // device scalar, may be nullptr
+};
+
+__device__ __forceinline__ float dyn_weight(float sum, float count, float w0)
+{
+    const float avg = __fdiv_rn(sum, count);
+    const float wv = __fmul_rn(w0, __fsub_rn(1.0f, __fmul_rn(avg, 0.8f)));
+    return wv < 0.1f ? 0.1f : (wv > 5.0f ? 5.0f : wv);
+}
+
+__device__ __forceinline__ void peer_exchange(const PeerXchg& px, float& s, float& cnt)
+{
+    const int par = int(px.seq & 1u);
+    for (int r = 0; r < px.world; ++r) {
+        volatile float* slot = reinterpret_cast<volatile float*>(px.peers[r]) + (size_t(par) * kPeerMax + px.rank) * 2;
+        slot[0] = s;
+        slot[1] = cnt;
+    }
+    __threadfence_system();
+    for (int r = 0; r < px.world; ++r) {
+        volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(px.peers[r] + size_t(2) * kPeerMax * 2 * sizeof(float)) +
+                                  size_t(par) * kPeerMax + px.rank;
+        *flag = px.seq;
+    }
+    const unsigned long long mine = px.peers[px.rank];
+    volatile unsigned* myflags = reinterpret_cast<volatile unsigned*>(mine + size_t(2) * kPeerMax * 2 * sizeof(float)) + size_t(par) * kPeerMax;
+    for (int r = 0; r < px.world; ++r) {
+        long long spins = 0;
+        while (myflags[r] != px.seq) {
+            if (++spins > (1LL << 28)) __trap();   // a peer that never arrives must fail loudly, not hang the device
+        }
+    }
+    __threadfence_system();
+    volatile float* myslots = reinterpret_cast<volatile float*>(mine) + size_t(par) * kPeerMax * 2;
+    float ts = 0.0f, tc = 0.0f;
+    for (int r = 0; r < px.world; ++r) {
+        ts = __fadd_rn(ts, myslots[2 * r]);
+        tc = __fadd_rn(tc, myslots[2 * r + 1]);
+    }
+    s = ts;
+    cnt = tc;
+}
+
 // Called by thread 0 of the CTA that finished image f: the image that finishes LAST adds the
 // per-image values in index order (deterministic) into stats2 = [sum of complexity, image count],
-// the two numbers the data-parallel all-reduce carries (loss.py:710 batch mean).
-__device__ __forceinline__ void finish_batch(unsigned* batch_ticket, int n, const float* per_image, float* stats2)
+// the two numbers the data-parallel all-reduce carries (loss.py:710 batch mean).  With a peer table the all-reduce
+// happens right here and the dynamic smoothness weight is written too.
+__device__ __forceinline__ void finish_batch(unsigned* batch_ticket, int n, const float* per_image, float* stats2,
+                                             const PeerXchg px = PeerXchg{nullptr, 0, 1, 0u, 0.0f, nullptr})
 {
     if (!stats2) return;
     __threadfence();
@@ -63,8 +126,11 @@ __device__ __forceinline__ void finish_batch(unsigned* batch_ticket, int n, cons
     __threadfence();
     float s = 0.0f;
     for (int i = 0; i < n; ++i) s = __fadd_rn(s, __ldcg(per_image + i));
+    float cnt = float(n);
+    if (px.peers) peer_exchange(px, s, cnt);
     stats2[0] = s;
-    stats2[1] = float(n);
+    stats2[1] = cnt;
+    if (px.weight_out) px.weight_out[0] = dyn_weight(s, cnt, px.w0);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -109,7 +175,7 @@ k_brightness_hist(const float* __restrict__ in, unsigned* __restrict__ hist, lon
 // workspace: partial [n][parts][2] fp64, tickets [n] + 1 batch ticket, mean magnitude [n] fp64
 __global__ void __launch_bounds__(kStThreads)
 k_texture_tv(const float* __restrict__ x, int c, int h, int w, double* __restrict__ partial,
-             unsigned* __restrict__ tickets, float* __restrict__ per_image, float* __restrict__ stats2)
+             unsigned* __restrict__ tickets, float* __restrict__ per_image, float* __restrict__ stats2, const PeerXchg px)
 {
     __shared__ double s_red[kStThreads / 32];
     __shared__ int s_flag;
@@ -166,7 +232,7 @@ k_texture_tv(const float* __restrict__ x, int c, int h, int w, double* __restric
         const float mv = float(tv / (double(c) * (h - 1) * w));
         const float cx = __fadd_rn(mh, mv);
         per_image[f] = cx;
-        finish_batch(tickets + gridDim.y, gridDim.y, per_image, stats2);
+        finish_batch(tickets + gridDim.y, gridDim.y, per_image, stats2, px);
     }
 }
 
@@ -207,7 +273,7 @@ template <int kPass>
 __global__ void __launch_bounds__(kStThreads)
 k_texture_edge(const float* __restrict__ x, int c, int h, int w, double* __restrict__ partial,
                unsigned* __restrict__ tickets, double* __restrict__ mean_mag, float* __restrict__ per_image,
-               float* __restrict__ stats2)
+               float* __restrict__ stats2, const PeerXchg px)
 {
     __shared__ double s_red[kStThreads / 32];
     __shared__ int s_flag;
@@ -235,16 +301,14 @@ k_texture_edge(const float* __restrict__ x, int c, int h, int w, double* __restr
         } else {
             const float cx = float(t / double(plane));
             per_image[f] = cx;
-            finish_batch(tickets + gridDim.y, gridDim.y, per_image, stats2);
+            finish_batch(tickets + gridDim.y, gridDim.y, per_image, stats2, px);
         }
     }
 }
 
 __global__ void k_dynamic_weight(const float* __restrict__ stats2, float w0, float* __restrict__ out)
 {
-    const float avg = __fdiv_rn(stats2[0], stats2[1]);
-    const float wv = __fmul_rn(w0, __fsub_rn(1.0f, __fmul_rn(avg, 0.8f)));
-    out[0] = wv < 0.1f ? 0.1f : (wv > 5.0f ? 5.0f : wv);
+    out[0] = dyn_weight(stats2[0], stats2[1], w0);
 }
 
 static int tex_parts(int n, long long items_per_image)
@@ -306,7 +370,8 @@ int upr_texture_workspace_init(void* workspace, size_t workspace_bytes, int n, u
 }
 
 static int texture_run(int method, const float* x, int n, int c, int h, int w, float* per_image, float* stats2,
-                       void* ws, size_t ws_bytes, cudaStream_t s)
+                       void* ws, size_t ws_bytes, cudaStream_t s,
+                       const upr::PeerXchg px = upr::PeerXchg{nullptr, 0, 1, 0u, 0.0f, nullptr})
 {
     if (n < 0 || n > 65535 || c <= 0 || h <= 0 || w <= 0) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
@@ -324,15 +389,15 @@ static int texture_run(int method, const float* x, int n, int c, int h, int w, f
         if (method == 0) {
             const int parts = upr::tex_parts(n, (long long)c * plane / 4 + 1);
             upr::k_texture_tv<<<dim3(parts, nf), upr::kStThreads, 0, s>>>(xf, c, h, w, partial + (long long)f0 * parts * 2,
-                                                                         tickets + f0, per_image + f0, stats2);
+                                                                         tickets + f0, per_image + f0, stats2, px);
             UPR_LAUNCH_CHECK();
         } else {
             const int parts = upr::tex_parts(n, plane);
             upr::k_texture_edge<1><<<dim3(parts, nf), upr::kStThreads, 0, s>>>(xf, c, h, w, partial + (long long)f0 * parts,
-                                                                              tickets + f0, mean + f0, per_image + f0, nullptr);
+                                                                              tickets + f0, mean + f0, per_image + f0, nullptr, px);
             UPR_LAUNCH_CHECK();
             upr::k_texture_edge<2><<<dim3(parts, nf), upr::kStThreads, 0, s>>>(xf, c, h, w, partial + (long long)f0 * parts,
-                                                                              tickets + f0, mean + f0, per_image + f0, stats2);
+                                                                              tickets + f0, mean + f0, per_image + f0, stats2, px);
             UPR_LAUNCH_CHECK();
         }
     }
@@ -351,6 +416,21 @@ int upr_texture_edge_density_f32(const float* x, int n, int c, int h, int w, flo
 {
     return texture_run(1, x, n, c, h, w, per_image, batch_stats2, workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream));
+}
+
+size_t upr_peer_stats_buffer_bytes(void) { return upr::kPeerBufBytes; }
+
+int upr_texture_weight_peer_f32(const float* x, int n, int c, int h, int w, int method, float* per_image, float* batch_stats2,
+                                void* workspace, size_t workspace_bytes, const unsigned long long* peer_buffers_dev, int rank,
+                                int world, unsigned seq, float weight_smooth, float* weight_out, upr_stream_t stream)
+{
+    if (method != 0 && method != 1) return UPR_E_PARAM;
+    if (!batch_stats2 || !weight_out) return UPR_E_NULL;
+    if (peer_buffers_dev && (world < 1 || world > upr::kPeerMax || rank < 0 || rank >= world || seq == 0)) return UPR_E_PARAM;
+    if (n <= 0) return UPR_E_SHAPE;   // every rank must contribute to the exchange
+    const upr::PeerXchg px{peer_buffers_dev, rank, world, seq, weight_smooth, weight_out};
+    return texture_run(method, x, n, c, h, w, per_image, batch_stats2, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream), px);
 }
 
 int upr_dynamic_smooth_weight_f32(const float* batch_stats2, float weight_smooth, float* weight_out, upr_stream_t stream)

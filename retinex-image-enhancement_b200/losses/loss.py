@@ -48,20 +48,61 @@ def weight_from_stats(stats: torch.Tensor, weight_smooth: float = 1.0) -> torch.
     return torch.clamp(torch.tensor(weight_smooth, dtype=torch.float32) * (1.0 - avg * 0.8), 0.1, 5.0)
 
 
+class PeerBatchStats:
+    """Symmetric-memory exchange buffers for the fused statistics + all-reduce + weight kernel
+    (``upr_texture_weight_peer_f32``): one small buffer per rank, mapped into every rank of ``group`` over NVLink
+    (``torch.distributed._symmetric_memory``).  Collective: construct it on every rank of the group."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerBatchStats needs an initialised process group")
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nfloats = (native.lib().upr_peer_stats_buffer_bytes() + 3) // 4
+        self.buf = symm.empty(nfloats, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group=group.group_name)
+        self.table = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)          # every buffer is zeroed and mapped before the first exchange
+        self.seq = 0
+
+    def next_seq(self) -> int:
+        self.seq += 1
+        return self.seq
+
+
 class DynamicSmoothWeight:
     """``TotalLoss``'s dynamic smoothness weight (losses/loss.py:607-656 constructor arguments
-    ``weight_smooth``, ``use_dynamic_smooth_weight``, ``texture_method``)."""
+    ``weight_smooth``, ``use_dynamic_smooth_weight``, ``texture_method``).
+
+    ``fused_collective=True`` (data-parallel CUDA training on one NVLink node): statistics, the all-rank batch mean and the
+    weight come out of ONE kernel per rank that exchanges the [sum, count] pair through peer memory, instead of a statistics
+    kernel + NCCL all-reduce + weight kernel.  Same result on every rank, bit for bit equal to the NCCL path's."""
 
     def __init__(self, weight_smooth: float = 1.0, use_dynamic_smooth_weight: bool = True, texture_method: str = "tv",
-                 group=None):
+                 group=None, fused_collective: bool = False):
         self.weight_smooth = weight_smooth
         self.use_dynamic_smooth_weight = use_dynamic_smooth_weight
         self.texture_method = texture_method
         self.group = group
+        self.fused_collective = fused_collective
+        self._peer = None
 
     def __call__(self, img_low: torch.Tensor) -> torch.Tensor:
         if not self.use_dynamic_smooth_weight:
             return torch.tensor(self.weight_smooth, dtype=torch.float32, device=img_low.device)
+        if self.fused_collective and img_low.is_cuda:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                if self._peer is None:
+                    self._peer = PeerBatchStats(img_low.device, self.group)
+                p = self._peer
+                return native.texture_weight_peer(img_low, self.texture_method, self.weight_smooth, p.table, p.rank, p.world,
+                                                  p.next_seq())[2]
+            return native.texture_weight_peer(img_low, self.texture_method, self.weight_smooth, None, 0, 1, 1)[2]
         _per_image, stats = batch_texture_stats(img_low, self.texture_method)
         all_reduce_batch_stats(stats, self.group)
         return weight_from_stats(stats, self.weight_smooth)

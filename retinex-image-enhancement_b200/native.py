@@ -87,6 +87,9 @@ def _declare(lib):
     lib.upr_texture_tv_f32.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     lib.upr_texture_edge_density_f32.restype = i32
     lib.upr_texture_edge_density_f32.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.upr_peer_stats_buffer_bytes.restype = sz
+    lib.upr_texture_weight_peer_f32.restype = i32
+    lib.upr_texture_weight_peer_f32.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, i32, i32, C.c_uint, f32, vp, vp]
     lib.upr_dynamic_smooth_weight_f32.restype = i32
     lib.upr_dynamic_smooth_weight_f32.argtypes = [vp, f32, vp, vp]
 
@@ -446,6 +449,29 @@ def texture_complexity(x: torch.Tensor, method: str = "tv", want_batch_stats: bo
         check(fn(x.data_ptr(), b, c, h, w, out.data_ptr(), stats.data_ptr() if stats is not None else None,
                  ws.data_ptr(), ws.numel(), _stream()), f"upr_texture_{method}_f32")
     return (out, stats) if want_batch_stats else out
+
+
+def texture_weight_peer(x: torch.Tensor, method: str, weight_smooth: float, peer_table: Optional[torch.Tensor], rank: int,
+                        world: int, seq: int):
+    """One kernel per rank: per-image texture complexity, the [sum, count] exchange with every peer over NVLink-mapped
+    symmetric memory, and the dynamic smoothness weight (upr_texture_weight_peer_f32).
+    -> (per_image [B], stats [2] over all ranks, weight 0-dim).  peer_table: int64 CUDA tensor of `world` buffer addresses
+    (None = single process)."""
+    if method not in ("tv", "edge_density"):
+        raise ValueError(f"unsupported texture complexity method: {method}")
+    x = _require_cuda_f32(x, "x")
+    b, c, h, w = x.shape
+    out = torch.empty((b,), dtype=torch.float32, device=x.device)
+    stats = torch.empty((2,), dtype=torch.float32, device=x.device)
+    weight = torch.empty((), dtype=torch.float32, device=x.device)
+    L = lib()
+    with torch.cuda.device(x.device):
+        ws = zero_workspace("tex", L.upr_texture_workspace_bytes(b), x.device)
+        check(L.upr_texture_weight_peer_f32(x.data_ptr(), b, c, h, w, 0 if method == "tv" else 1, out.data_ptr(), stats.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), peer_table.data_ptr() if peer_table is not None else None,
+                                            int(rank), int(world), int(seq), float(weight_smooth), weight.data_ptr(), _stream()),
+              "upr_texture_weight_peer_f32")
+    return out, stats, weight
 
 
 def dynamic_smooth_weight(batch_stats2: torch.Tensor, weight_smooth: float = 1.0) -> torch.Tensor:

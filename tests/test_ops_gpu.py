@@ -308,3 +308,31 @@ def test_content_aware_apply_fused(native):
         out, att2 = native.content_aware_apply(dev(xs), dev(enh), want_attention=True)
         assert torch.equal(out, ref) and torch.equal(att2, att)
         assert torch.equal(native.content_aware_apply(dev(xs), dev(enh)), ref)
+
+
+def test_fused_peer_allreduce_two_gpus():
+    """upr_texture_weight_peer_f32 under torchrun on two GPUs: bit-equal to statistics kernel + NCCL all-reduce + weight kernel on
+    every rank, every step (unequal local batches included).  Skipped on single-GPU boxes; scripts/peer_allreduce_check.py."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "scripts", "peer_allreduce_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+    assert json.loads(line)["weights_equal_to_nccl_path_and_across_ranks"] is True
+
+
+def test_texture_weight_peer_single_process(native):
+    """Without a peer table the fused entry is statistics + weight in one kernel: equal to the two-kernel path."""
+    x = dev(O.kat_input(31, 64, 96, "uniform").repeat(4, axis=0) * np.linspace(0.2, 1.0, 4, dtype=np.float32)[:, None, None, None])
+    for method in ("tv", "edge_density"):
+        per, stats = native.texture_complexity(x, method, want_batch_stats=True)
+        w_ref = native.dynamic_smooth_weight(stats, 1.3)
+        per2, stats2, w = native.texture_weight_peer(x, method, 1.3, None, 0, 1, 1)
+        assert torch.equal(per, per2) and torch.equal(stats, stats2) and torch.equal(w, w_ref)
