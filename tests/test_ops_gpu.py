@@ -338,3 +338,24 @@ def test_texture_weight_peer_single_process(native):
         w_ref = native.dynamic_smooth_weight(stats, 1.3)
         per2, stats2, w = native.texture_weight_peer(x, method, 1.3, None, 0, 1, 1)
         assert torch.equal(per, per2) and torch.equal(stats, stats2) and torch.equal(w, w_ref)
+
+
+def test_ops_are_cuda_graph_capturable(native):
+    """Every entry point is asynchronous on the caller's stream and never synchronises: the whole enhance arithmetic can be
+    captured once in a CUDA graph and replayed on new data (the persistent map kernel's work-queue reset is a memset node)."""
+    x = dev(O.kat_input(41, 400, 600, "dark"))
+    e = dev(np.random.default_rng(42).random((1, 3, 400, 600), dtype=np.float32))
+    illu = (x[:, :1] * 0.5 + 0.25).contiguous()
+    refs = (native.clahe_lab(x), native.retinex_clahe(x, illu, e), native.content_aware_apply(x, e), native.multiscale_stats(x)[1])
+    torch.cuda.synchronize()
+    xs, es, ils = x.clone(), e.clone(), illu.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = (native.clahe_lab(xs), native.retinex_clahe(xs, ils, es), native.content_aware_apply(xs, es), native.multiscale_stats(xs)[1])
+    xs.zero_(); es.zero_(); ils.fill_(1.0)      # replay must recompute from the CURRENT contents of the captured buffers
+    g.replay()
+    xs.copy_(x); es.copy_(e); ils.copy_(illu)
+    g.replay()
+    torch.cuda.synchronize()
+    for got, ref in zip(outs, refs):
+        assert torch.equal(got, ref)
