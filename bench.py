@@ -469,7 +469,7 @@ def bench_c5(torch, dist, rank, world, local, args):
                        "h": h, "w": w, "l2": "inputs larger than L2"},
             "clocks": clk.summary(), "gpu_launches": 4 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "attention chain (k_saliency_stream + k_sal_normalize + k_att_normalize)", "kernel_ms": k_att,
+                         "kernel": "upr_attention_f32 chain (k_saliency_stream + k_sal_normalize + k_att_normalize)", "kernel_ms": k_att,
                          "peak_source": peak_src,
                          "op": {"algorithmic_bytes_per_px": 36, "achieved": 36.0 * px / (ms_step / 1e3) / 1e9,
                                 "frac": 36.0 * px / (ms_step / 1e3) / 1e9 / peak}}}
