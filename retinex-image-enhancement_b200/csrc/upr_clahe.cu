@@ -56,6 +56,7 @@ struct ClaheGeom {
     float lut_scale;   // 255 / (tw*th)
     int nstrips;       // K1 row strips per tile
     int strip_rows;
+    int lab_mod;       // development (timing only, WRONG results): frame f uses the Lab planes of frame f % lab_mod
     uint32_t gam_bias; // 0 - 4 * 0x4B000000, passed as a PARAMETER: ptxas splits a compile-time constant off the gamma
                        // table address again and re-adds it per gather (one extra instruction per table lookup)
 };
@@ -65,6 +66,7 @@ struct MapGeom {
     int tiles_x, tiles_y;
     float inv_tw, inv_th;
     int nstrips;
+    int lab_mod;       // development (timing only): see ClaheGeom
     int bx[kMaxTiles + 2];  // cell c covers x in [bx[c], bx[c+1]); raw tile index of the cell is c-1
     int by[kMaxTiles + 2];
 };
@@ -537,7 +539,7 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
     const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;      // fast path: 3 * plane < 2^32
     // item offsets count 4-pixel groups: a float4 of the input and a u32 word of the Lab planes share the same index
     const float4* inT = reinterpret_cast<const float4*>(in) + size_t(f) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
-    uint32_t* labT = reinterpret_cast<uint32_t*>(lab) + size_t(f) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
+    uint32_t* labT = reinterpret_cast<uint32_t*>(lab) + size_t(f % g.lab_mod) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
 
     const int dr = kK1Threads / tw4, dc = kK1Threads - dr * tw4;
     const uint32_t dstep = uint32_t(dr) * w4 + uint32_t(dc), dwrap = w4 - uint32_t(tw4);
@@ -909,6 +911,11 @@ k_hist_lab_vec3(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
 // address is one IMAD.WIDE, the prefetch target is the same offset plus a constant.  (The 16 spare threads of the last
 // warp idle in the main loop and own a histogram bin in the epilogue.)  Same arithmetic (k1_item): bit-identical output.
 // ---------------------------------------------------------------------------------------------
+// kCluster: the CTAs of one tile ROW form a thread-block cluster and meet at a cluster barrier every four iterations, so
+// that together they stream whole image rows (7680 contiguous bytes per plane at 1080p) instead of eight unrelated
+// 960-byte segments: measured with a traffic-only kernel (scripts/dev/pattern_probe.cu), 12 B/px read + 3 B/px written
+// takes 0.44 ms in the tile pattern and 0.37-0.39 ms in full-row bands.
+template <int kSets, bool kCluster>   // kSets register sets: global loads run kSets - 1 iterations ahead of their use
 __global__ void __launch_bounds__(kK1Threads, 3)
 k_hist_lab_vec4(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
                 uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g)
@@ -921,9 +928,12 @@ k_hist_lab_vec4(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
     __shared__ int s_flag;
 
     const int tid = threadIdx.x;
-    const int strip = blockIdx.x % g.nstrips;
-    const int tile = blockIdx.x / g.nstrips;
-    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    // band order: consecutive CTAs are the SAME row strip of the tiles of one tile row, so that the CTAs that run together
+    // stream full-width bands of the frame (see pattern_probe.cu: the tile pattern costs 12-19 % of the DRAM throughput)
+    const int tx = blockIdx.x % g.tiles_x;
+    const int strip = (blockIdx.x / g.tiles_x) % g.nstrips;
+    const int ty = blockIdx.x / (g.tiles_x * g.nstrips);
+    const int tile = ty * g.tiles_x + tx;
     const int f = blockIdx.y;
     const int ntiles = g.tiles_x * g.tiles_y;
 
@@ -959,29 +969,31 @@ k_hist_lab_vec4(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
     // per-THREAD plane bases (frame, tile column, this thread's 4-pixel column): a base that lives in vector registers
     // lets ptxas address base[o] with one IMAD.WIDE.U32 (block-uniform bases end up in uniform registers and cost a
     // shift, a multiply-high and two 64-bit adds per access).  Row offsets count 4-pixel groups: a float4 of the input
-    // and a u32 word of the Lab planes share the same index.
+    // and a u32 word of the Lab planes share the same index.  With three register sets the G/B (a/b) planes are reached
+    // through the 32-bit index instead of their own base pointers (registers).
     // (opaque_ptr: otherwise the front end re-associates base + (K + o) back onto the kernel parameter)
     const float4* inR = opaque_ptr(reinterpret_cast<const float4*>(in) + (size_t(f) * 3 * plane4 + uint32_t(tx * tw4 + lc)));
-    const float4* inG = opaque_ptr(inR + plane4);
-    const float4* inB = opaque_ptr(inG + plane4);
+    const float4* inG = kSets == 2 ? opaque_ptr(inR + plane4) : inR;
+    const float4* inB = kSets == 2 ? opaque_ptr(inG + plane4) : inR;
     uint32_t* labL = opaque_ptr(reinterpret_cast<uint32_t*>(lab) + (size_t(f) * 3 * plane4 + uint32_t(tx * tw4 + lc)));
-    uint32_t* labA = opaque_ptr(labL + plane4);
-    uint32_t* labB = opaque_ptr(labA + plane4);
+    uint32_t* labA = kSets == 2 ? opaque_ptr(labL + plane4) : labL;
+    uint32_t* labB = kSets == 2 ? opaque_ptr(labA + plane4) : labL;
+    const uint32_t pG = kSets == 2 ? 0u : plane4, pB = kSets == 2 ? 0u : 2u * plane4;
 
     auto load = [&](uint32_t o, float4& r, float4& gch, float4& b) {
         r = ld_nc_f4(inR + o);
-        gch = ld_nc_f4(inG + o);
-        b = ld_nc_f4(inB + o);
+        gch = ld_nc_f4(inG + (o + pG));
+        b = ld_nc_f4(inB + (o + pB));
     };
     auto prefetch = [&](uint32_t o) {
         prefetch_l2(inR + o);
-        prefetch_l2(inG + o);
-        prefetch_l2(inB + o);
+        prefetch_l2(inG + (o + pG));
+        prefetch_l2(inB + (o + pB));
     };
     auto store = [&](uint32_t o, uint32_t wl, uint32_t wa, uint32_t wb) {
         st_global_u32(labL + o, wl);
-        st_global_u32(labA + o, wa);
-        st_global_u32(labB + o, wb);
+        st_global_u32(labA + (o + pG), wa);
+        st_global_u32(labB + (o + pB), wb);
     };
 
     int row = row0 + lr;
@@ -995,6 +1007,50 @@ k_hist_lab_vec4(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
         for (int k = 1; k < kPf; ++k)
             if (row + k * rpi < row1) prefetch(o + uint32_t(k) * step);
     }
+    if constexpr (kSets == 3) {
+        float4 cr, cg, cb;
+        const int row_ld2 = row1 - 2 * rpi;
+        if (row < row_ld) load(o + step, br, bg, bb);
+        auto phase = [&](const float4& xr, const float4& xg, const float4& xb, float4& zr, float4& zg, float4& zb) -> bool {
+            uint32_t wl, wa, wb;
+            if (row < row_ld2) load(o + 2u * step, zr, zg, zb);
+            if (row < row_pf) prefetch(o + pfo);
+            k1_item<false>(xr, xg, xb, t, s_cnt, tid4, wl, wa, wb);
+            store(o, wl, wa, wb);
+            row += rpi;
+            o += step;
+            return row < row1;
+        };
+        while (row < row1) {
+            if (!phase(ar, ag, ab, cr, cg, cb)) break;
+            if (!phase(br, bg, bb, ar, ag, ab)) break;
+            if (!phase(cr, cg, cb, br, bg, bb)) break;
+        }
+    } else if constexpr (kCluster) {
+        // block- and cluster-uniform trip count (every thread of every CTA of the tile row reaches every barrier)
+        const int rows_all = min(row0 + g.strip_rows, (ty + 1) * g.th) - row0;
+        const int niter = (rows_all + rpi - 1) / rpi;
+        for (int it = 0; it < niter; it += 2) {
+            uint32_t wl, wa, wb;
+            if (row < row1) {
+                if (row < row_ld) load(o + step, br, bg, bb);
+                if (row < row_pf) prefetch(o + pfo);
+                k1_item<false>(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
+                store(o, wl, wa, wb);
+                row += rpi;
+                o += step;
+            }
+            if (row < row1) {
+                if (row < row_ld) load(o + step, ar, ag, ab);
+                if (row < row_pf) prefetch(o + pfo);
+                k1_item<false>(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
+                store(o, wl, wa, wb);
+                row += rpi;
+                o += step;
+            }
+            if (it & 2) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+        }
+    } else {
     while (row < row1) {
         uint32_t wl, wa, wb;
         if (row < row_ld) load(o + step, br, bg, bb);
@@ -1010,6 +1066,7 @@ k_hist_lab_vec4(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
         store(o, wl, wa, wb);
         row += rpi;
         o += step;
+    }
     }
     __syncthreads();
 
@@ -1307,7 +1364,7 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
         const int y0 = g.by[cy] + strip * srows;
         const int y1 = min(y0 + srows, g.by[cy + 1]);
 
-        const uint32_t* labL = reinterpret_cast<const uint32_t*>(lab) + size_t(f) * 3 * plane4;
+        const uint32_t* labL = reinterpret_cast<const uint32_t*>(lab) + size_t(f % g.lab_mod) * 3 * plane4;
         float4* outR = reinterpret_cast<float4*>(out) + size_t(f) * 3 * plane4;
         const float txbase = float(cx - 1), tybase = float(cy - 1);
         const int cw4 = (x1 - x0) >> 2;
@@ -1499,6 +1556,8 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
     if (clip_limit > 0.0) g.clip = std::max(int(clip_limit * area / 256), 1);
     g.lut_scale = float(255) / float(area);
     g.gam_bias = 0u - 4u * 0x4B000000u;
+    const char* lm = std::getenv("UPR_LAB_MOD");   // development switch (timing experiment, wrong results)
+    g.lab_mod = lm ? std::max(1, std::atoi(lm)) : 0x7fffffff;
     const float inv_tw = 1.0f / float(g.tw), inv_th = 1.0f / float(g.th);
 
     // interpolation cell boundaries from the exact fp32 recipe (monotone in p)
@@ -1506,6 +1565,7 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
     bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && aligned16(in) && aligned16(out) &&
                 size_t(h) * w * 3 < (size_t(1) << 32) && (!rx || (aligned16(rx->illu) && aligned16(rx->e)));
     if (fast) {
+        m.lab_mod = g.lab_mod;
         m.n = n; m.h = h; m.w = w; m.tiles_x = tiles_x; m.tiles_y = tiles_y; m.inv_tw = inv_tw; m.inv_th = inv_th;
         int c = 0;
         m.bx[0] = 0;
@@ -1571,10 +1631,27 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                     k_hist_lab_vec<<<grid1, kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
                                                                          lut + ftile * 256, tickets + ftile, g);
                 } else if ((variant() & 64) && tw4 <= kK1Threads) {
-                    static unsigned long long m7 = 0;
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec4, smem1, m7));
-                    k_hist_lab_vec4<<<grid1, kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
-                                                                          lut + ftile * 256, tickets + ftile, g);
+                    static unsigned long long m7 = 0, m8 = 0, m9 = 0;
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec4<2, false>, smem1, m7));
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec4<3, false>, smem1, m8));
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec4<2, true>, smem1, m9));
+                    int32_t* a_hist = hist + ftile * 256;
+                    uint8_t* a_lut = lut + ftile * 256;
+                    unsigned* a_tick = tickets + ftile;
+                    const float* a_in = in + fplane;
+                    uint8_t* a_lab = lab + fplane;
+                    if ((variant() & 256) && g.nstrips == 1 && tiles_x <= 8 && ntiles % tiles_x == 0) {
+                        cudaLaunchConfig_t cfg{};
+                        cfg.gridDim = grid1; cfg.blockDim = dim3(kK1Threads); cfg.dynamicSmemBytes = smem1; cfg.stream = stream;
+                        cudaLaunchAttribute at[1];
+                        at[0].id = cudaLaunchAttributeClusterDimension;
+                        at[0].val.clusterDim.x = unsigned(tiles_x); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                        cfg.attrs = at; cfg.numAttrs = 1;
+                        UPR_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_hist_lab_vec4<2, true>, a_in, a_lab, a_hist, a_lut, a_tick, g));
+                    } else if (variant() & 128)
+                        k_hist_lab_vec4<3, false><<<grid1, kK1Threads, smem1, stream>>>(a_in, a_lab, a_hist, a_lut, a_tick, g);
+                    else
+                        k_hist_lab_vec4<2, false><<<grid1, kK1Threads, smem1, stream>>>(a_in, a_lab, a_hist, a_lut, a_tick, g);
                 } else if (variant() & 32) {
                     // persistent third generation: one queue head (work[1]; work[0] belongs to the map kernel)
                     static unsigned long long m6 = 0;

@@ -1,6 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/../.."
-for F in 2 4 8; do
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --cache-control none --clock-control none -k regex:k_ --csv --log-file gpurun_out/r3_l2probe_F$F.csv python scripts/dev/l2_probe.py $F > gpurun_out/r3_l2probe_F$F.log 2>&1
+O=gpurun_out/r3_labmod.log
+: > $O
+for m in 0 16 8 4 2; do
+  if [ $m = 0 ]; then timeout 120 python scripts/stage_bench.py >> $O 2>&1; else UPR_LAB_MOD=$m timeout 120 python scripts/stage_bench.py >> $O 2>&1; fi
 done
-tail -3 gpurun_out/r3_l2probe_F4.log
+tail -40 $O
