@@ -6,7 +6,7 @@
 //   -> LAB2BGR -> BGR2RGB -> /255
 // with two kernels per batch and a 3 B/px u8 Lab intermediate:
 //
-//   K1  k_hist_lab_vec2  one CTA per (frame, tile, row-strip): planar f32 RGB -> u8 quantise -> OpenCV fixed-point
+//   K1  k_hist_lab_vec3  one CTA per (frame, tile, row-strip): planar f32 RGB -> u8 quantise -> OpenCV fixed-point
 //                        Lab; stores L,a,b (u8 planes); per-THREAD private byte counters in shared memory build the
 //                        tile histogram without atomics; the CTA (or the last strip CTA of the tile) then does
 //                        clip -> redistribute -> prefix scan -> LUT in place.
@@ -14,7 +14,8 @@
 //                        that surround a cell are interleaved into one 32-bit word per grey level, so the bilinear
 //                        LUT interpolation costs ONE shared-memory lookup per pixel; fused with Lab -> sRGB (integer
 //                        path) and the /255 de-quantisation.
-//   (k_hist_lab_vec / k_map_vec are the first generations, kept behind UPR_CLAHE_VARIANT for A/B timing;
+//   (k_hist_lab_vec / k_map_vec are the first generations, k_hist_lab_vec2 the second one -- also the body of the fused
+//    Retinex prologue -- kept behind UPR_CLAHE_VARIANT for A/B timing;
 //    k_*_generic handle ragged shapes incl. OpenCV's padding quirk.)
 //
 // All fixed-point recipes follow SURVEY.md Appendix A (pinned against the cv2 binary by the
@@ -56,7 +57,6 @@ struct ClaheGeom {
     float lut_scale;   // 255 / (tw*th)
     int nstrips;       // K1 row strips per tile
     int strip_rows;
-    int lab_mod;       // development (timing only, WRONG results): frame f uses the Lab planes of frame f % lab_mod
     uint32_t gam_bias; // 0 - 4 * 0x4B000000, passed as a PARAMETER: ptxas splits a compile-time constant off the gamma
                        // table address again and re-adds it per gather (one extra instruction per table lookup)
 };
@@ -66,7 +66,6 @@ struct MapGeom {
     int tiles_x, tiles_y;
     float inv_tw, inv_th;
     int nstrips;
-    int lab_mod;       // development (timing only): see ClaheGeom
     int bx[kMaxTiles + 2];  // cell c covers x in [bx[c], bx[c+1]); raw tile index of the cell is c-1
     int by[kMaxTiles + 2];
 };
@@ -406,14 +405,9 @@ struct K1Tables {
 };
 
 // 12 floats (4 px x RGB) -> three Lab words + four counter increments
-// kRep: the gamma table is replicated once per lane, [entry][lane] -> entry stride 128 bytes, with the lane's byte offset
-// already folded into t.gam_q / t.gam: lane l only ever touches bank l, so the three gamma gathers of a pixel are one
-// shared-memory wavefront each whatever the image content (noise frames: x2.2 with the plain table).
-template <bool kRep>
 __device__ __forceinline__ void k1_item(const float4 vr, const float4 vg, const float4 vb, const K1Tables& t,
                                         unsigned char* s_cnt, uint32_t tid4, uint32_t& wl, uint32_t& wa, uint32_t& wb)
 {
-    constexpr uint32_t kGamStride = kRep ? 128u : 4u;
     const float pr[4] = {vr.x, vr.y, vr.z, vr.w};
     const float pg[4] = {vg.x, vg.y, vg.z, vg.w};
     const float pb[4] = {vb.x, vb.y, vb.z, vb.w};
@@ -427,16 +421,16 @@ __device__ __forceinline__ void k1_item(const float4 vr, const float4 vg, const 
     if (m0 <= 0x3F800000u) {   // every value in [+0, 1]: as unsigned integers, positive floats order like their values
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            R[k] = lds_f32(__float_as_uint(__fadd_rz(__fmul_rn(pr[k], 255.0f), 8388608.0f)) * kGamStride + t.gam_q);
-            G[k] = lds_f32(__float_as_uint(__fadd_rz(__fmul_rn(pg[k], 255.0f), 8388608.0f)) * kGamStride + t.gam_q);
-            B[k] = lds_f32(__float_as_uint(__fadd_rz(__fmul_rn(pb[k], 255.0f), 8388608.0f)) * kGamStride + t.gam_q);
+            R[k] = lds_f32(__float_as_uint(__fadd_rz(__fmul_rn(pr[k], 255.0f), 8388608.0f)) * 4u + t.gam_q);
+            G[k] = lds_f32(__float_as_uint(__fadd_rz(__fmul_rn(pg[k], 255.0f), 8388608.0f)) * 4u + t.gam_q);
+            B[k] = lds_f32(__float_as_uint(__fadd_rz(__fmul_rn(pb[k], 255.0f), 8388608.0f)) * 4u + t.gam_q);
         }
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            R[k] = lds_f32(uint32_t(quantize_u8(pr[k])) * kGamStride + t.gam);
-            G[k] = lds_f32(uint32_t(quantize_u8(pg[k])) * kGamStride + t.gam);
-            B[k] = lds_f32(uint32_t(quantize_u8(pb[k])) * kGamStride + t.gam);
+            R[k] = lds_f32(uint32_t(quantize_u8(pr[k])) * 4u + t.gam);
+            G[k] = lds_f32(uint32_t(quantize_u8(pg[k])) * 4u + t.gam);
+            B[k] = lds_f32(uint32_t(quantize_u8(pb[k])) * 4u + t.gam);
         }
     }
     int vL[4], vA[4], vB[4], fY[4];
@@ -486,15 +480,15 @@ struct RetinexIn {
     float eps;
 };
 
-template <bool kFused, bool kRep>
-__global__ void __launch_bounds__(kK1Threads, kRep ? 2 : 3)
+template <bool kFused>
+__global__ void __launch_bounds__(kK1Threads, 3)
 k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
                 uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g, const RetinexIn rx)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
-    float* s_gammaf = reinterpret_cast<float*>(smem + 256 * kK1Threads);           // 256 x f32 (kRep: x 32 lanes)
-    uint16_t* s_cbrt = reinterpret_cast<uint16_t*>(s_gammaf + UPR_TAB_GAMMA_LEN * (kRep ? 32 : 1));  // 2048 x u16
+    float* s_gammaf = reinterpret_cast<float*>(smem + 256 * kK1Threads);           // 256 x f32
+    uint16_t* s_cbrt = reinterpret_cast<uint16_t*>(s_gammaf + UPR_TAB_GAMMA_LEN);  // 2048 x u16
     __shared__ int s_tmp[8];
     __shared__ int s_flag;
 
@@ -509,24 +503,15 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
         uint4* z = reinterpret_cast<uint4*>(s_cnt);
 #pragma unroll
         for (int i = 0; i < 256 * kK1Threads / 16 / kK1Threads; ++i) z[tid + i * kK1Threads] = make_uint4(0, 0, 0, 0);
-        if constexpr (kRep) {
-            const float gv = float(d_gamma[tid]);   // thread `tid` writes the 32 copies of entry `tid` (128 contiguous bytes)
-            float4* row = reinterpret_cast<float4*>(s_gammaf + tid * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) row[(i + tid) & 7] = make_float4(gv, gv, gv, gv);
-        } else {
-            s_gammaf[tid] = float(d_gamma[tid]);
-        }
+        s_gammaf[tid] = float(d_gamma[tid]);
         reinterpret_cast<uint4*>(s_cbrt)[tid] = reinterpret_cast<const uint4*>(d_cbrt)[tid];  // 256 x 16 B = 4 KB
     }
     __syncthreads();
 
     const uint32_t zero = blockIdx.z;  // always 0: keeps the constants below in registers (see wide_addr)
     K1Tables t;
-    constexpr uint32_t kGamStride = kRep ? 128u : 4u;
-    t.gam = uint32_t(__cvta_generic_to_shared(s_gammaf)) + (kRep ? uint32_t(tid & 31) * 4u : 0u);
-    // (the constant is xor-ed with a run-time zero: a plain immediate is split off again by ptxas and re-added per gather)
-    t.gam_q = kRep ? t.gam + ((0u - kGamStride * 0x4B000000u) ^ zero) : opaque(t.gam - kGamStride * 0x4B000000u);
+    t.gam = uint32_t(__cvta_generic_to_shared(s_gammaf));
+    t.gam_q = opaque(t.gam - 4u * 0x4B000000u);
     t.cbr_q = opaque(uint32_t(__cvta_generic_to_shared(s_cbrt)) - 2u * 0x4B000000u);
     t.four = opaque(4u + zero);
     t.sixteen = opaque(16u + zero);
@@ -539,7 +524,7 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
     const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;      // fast path: 3 * plane < 2^32
     // item offsets count 4-pixel groups: a float4 of the input and a u32 word of the Lab planes share the same index
     const float4* inT = reinterpret_cast<const float4*>(in) + size_t(f) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
-    uint32_t* labT = reinterpret_cast<uint32_t*>(lab) + size_t(f % g.lab_mod) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
+    uint32_t* labT = reinterpret_cast<uint32_t*>(lab) + size_t(f) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
 
     const int dr = kK1Threads / tw4, dc = kK1Threads - dr * tw4;
     const uint32_t dstep = uint32_t(dr) * w4 + uint32_t(dc), dwrap = w4 - uint32_t(tw4);
@@ -648,43 +633,9 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
             if (i < nitems) load7(pin, pil);
             prefetch7();
             uint32_t wl, wa, wb;
-            k1_item<kRep>(er, eg, eb, t, s_cnt, tid4, wl, wa, wb);
+            k1_item(er, eg, eb, t, s_cnt, tid4, wl, wa, wb);
             store(plab, wl, wa, wb);
             plab = const_cast<char*>(wide_imm<4>(plab, st1));
-        }
-    } else if constexpr (kRep) {
-        // 2 CTAs per SM leave 128 registers per thread: three register sets, global loads TWO items ahead of their use
-        // (with 16 instead of 24 warps per SM one item of distance no longer covers the L2 latency)
-        float4 ar, ag, ab, br, bg, bb, cr, cg, cb;
-        int i = tid;
-        const char* pld = pin;
-        uint32_t sA = 0;
-        if (i < nitems) load(pld, ar, ag, ab);
-        if (i + kK1Threads < nitems) {
-            sA = advance(c);
-            pld = wide_imm<16>(pld, sA);
-            load(pld, br, bg, bb);
-        }
-        auto phase = [&](const float4& xr, const float4& xg, const float4& xb, float4& zr, float4& zg, float4& zb) -> bool {
-            uint32_t sB = 0;
-            if (i + 2 * kK1Threads < nitems) {
-                sB = advance(c);
-                pld = wide_imm<16>(pld, sB);
-                load(pld, zr, zg, zb);
-            }
-            prefetch_next();
-            uint32_t wl, wa, wb;
-            k1_item<kRep>(xr, xg, xb, t, s_cnt, tid4, wl, wa, wb);
-            store(plab, wl, wa, wb);
-            plab = const_cast<char*>(wide_imm<4>(plab, sA));
-            sA = sB;
-            i += kK1Threads;
-            return i < nitems;
-        };
-        while (i < nitems) {
-            if (!phase(ar, ag, ab, cr, cg, cb)) break;
-            if (!phase(br, bg, bb, ar, ag, ab)) break;
-            if (!phase(cr, cg, cb, br, bg, bb)) break;
         }
     } else {
     float4 ar, ag, ab, br, bg, bb;
@@ -696,7 +647,7 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
         if (i2 < nitems) load(wide_imm<16>(pin, st1), br, bg, bb);
         prefetch_next();
         uint32_t wl, wa, wb;
-        k1_item<kRep>(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
+        k1_item(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
         store(plab, wl, wa, wb);
         if (i2 >= nitems) break;
         const uint32_t st2 = advance(c);
@@ -704,7 +655,7 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
         i = i2 + kK1Threads;
         if (i < nitems) load(pin, ar, ag, ab);
         prefetch_next();
-        k1_item<kRep>(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
+        k1_item(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
         store(const_cast<char*>(wide_imm<4>(plab, st1)), wl, wa, wb);
         plab = const_cast<char*>(wide_imm<4>(plab, st1 + st2));
     }
@@ -734,190 +685,19 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1 fast path, third generation: PERSISTENT CTAs.  Measured on the second generation (profiles/r3_clahe.md): every extra
-// CTA of the (frame, tile, strip) grid costs ~5 us of SM time (64 x 1080p: 4096 CTAs 0.402 ms, 8192 half-tile CTAs
-// 0.451 ms) -- table staging, a cold load pipeline, the drain before the counter reduction, the CTA hand-over.  Here a
-// CTA stays resident (3 per SM), pulls items from an atomic queue, stages its tables once, and issues the first loads and
-// the L2 prefetches of the NEXT item before it reduces the counters of the current one, so the load pipeline never runs
-// dry.  The reduction also clears the counters (each row of counters is read and then zeroed by the same four lanes).
-// Same arithmetic as the second generation (k1_item): bit-identical Lab planes, histograms and LUTs.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kK1Threads, 3)
-k_hist_lab_vec3(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
-                uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g, unsigned* __restrict__ work,
-                int total_items)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
-    float* s_gammaf = reinterpret_cast<float*>(smem + 256 * kK1Threads);           // 256 x f32
-    uint16_t* s_cbrt = reinterpret_cast<uint16_t*>(s_gammaf + UPR_TAB_GAMMA_LEN);  // 2048 x u16
-    __shared__ int s_tmp[8];
-    __shared__ int s_flag;
-    __shared__ int s_nxt[2];
-
-    const int tid = threadIdx.x;
-    const int ntiles = g.tiles_x * g.tiles_y;
-    int cur = blockIdx.x;
-    {
-        uint4* z = reinterpret_cast<uint4*>(s_cnt);
-#pragma unroll
-        for (int i = 0; i < 256 * kK1Threads / 16 / kK1Threads; ++i) z[tid + i * kK1Threads] = make_uint4(0, 0, 0, 0);
-        s_gammaf[tid] = float(d_gamma[tid]);
-        reinterpret_cast<uint4*>(s_cbrt)[tid] = reinterpret_cast<const uint4*>(d_cbrt)[tid];  // 256 x 16 B = 4 KB
-        if (tid == 0) s_nxt[0] = int(gridDim.x + atomicAdd(work, 1u));
-    }
-    __syncthreads();
-
-    const uint32_t zero = blockIdx.z;  // always 0: keeps the constants below in registers (see wide_addr)
-    K1Tables t;
-    t.gam = uint32_t(__cvta_generic_to_shared(s_gammaf));
-    t.gam_q = opaque(t.gam - 4u * 0x4B000000u);
-    t.cbr_q = opaque(uint32_t(__cvta_generic_to_shared(s_cbrt)) - 2u * 0x4B000000u);
-    t.four = opaque(4u + zero);
-    t.sixteen = opaque(16u + zero);
-
-    const int tw4 = g.tw >> 2;
-    const uint32_t w4 = uint32_t(g.w) >> 2;
-    const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;      // fast path: 3 * plane < 2^32
-    const int dr = kK1Threads / tw4, dc = kK1Threads - dr * tw4;
-    const uint32_t dstep = uint32_t(dr) * w4 + uint32_t(dc), dwrap = w4 - uint32_t(tw4);
-    const uint32_t tid4 = uint32_t(tid) * 4u;
-    const int c0 = tid % tw4;
-    const uint32_t off0 = uint32_t(tid / tw4) * w4 + uint32_t(c0);     // this thread's first 4-pixel group inside a strip
-    constexpr int kPfAhead = 6;
-
-    auto load = [&](const char* p, float4& r, float4& gch, float4& b) {
-        r = ld_nc_f4(p);
-        gch = ld_nc_f4(wide_imm<16>(p, plane4));
-        b = ld_nc_f4(wide_imm<32>(p, plane4));
-    };
-    auto store = [&](char* p, uint32_t wl, uint32_t wa, uint32_t wb) {
-        st_global_u32(p, wl);
-        st_global_u32(wide_imm<4>(p, plane4), wa);
-        st_global_u32(wide_imm<8>(p, plane4), wb);
-    };
-
-    // per-item streaming state
-    int nitems = 0, c = 0, cpf = 0, ipf = 0;
-    const char* pin = nullptr;
-    const char* ppf = nullptr;
-    char* plab = nullptr;
-    size_t t_idx = 0;
-    float4 ar, ag, ab, br, bg, bb;
-
-    auto advance = [&](int& cc) -> uint32_t {
-        cc += dc;
-        uint32_t st = dstep;
-        if (cc >= tw4) { cc -= tw4; st += dwrap; }
-        return st;
-    };
-    auto prefetch_next = [&]() {
-        ipf += kK1Threads;
-        cpf += dc;
-        uint32_t st = dstep;
-        if (cpf >= tw4) { cpf -= tw4; st += dwrap; }
-        ppf = wide_imm<16>(ppf, st);
-        if (ipf < nitems) {
-            prefetch_l2(ppf);
-            prefetch_l2(wide_imm<16>(ppf, plane4));
-            prefetch_l2(wide_imm<32>(ppf, plane4));
-        }
-    };
-    // decode an item, request its first 4-pixel group and start the L2 prefetch stream
-    auto open_item = [&](int item) {
-        const int strip = item % g.nstrips;
-        const int ft = item / g.nstrips;                 // frame * ntiles + tile
-        const int f = ft / ntiles, tile = ft - f * ntiles;
-        const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-        const int row0 = ty * g.th + strip * g.strip_rows;
-        const int row1 = min(row0 + g.strip_rows, (ty + 1) * g.th);
-        nitems = max(row1 - row0, 0) * tw4;
-        t_idx = size_t(ft);
-        const size_t base4 = size_t(f) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4) + off0;
-        pin = reinterpret_cast<const char*>(reinterpret_cast<const float4*>(in) + base4);
-        plab = reinterpret_cast<char*>(reinterpret_cast<uint32_t*>(lab) + base4);
-        c = c0;
-        cpf = c0;
-        ppf = pin;
-        ipf = tid;
-        if (tid < nitems) load(pin, ar, ag, ab);
-#pragma unroll 1
-        for (int k = 0; k < kPfAhead; ++k) prefetch_next();
-    };
-
-    if (cur < total_items) open_item(cur);
-    for (int buf = 0; cur < total_items; buf ^= 1) {
-        const int nxt = s_nxt[buf];
-        if (tid == 0) s_nxt[buf ^ 1] = int(gridDim.x + atomicAdd(work, 1u));
-        const size_t cur_tidx = t_idx;
-
-        int i = tid;
-        while (i < nitems) {
-            const uint32_t st1 = advance(c);
-            const int i2 = i + kK1Threads;
-            if (i2 < nitems) load(wide_imm<16>(pin, st1), br, bg, bb);
-            prefetch_next();
-            uint32_t wl, wa, wb;
-            k1_item<false>(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
-            store(plab, wl, wa, wb);
-            if (i2 >= nitems) break;
-            const uint32_t st2 = advance(c);
-            pin = wide_imm<16>(pin, st1 + st2);
-            i = i2 + kK1Threads;
-            if (i < nitems) load(pin, ar, ag, ab);
-            prefetch_next();
-            k1_item<false>(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
-            store(const_cast<char*>(wide_imm<4>(plab, st1)), wl, wa, wb);
-            plab = const_cast<char*>(wide_imm<4>(plab, st1 + st2));
-        }
-        // the next item's first loads and prefetches fly while this item's counters are reduced
-        if (nxt < total_items) open_item(nxt);
-        __syncthreads();
-
-        // thread `tid` sums bin `tid`: byte (tid&3) of the 256 words of row (tid>>2).  The four threads of a row read the
-        // same 16-byte chunks (broadcast); chunk order is rotated by the row so that the eight rows of a warp hit disjoint
-        // banks.  The same four lanes then clear the row for the next item.
-        unsigned total_u = 0;
-        {
-            uint4* row = reinterpret_cast<uint4*>(s_cnt + (tid >> 2) * (kK1Threads * 4));
-            const unsigned sel = 1u << (8 * (tid & 3));
-#pragma unroll 8
-            for (int k = 0; k < kK1Threads / 4; ++k) {
-                const uint4 v = row[(k + (tid >> 2)) & (kK1Threads / 4 - 1)];
-                total_u = __dp4a(v.x, sel, total_u);
-                total_u = __dp4a(v.y, sel, total_u);
-                total_u = __dp4a(v.z, sel, total_u);
-                total_u = __dp4a(v.w, sel, total_u);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < kK1Threads / 16; ++k)
-                row[(4 * k + (tid & 3) + (tid >> 2)) & (kK1Threads / 4 - 1)] = make_uint4(0, 0, 0, 0);
-        }
-        int total = int(total_u);
-        if (publish_hist(total, hist_g + cur_tidx * 256, tickets + cur_tidx, g.nstrips, &s_flag))
-            tile_lut_256(total, g.clip, g.lut_scale, lut_g + cur_tidx * 256, s_tmp);
-        __syncthreads();
-        cur = nxt;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1 fast path, fourth generation: COLUMN-OWNER threads.  The SASS of the second generation spends 57 of its 224
+// K1 fast path, third generation: COLUMN-OWNER threads.  The SASS of the second generation spends 57 of its 224
 // instructions per 4-pixel item on bookkeeping: a thread's items are 256 apart in the (rows x tw/4) strip, so the three
 // pointer sets (loads, L2 prefetches, Lab stores) each carry a row/column wrap, and every address is a 64-bit LEA pair.
 // Here the first nact = (256 / (tw/4)) * (tw/4) threads of the CTA own one 4-pixel column each and walk down the strip
 // rpi = nact / (tw/4) rows at a time (1080p: 240 threads, 4 rows): ONE 32-bit group offset advances by a constant, every
-// address is one IMAD.WIDE, the prefetch target is the same offset plus a constant.  (The 16 spare threads of the last
-// warp idle in the main loop and own a histogram bin in the epilogue.)  Same arithmetic (k1_item): bit-identical output.
+// address is one IMAD.WIDE.U32 against a per-thread base, the prefetch target is the same offset plus a constant.  (The
+// spare threads of the last warp idle in the main loop and own a histogram bin in the epilogue.)  Together with the
+// gamma-address bias passed as a parameter and the PRMT counter index this is 585 instead of 668 SASS instructions per
+// loop trip (two items), 263 M instead of 293 M executed warp instructions per 64 x 1080p -- at the SAME 0.402 ms: the
+// kernel is bound by its memory streams, not by issue (profiles/r3_clahe.md).  Same arithmetic (k1_item): bit-identical.
 // ---------------------------------------------------------------------------------------------
-// kCluster: the CTAs of one tile ROW form a thread-block cluster and meet at a cluster barrier every four iterations, so
-// that together they stream whole image rows (7680 contiguous bytes per plane at 1080p) instead of eight unrelated
-// 960-byte segments: measured with a traffic-only kernel (scripts/dev/pattern_probe.cu), 12 B/px read + 3 B/px written
-// takes 0.44 ms in the tile pattern and 0.37-0.39 ms in full-row bands.
-template <int kSets, bool kCluster>   // kSets register sets: global loads run kSets - 1 iterations ahead of their use
 __global__ void __launch_bounds__(kK1Threads, 3)
-k_hist_lab_vec4(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
+k_hist_lab_vec3(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
                 uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -928,12 +708,9 @@ k_hist_lab_vec4(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
     __shared__ int s_flag;
 
     const int tid = threadIdx.x;
-    // band order: consecutive CTAs are the SAME row strip of the tiles of one tile row, so that the CTAs that run together
-    // stream full-width bands of the frame (see pattern_probe.cu: the tile pattern costs 12-19 % of the DRAM throughput)
-    const int tx = blockIdx.x % g.tiles_x;
-    const int strip = (blockIdx.x / g.tiles_x) % g.nstrips;
-    const int ty = blockIdx.x / (g.tiles_x * g.nstrips);
-    const int tile = ty * g.tiles_x + tx;
+    const int strip = blockIdx.x % g.nstrips;
+    const int tile = blockIdx.x / g.nstrips;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
     const int f = blockIdx.y;
     const int ntiles = g.tiles_x * g.tiles_y;
 
@@ -969,31 +746,29 @@ k_hist_lab_vec4(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
     // per-THREAD plane bases (frame, tile column, this thread's 4-pixel column): a base that lives in vector registers
     // lets ptxas address base[o] with one IMAD.WIDE.U32 (block-uniform bases end up in uniform registers and cost a
     // shift, a multiply-high and two 64-bit adds per access).  Row offsets count 4-pixel groups: a float4 of the input
-    // and a u32 word of the Lab planes share the same index.  With three register sets the G/B (a/b) planes are reached
-    // through the 32-bit index instead of their own base pointers (registers).
+    // and a u32 word of the Lab planes share the same index.
     // (opaque_ptr: otherwise the front end re-associates base + (K + o) back onto the kernel parameter)
     const float4* inR = opaque_ptr(reinterpret_cast<const float4*>(in) + (size_t(f) * 3 * plane4 + uint32_t(tx * tw4 + lc)));
-    const float4* inG = kSets == 2 ? opaque_ptr(inR + plane4) : inR;
-    const float4* inB = kSets == 2 ? opaque_ptr(inG + plane4) : inR;
+    const float4* inG = opaque_ptr(inR + plane4);
+    const float4* inB = opaque_ptr(inG + plane4);
     uint32_t* labL = opaque_ptr(reinterpret_cast<uint32_t*>(lab) + (size_t(f) * 3 * plane4 + uint32_t(tx * tw4 + lc)));
-    uint32_t* labA = kSets == 2 ? opaque_ptr(labL + plane4) : labL;
-    uint32_t* labB = kSets == 2 ? opaque_ptr(labA + plane4) : labL;
-    const uint32_t pG = kSets == 2 ? 0u : plane4, pB = kSets == 2 ? 0u : 2u * plane4;
+    uint32_t* labA = opaque_ptr(labL + plane4);
+    uint32_t* labB = opaque_ptr(labA + plane4);
 
     auto load = [&](uint32_t o, float4& r, float4& gch, float4& b) {
         r = ld_nc_f4(inR + o);
-        gch = ld_nc_f4(inG + (o + pG));
-        b = ld_nc_f4(inB + (o + pB));
+        gch = ld_nc_f4(inG + o);
+        b = ld_nc_f4(inB + o);
     };
     auto prefetch = [&](uint32_t o) {
         prefetch_l2(inR + o);
-        prefetch_l2(inG + (o + pG));
-        prefetch_l2(inB + (o + pB));
+        prefetch_l2(inG + o);
+        prefetch_l2(inB + o);
     };
     auto store = [&](uint32_t o, uint32_t wl, uint32_t wa, uint32_t wb) {
         st_global_u32(labL + o, wl);
-        st_global_u32(labA + (o + pG), wa);
-        st_global_u32(labB + (o + pB), wb);
+        st_global_u32(labA + o, wa);
+        st_global_u32(labB + o, wb);
     };
 
     int row = row0 + lr;
@@ -1007,66 +782,21 @@ k_hist_lab_vec4(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
         for (int k = 1; k < kPf; ++k)
             if (row + k * rpi < row1) prefetch(o + uint32_t(k) * step);
     }
-    if constexpr (kSets == 3) {
-        float4 cr, cg, cb;
-        const int row_ld2 = row1 - 2 * rpi;
-        if (row < row_ld) load(o + step, br, bg, bb);
-        auto phase = [&](const float4& xr, const float4& xg, const float4& xb, float4& zr, float4& zg, float4& zb) -> bool {
-            uint32_t wl, wa, wb;
-            if (row < row_ld2) load(o + 2u * step, zr, zg, zb);
-            if (row < row_pf) prefetch(o + pfo);
-            k1_item<false>(xr, xg, xb, t, s_cnt, tid4, wl, wa, wb);
-            store(o, wl, wa, wb);
-            row += rpi;
-            o += step;
-            return row < row1;
-        };
-        while (row < row1) {
-            if (!phase(ar, ag, ab, cr, cg, cb)) break;
-            if (!phase(br, bg, bb, ar, ag, ab)) break;
-            if (!phase(cr, cg, cb, br, bg, bb)) break;
-        }
-    } else if constexpr (kCluster) {
-        // block- and cluster-uniform trip count (every thread of every CTA of the tile row reaches every barrier)
-        const int rows_all = min(row0 + g.strip_rows, (ty + 1) * g.th) - row0;
-        const int niter = (rows_all + rpi - 1) / rpi;
-        for (int it = 0; it < niter; it += 2) {
-            uint32_t wl, wa, wb;
-            if (row < row1) {
-                if (row < row_ld) load(o + step, br, bg, bb);
-                if (row < row_pf) prefetch(o + pfo);
-                k1_item<false>(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
-                store(o, wl, wa, wb);
-                row += rpi;
-                o += step;
-            }
-            if (row < row1) {
-                if (row < row_ld) load(o + step, ar, ag, ab);
-                if (row < row_pf) prefetch(o + pfo);
-                k1_item<false>(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
-                store(o, wl, wa, wb);
-                row += rpi;
-                o += step;
-            }
-            if (it & 2) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
-        }
-    } else {
     while (row < row1) {
         uint32_t wl, wa, wb;
         if (row < row_ld) load(o + step, br, bg, bb);
         if (row < row_pf) prefetch(o + pfo);
-        k1_item<false>(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
+        k1_item(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
         store(o, wl, wa, wb);
         row += rpi;
         o += step;
         if (row >= row1) break;
         if (row < row_ld) load(o + step, ar, ag, ab);
         if (row < row_pf) prefetch(o + pfo);
-        k1_item<false>(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
+        k1_item(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
         store(o, wl, wa, wb);
         row += rpi;
         o += step;
-    }
     }
     __syncthreads();
 
@@ -1294,8 +1024,7 @@ __device__ __forceinline__ void map_pixel5(uint32_t Lv, int av, int bv, float xa
     b = lds_f32(uint32_t(bo) * t.four + t.outf);
 }
 
-template <int kMaxThr, bool kAyFold>
-__global__ void __launch_bounds__(kMaxThr, 2)
+__global__ void __launch_bounds__(kK5MaxThreads, 2)
 k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out, const MapGeom g,
            unsigned* __restrict__ work, int nitems)
 {
@@ -1338,9 +1067,7 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
     Map5Tables t;
     const uint32_t zero = blockIdx.z;  // always 0
     t.four = opaque(4u + zero);
-    // (constant xor-ed with a run-time zero: ptxas splits a plain immediate off again and re-adds it per pixel)
-    t.ay_lp = kAyFold ? uint32_t(__cvta_generic_to_shared(s_ay)) + ((0u - 0x4B400000u * 8u) ^ zero)
-                      : opaque(uint32_t(__cvta_generic_to_shared(s_ay)) - 0x4B400000u * 8u);
+    t.ay_lp = opaque(uint32_t(__cvta_generic_to_shared(s_ay)) - 0x4B400000u * 8u);
     t.outf = opaque(uint32_t(__cvta_generic_to_shared(s_outf)));
     t.lin = opaque(uint32_t(__cvta_generic_to_shared(s_lin)) - 2u * uint32_t(kXzLinMin));
     const uint32_t sixteen = opaque(16u + zero);
@@ -1364,7 +1091,7 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
         const int y0 = g.by[cy] + strip * srows;
         const int y1 = min(y0 + srows, g.by[cy + 1]);
 
-        const uint32_t* labL = reinterpret_cast<const uint32_t*>(lab) + size_t(f % g.lab_mod) * 3 * plane4;
+        const uint32_t* labL = reinterpret_cast<const uint32_t*>(lab) + size_t(f) * 3 * plane4;
         float4* outR = reinterpret_cast<float4*>(out) + size_t(f) * 3 * plane4;
         const float txbase = float(cx - 1), tybase = float(cy - 1);
         const int cw4 = (x1 - x0) >> 2;
@@ -1508,8 +1235,9 @@ static bool valid_shape(int n, int h, int w, int tiles_x, int tiles_y)
            size_t(h) * w <= (size_t(1) << 30);
 }
 
-// development switch (A/B timing on the GPU box, profiles/r2_clahe.md): UPR_CLAHE_VARIANT bit 0 = first-generation
-// map kernel (k_map_vec), bit 1 = first-generation histogram kernel (k_hist_lab_vec).  Same results either way.
+// development switch (A/B timing on the GPU box, profiles/r2_clahe.md, r3_clahe.md): UPR_CLAHE_VARIANT bit 0 =
+// first-generation map kernel (k_map_vec), bit 1 = first-generation histogram kernel (k_hist_lab_vec), bit 2 = second-
+// generation histogram kernel (k_hist_lab_vec2) instead of the column-owner one.  Same results either way.
 static int variant()
 {
     const char* e = std::getenv("UPR_CLAHE_VARIANT");   // read per call so that tests can A/B within one process
@@ -1556,8 +1284,6 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
     if (clip_limit > 0.0) g.clip = std::max(int(clip_limit * area / 256), 1);
     g.lut_scale = float(255) / float(area);
     g.gam_bias = 0u - 4u * 0x4B000000u;
-    const char* lm = std::getenv("UPR_LAB_MOD");   // development switch (timing experiment, wrong results)
-    g.lab_mod = lm ? std::max(1, std::atoi(lm)) : 0x7fffffff;
     const float inv_tw = 1.0f / float(g.tw), inv_th = 1.0f / float(g.th);
 
     // interpolation cell boundaries from the exact fp32 recipe (monotone in p)
@@ -1565,7 +1291,6 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
     bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && aligned16(in) && aligned16(out) &&
                 size_t(h) * w * 3 < (size_t(1) << 32) && (!rx || (aligned16(rx->illu) && aligned16(rx->e)));
     if (fast) {
-        m.lab_mod = g.lab_mod;
         m.n = n; m.h = h; m.w = w; m.tiles_x = tiles_x; m.tiles_y = tiles_y; m.inv_tw = inv_tw; m.inv_th = inv_th;
         int c = 0;
         m.bx[0] = 0;
@@ -1600,7 +1325,6 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             const int max_rows = tw4 <= kK1Threads ? 63 * (kK1Threads / tw4) : std::max(1, (63 * kK1Threads) / tw4);
             int nstrips = (g.th + max_rows - 1) / max_rows;
             const int want = (3 * kNumSMsB200 + nf * ntiles - 1) / (nf * ntiles);  // fill the machine for tiny batches
-            if (const char* se = std::getenv("UPR_K1_STRIPS")) nstrips = std::max(nstrips, std::atoi(se));   // development switch
             nstrips = std::min(std::max(nstrips, want), g.th);
             g.strip_rows = (g.th + nstrips - 1) / nstrips;
             g.nstrips = (g.th + g.strip_rows - 1) / g.strip_rows;
@@ -1609,65 +1333,26 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                 UPR_CUDA_TRY(cudaMemsetAsync(tickets + ftile, 0, size_t(nf) * ntiles * sizeof(unsigned), stream));
             }
             const size_t smem1 = size_t(256) * kK1Threads + UPR_TAB_GAMMA_LEN * 4 + UPR_TAB_CBRT_LEN * 2;
-            const size_t smem1r = smem1 + UPR_TAB_GAMMA_LEN * 4 * 31;   // gamma table replicated per lane (2 CTAs per SM)
-            static unsigned long long m1 = 0, m2 = 0, m3 = 0, m2r = 0, m3r = 0;
+            static unsigned long long m1 = 0, m2 = 0, m3 = 0, m4 = 0;
             UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec, smem1, m1));
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<false, false>, smem1, m2));
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<true, false>, smem1, m3));
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<false, true>, smem1r, m2r));
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<true, true>, smem1r, m3r));
+            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<false>, smem1, m2));
+            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<true>, smem1, m3));
+            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3, smem1, m4));
+            // the column-owner kernel wants (almost) every thread to own a column: 240 of 256 at 1080p and 4K
+            const bool col_owner = tw4 <= kK1Threads && (kK1Threads / tw4) * tw4 * 8 >= kK1Threads * 7;
             if (stage_mask & 1) {
-                const bool rep = (variant() & 4) != 0;
-                const dim3 grid1(ntiles * g.nstrips, nf);
                 if (rx) {
                     const RetinexIn rxf{rx->illu + size_t(f0) * h * w, rx->e + fplane, rx->eps};
-                    if (rep)
-                        k_hist_lab_vec2<true, true><<<grid1, kK1Threads, smem1r, stream>>>(
-                            in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
-                    else
-                        k_hist_lab_vec2<true, false><<<grid1, kK1Threads, smem1, stream>>>(
-                            in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
+                    k_hist_lab_vec2<true><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
+                        in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
                 } else if (variant() & 2) {
-                    k_hist_lab_vec<<<grid1, kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
-                                                                         lut + ftile * 256, tickets + ftile, g);
-                } else if ((variant() & 64) && tw4 <= kK1Threads) {
-                    static unsigned long long m7 = 0, m8 = 0, m9 = 0;
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec4<2, false>, smem1, m7));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec4<3, false>, smem1, m8));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec4<2, true>, smem1, m9));
-                    int32_t* a_hist = hist + ftile * 256;
-                    uint8_t* a_lut = lut + ftile * 256;
-                    unsigned* a_tick = tickets + ftile;
-                    const float* a_in = in + fplane;
-                    uint8_t* a_lab = lab + fplane;
-                    if ((variant() & 256) && g.nstrips == 1 && tiles_x <= 8 && ntiles % tiles_x == 0) {
-                        cudaLaunchConfig_t cfg{};
-                        cfg.gridDim = grid1; cfg.blockDim = dim3(kK1Threads); cfg.dynamicSmemBytes = smem1; cfg.stream = stream;
-                        cudaLaunchAttribute at[1];
-                        at[0].id = cudaLaunchAttributeClusterDimension;
-                        at[0].val.clusterDim.x = unsigned(tiles_x); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                        cfg.attrs = at; cfg.numAttrs = 1;
-                        UPR_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_hist_lab_vec4<2, true>, a_in, a_lab, a_hist, a_lut, a_tick, g));
-                    } else if (variant() & 128)
-                        k_hist_lab_vec4<3, false><<<grid1, kK1Threads, smem1, stream>>>(a_in, a_lab, a_hist, a_lut, a_tick, g);
-                    else
-                        k_hist_lab_vec4<2, false><<<grid1, kK1Threads, smem1, stream>>>(a_in, a_lab, a_hist, a_lut, a_tick, g);
-                } else if (variant() & 32) {
-                    // persistent third generation: one queue head (work[1]; work[0] belongs to the map kernel)
-                    static unsigned long long m6 = 0;
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3, smem1, m6));
-                    const long long items1 = (long long)nf * ntiles * g.nstrips;
-                    if (items1 > 0x7fffffffLL / 2) return UPR_E_SHAPE;
-                    UPR_CUDA_TRY(cudaMemsetAsync(work + 1, 0, sizeof(unsigned), stream));
-                    const char* c1 = std::getenv("UPR_K1_CTAS");   // development switch
-                    const long long ctas1 = c1 ? std::max(1, std::atoi(c1)) : 3 * kNumSMsB200;
-                    k_hist_lab_vec3<<<dim3(unsigned(std::min<long long>(items1, ctas1))), kK1Threads, smem1, stream>>>(
-                        in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, work + 1, int(items1));
-                } else if (rep) {
-                    k_hist_lab_vec2<false, true><<<grid1, kK1Threads, smem1r, stream>>>(
-                        in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, RetinexIn{nullptr, nullptr, 0.0f});
+                    k_hist_lab_vec<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
+                                                                                                lut + ftile * 256, tickets + ftile, g);
+                } else if (col_owner && !(variant() & 4)) {
+                    k_hist_lab_vec3<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
+                        in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g);
                 } else {
-                    k_hist_lab_vec2<false, false><<<grid1, kK1Threads, smem1, stream>>>(
+                    k_hist_lab_vec2<false><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
                         in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, RetinexIn{nullptr, nullptr, 0.0f});
                 }
                 UPR_LAUNCH_CHECK();
@@ -1682,19 +1367,13 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                 if (variant() & 1) {
                     k_map_vec<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
                 } else {
-                    // thread count: the largest multiple of the interior cell width (in 4-px columns) <= the variant's cap
-                    // (512 threads -> 64 registers per thread at 2 CTAs per SM, 448 -> 72)
-                    const int v5 = (variant() >> 3) & 3;   // development switch: 0 = <512, plain>, 1 = <512, folded>, 2 = <448, folded>, 3 = <448, plain>
-                    const int cap = (v5 >= 2) ? 448 : kK5MaxThreads;
+                    // thread count: the largest multiple of the interior cell width (in 4-px columns) <= 512
                     const int cw4 = g.tw / 4;
-                    int nthr = cw4 <= cap ? (cap / cw4) * cw4 : cap;
-                    if (nthr < 256) nthr = cap;
+                    int nthr = cw4 <= kK5MaxThreads ? (kK5MaxThreads / cw4) * cw4 : kK5MaxThreads;
+                    if (nthr < 256) nthr = kK5MaxThreads;
                     const size_t smem5 = size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4;
-                    static unsigned long long m5[4] = {0, 0, 0, 0};
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<512, false>, smem5, m5[0]));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<512, true>, smem5, m5[1]));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<448, true>, smem5, m5[2]));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<448, false>, smem5, m5[3]));
+                    static unsigned long long m5 = 0;
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5, smem5, m5));
                     // items = (frame, cell, strip): ~4 items per resident CTA on small batches, strips of >= 16 rows (every item
                     // costs a barrier and a quad-table build: with 16 items per CTA and 8-row strips a 3-frame call took 99 us
                     // instead of 78 us for the first-generation kernel)
@@ -1705,11 +1384,8 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                     const long long nitems = (long long)nf * ncells * ks5;
                     if (nitems > 0x7fffffffLL / 2) return UPR_E_SHAPE;
                     UPR_CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(unsigned), stream));
-                    const char* ce = std::getenv("UPR_K3_CTAS");   // development switch (overlap experiments): persistent grid size
-                    const long long ctas = ce ? std::max(1, std::atoi(ce)) : resident;
-                    const dim3 grid5(unsigned(std::min<long long>(nitems, ctas)));
-                    auto* kfn = v5 == 0 ? k_map_vec5<512, false> : v5 == 1 ? k_map_vec5<512, true> : v5 == 2 ? k_map_vec5<448, true> : k_map_vec5<448, false>;
-                    kfn<<<grid5, nthr, smem5, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m, work, int(nitems));
+                    k_map_vec5<<<dim3(unsigned(std::min<long long>(nitems, resident))), nthr, smem5, stream>>>(
+                        lab + fplane, lut + ftile * 256, out + fplane, m, work, int(nitems));
                 }
                 UPR_LAUNCH_CHECK();
             }

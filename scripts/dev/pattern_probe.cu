@@ -92,6 +92,29 @@ __global__ void __launch_bounds__(256, 3) k1_band(const float4* __restrict__ in,
         if (c1 < W4) { q[size_t(r) * W4 + c1] = __float_as_uint(a2.x + a2.w); q[PLANE4 + size_t(r) * W4 + c1] = __float_as_uint(b2.y); q[2 * PLANE4 + size_t(r) * W4 + c1] = __float_as_uint(c2.z); }
     }
 }
+// K3-like traffic: read 3 u8 planes (one u32 per 4 pixels), write 3 f32 planes
+__global__ void __launch_bounds__(512, 2) k3_tile(const unsigned* __restrict__ lab, float4* __restrict__ o)
+{
+    const int tile = blockIdx.x, f = blockIdx.y, ty = tile / 8, tx = tile % 8;
+    const int lr = threadIdx.x / 60, lc = threadIdx.x % 60;   // 480 threads = 8 rows x 60 columns
+    const size_t base = size_t(f) * 3 * PLANE4 + size_t(ty * 135) * W4 + tx * 60 + lc;
+    for (int r = lr; r < 135; r += 8) {
+        const unsigned a = __ldg(lab + base + size_t(r) * W4), b = __ldg(lab + base + PLANE4 + size_t(r) * W4), c = __ldg(lab + base + 2 * PLANE4 + size_t(r) * W4);
+        const float4 v = make_float4(float(a & 255), float(b & 255), float(c & 255), float(a >> 24));
+        __stcs(o + base + size_t(r) * W4, v); __stcs(o + base + PLANE4 + size_t(r) * W4, v); __stcs(o + base + 2 * PLANE4 + size_t(r) * W4, v);
+    }
+}
+__global__ void __launch_bounds__(512, 2) k3_band(const unsigned* __restrict__ lab, float4* __restrict__ o, int rows)
+{
+    const int band = blockIdx.x, f = blockIdx.y;
+    const size_t base = size_t(f) * 3 * PLANE4 + size_t(band * rows) * W4 + threadIdx.x;   // 480 threads = one full row
+    const int r1 = min(rows, H - band * rows);
+    for (int r = 0; r < r1; ++r) {
+        const unsigned a = __ldg(lab + base + size_t(r) * W4), b = __ldg(lab + base + PLANE4 + size_t(r) * W4), c = __ldg(lab + base + 2 * PLANE4 + size_t(r) * W4);
+        const float4 v = make_float4(float(a & 255), float(b & 255), float(c & 255), float(a >> 24));
+        __stcs(o + base + size_t(r) * W4, v); __stcs(o + base + PLANE4 + size_t(r) * W4, v); __stcs(o + base + 2 * PLANE4 + size_t(r) * W4, v);
+    }
+}
 template <typename F> float timeit(F f)
 {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -128,6 +151,11 @@ int main()
     t = timeit([&] { k1_tile<<<dim3(64, N), 256, smem>>>(in, lab); }); printf("K1-like tile pattern        %.3f ms  (12 B/px read + 3 B/px written)\n", t);
     for (int rows : {17, 8, 4}) {
         t = timeit([&] { k1_band<<<dim3((H + rows - 1) / rows, N), 256, smem>>>(in, lab, rows); }); printf("K1-like band pattern %2d rows %.3f ms\n", rows, t);
+    }
+    const unsigned* labr = reinterpret_cast<const unsigned*>(in);
+    t = timeit([&] { k3_tile<<<dim3(64, N), 480>>>(labr, o); }); printf("K3-like tile pattern        %.3f ms  (3 B/px read + 12 B/px written)\n", t);
+    for (int rows : {17, 8}) {
+        t = timeit([&] { k3_band<<<dim3((H + rows - 1) / rows, N), 480>>>(labr, o, rows); }); printf("K3-like band pattern %2d rows %.3f ms\n", rows, t);
     }
     t = timeit([&] { cudaMemcpyAsync(o, in, bytes, cudaMemcpyDeviceToDevice); }); printf("memcpy d2d (r+w)            %.3f ms  %.0f GB/s\n", t, 2 * gb / t * 1e3);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));

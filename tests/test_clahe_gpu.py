@@ -137,9 +137,9 @@ def test_full_size_properties(native):
 
 # ---- kernel generations ----------------------------------------------------------------------------------
 def test_kernel_generations_bit_identical(native, monkeypatch):
-    """UPR_CLAHE_VARIANT selects the first-generation kernels (k_hist_lab_vec / k_map_vec); the production pair
-    (k_hist_lab_vec2 + k_map_vec5) must give the same Lab planes, histograms, LUTs and output, bit for bit, on the named
-    shapes, on a batch, and on inputs that leave [0,1] (slow quantisation path of the new histogram kernel)."""
+    """UPR_CLAHE_VARIANT selects earlier kernel generations (3: k_hist_lab_vec + k_map_vec, 4: k_hist_lab_vec2); the
+    production pair (k_hist_lab_vec3 + k_map_vec5) must give the same Lab planes, histograms, LUTs and output, bit for bit,
+    on the named shapes, on a batch, and on inputs that leave [0,1] (slow quantisation path of the newer histogram kernels)."""
     rng = np.random.default_rng(7)
     cases = [O.kat_input(3, 1080, 1920, "uniform"), O.kat_input(6, 2160, 3840, "dark"),
              np.concatenate([O.kat_input(20 + i, 400, 600, k) for i, k in enumerate(["uniform", "dark", "ramp", "const"])]),
@@ -148,11 +148,12 @@ def test_kernel_generations_bit_identical(native, monkeypatch):
     cases[3][1, 2, 9, 3] = np.inf
     for x in cases:
         res = {}
-        for v in ("0", "3"):
+        for v in ("0", "3", "4"):
             monkeypatch.setenv("UPR_CLAHE_VARIANT", v)
             res[v] = run_clahe(native, x)
-        for a, b in zip(res["0"], res["3"]):
-            assert np.array_equal(a, b)
+        for v in ("3", "4"):
+            for a, b in zip(res["0"], res[v]):
+                assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("n,h,w,tiles", [(1, 1080, 1920, (8, 8)), (3, 480, 640, (8, 8)), (2, 256, 1024, (4, 2)), (5, 64, 64, (8, 8)),
