@@ -446,9 +446,13 @@ __device__ __forceinline__ void k1_item(const float4 vr, const float4 vg, const 
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        // L sits in byte 2 of vL: one PRMT copies it into bytes 0 and 1 (= L * 257)
-        unsigned char* c = s_cnt + ((__byte_perm(uint32_t(vL[k]), 0u, 0x4422) & 0xFC03u) | tid4);   // bits 2..9 of the offset are the thread's column
-        *c = static_cast<unsigned char>(*c + 1);
+        // L sits in byte 2 of vL: one PRMT copies it into bytes 0 and 1 (= L * 257), which masked with 0xFC00 is the row
+        // of its counter word.  The four byte counters of a word belong to ONE thread and never exceed 255 between
+        // flushes, so adding 1 << 8 (L & 3) to the word with a shared-memory reduction cannot carry: one LSU operation
+        // instead of a dependent byte load / add / store (bits 2..9 of the offset are the thread's column: no conflicts)
+        const uint32_t a = uint32_t(__cvta_generic_to_shared(s_cnt)) + ((__byte_perm(uint32_t(vL[k]), 0u, 0x4422) & 0xFC00u) | tid4);
+        const uint32_t inc = 1u << ((uint32_t(vL[k]) >> 13) & 24u);
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(inc) : "memory");
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -818,6 +822,200 @@ k_hist_lab_vec3(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
     const size_t t_idx = size_t(f) * ntiles + tile;
     if (!publish_hist(total, hist_g + t_idx * 256, tickets + t_idx, g.nstrips, &s_flag)) return;
     tile_lut_256(total, g.clip, g.lut_scale, lut_g + t_idx * 256, s_tmp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 fast path, band kernel (8 tiles across, tile width a multiple of 120 px): one WARP per tile column, one CTA per
+// full-width band of <= 31 rows, persistent.  Why (profiles/r3_clahe.md): the tile kernels stream eight unrelated 960-byte
+// row segments per CTA wave and a traffic-only kernel in that pattern is 12-18 % slower than one that walks whole image rows;
+// 10 % of their warp time is spent at the CTA barrier in front of the counter reduction; and every extra CTA costs ~5 us of
+// SM-slot time.  Here the eight warps of a CTA read one image row together (7680 contiguous bytes per plane at 1080p), the
+// byte counters are still private per thread, so a warp's 32 counter columns ARE its tile's partial histogram: each warp
+// reduces, clears and publishes its own counters (no CTA barrier after the prologue) and moves on to its next band.
+// Lane l < 30 owns the 4-pixel columns l, l + 30, ... of its tile (kCols per row); lanes 30 and 31 only take part in the
+// reduction.  Partial histograms are added into the global histogram with RED; the warp that completes a tile builds its LUT.
+// Same arithmetic as the other generations (k1_item): bit-identical Lab planes, histograms and LUTs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_tile_lut(const int32_t* __restrict__ hg, int clip, float lut_scale, uint8_t* __restrict__ lut_out, int lane)
+{
+    // lane l owns bins 8l .. 8l+7 (Appendix A.3 steps 3-4; same integer recipe as tile_lut_256)
+    int hb[8];
+    {
+        const int4 a = __ldcg(reinterpret_cast<const int4*>(hg) + 2 * lane), b = __ldcg(reinterpret_cast<const int4*>(hg) + 2 * lane + 1);
+        hb[0] = a.x; hb[1] = a.y; hb[2] = a.z; hb[3] = a.w; hb[4] = b.x; hb[5] = b.y; hb[6] = b.z; hb[7] = b.w;
+    }
+    if (clip > 0) {
+        int excess = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { excess += max(hb[j] - clip, 0); hb[j] = min(hb[j], clip); }
+        const int clipped = warp_sum(excess);
+        const int batch = clipped >> 8, resid = clipped & 255;
+        const int step = resid ? max(256 / resid, 1) : 1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = 8 * lane + j;
+            hb[j] += batch;
+            if (resid != 0 && i % step == 0 && i / step < resid) ++hb[j];
+        }
+    }
+    int run = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { run += hb[j]; hb[j] = run; }
+    int incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int excl = incl - run;
+    uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int r = __float2int_rn(__fmul_rn(__int2float_rn(hb[j] + excl), lut_scale));
+        const uint32_t b = uint32_t(min(max(r, 0), 255));
+        if (j < 4) w0 |= b << (8 * j); else w1 |= b << (8 * (j - 4));
+    }
+    reinterpret_cast<uint2*>(lut_out)[lane] = make_uint2(w0, w1);
+}
+
+template <int kCols>   // 4-pixel columns per lane and row: tile width = 120 * kCols pixels
+__global__ void __launch_bounds__(kK1Threads, 3)
+k_hist_lab_band(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
+                uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g, int total_items)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
+    float* s_gammaf = reinterpret_cast<float*>(smem + 256 * kK1Threads);           // 256 x f32
+    uint16_t* s_cbrt = reinterpret_cast<uint16_t*>(s_gammaf + UPR_TAB_GAMMA_LEN);  // 2048 x u16
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntiles = g.tiles_x * g.tiles_y;
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cnt);
+#pragma unroll
+        for (int i = 0; i < 256 * kK1Threads / 16 / kK1Threads; ++i) z[tid + i * kK1Threads] = make_uint4(0, 0, 0, 0);
+        s_gammaf[tid] = float(d_gamma[tid]);
+        reinterpret_cast<uint4*>(s_cbrt)[tid] = reinterpret_cast<const uint4*>(d_cbrt)[tid];  // 256 x 16 B = 4 KB
+    }
+    __syncthreads();   // the only CTA-wide barrier
+
+    const uint32_t zero = blockIdx.z;  // always 0
+    K1Tables t;
+    t.gam = uint32_t(__cvta_generic_to_shared(s_gammaf));
+    t.gam_q = t.gam + g.gam_bias;
+    t.cbr_q = opaque(uint32_t(__cvta_generic_to_shared(s_cbrt)) - 2u * 0x4B000000u);
+    t.four = opaque(4u + zero);
+    t.sixteen = opaque(16u + zero);
+
+    const uint32_t w4 = uint32_t(g.w) >> 2;
+    const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;      // fast path: 3 * plane < 2^32
+    const uint32_t tid4 = uint32_t(tid) * 4u;
+    const bool active = lane < 30;
+    const int tx = warp;                              // host guarantees tiles_x == 8 == warps per CTA
+    constexpr int kPf = 4;                            // L2 prefetch distance in rows
+    // this warp's counter rows: group gq lives at s_cnt + gq * 1024 + warp * 128 (32 lanes x 4 bins)
+    unsigned char* wcnt = s_cnt + warp * 128;
+
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int strip = item % g.nstrips;
+        const int fty = item / g.nstrips;             // frame * tiles_y + ty
+        const int f = fty / g.tiles_y, ty = fty - f * g.tiles_y;
+        const int row0 = ty * g.th + strip * g.strip_rows;
+        const int row1 = active ? min(row0 + g.strip_rows, (ty + 1) * g.th) : 0;
+        // per-thread plane bases in vector registers (see k_hist_lab_vec3); offsets count 4-pixel groups
+        const size_t b4 = size_t(f) * 3 * plane4 + uint32_t(tx * (30 * kCols) + lane);
+        const float4* inR = opaque_ptr(reinterpret_cast<const float4*>(in) + b4);
+        const float4* inG = opaque_ptr(inR + plane4);
+        const float4* inB = opaque_ptr(inG + plane4);
+        uint32_t* labL = opaque_ptr(reinterpret_cast<uint32_t*>(lab) + b4);
+        uint32_t* labA = opaque_ptr(labL + plane4);
+        uint32_t* labB = opaque_ptr(labA + plane4);
+
+        auto load = [&](uint32_t o, int c, float4& r, float4& gch, float4& b) {
+            r = ld_nc_f4(inR + o + 30 * c);
+            gch = ld_nc_f4(inG + o + 30 * c);
+            b = ld_nc_f4(inB + o + 30 * c);
+        };
+        auto prefetch_row = [&](uint32_t o) {
+#pragma unroll
+            for (int c = 0; c < kCols; ++c) {
+                prefetch_l2(inR + o + 30 * c);
+                prefetch_l2(inG + o + 30 * c);
+                prefetch_l2(inB + o + 30 * c);
+            }
+        };
+        auto store = [&](uint32_t o, int c, uint32_t wl, uint32_t wa, uint32_t wb) {
+            st_global_u32(labL + o + 30 * c, wl);
+            st_global_u32(labA + o + 30 * c, wa);
+            st_global_u32(labB + o + 30 * c, wb);
+        };
+
+        int row = row0;
+        uint32_t o = uint32_t(row) * w4;
+        float4 ar, ag, ab, br, bg, bb;
+        if (row < row1) {
+            load(o, 0, ar, ag, ab);
+#pragma unroll 1
+            for (int k = 1; k < kPf; ++k)
+                if (row + k < row1) prefetch_row(o + uint32_t(k) * w4);
+        }
+        while (row < row1) {
+            uint32_t wl, wa, wb;
+            if (row + kPf < row1) prefetch_row(o + uint32_t(kPf) * w4);
+#pragma unroll
+            for (int c = 0; c < kCols; c += 2) {
+                load(o, c + 1, br, bg, bb);
+                k1_item(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
+                store(o, c, wl, wa, wb);
+                if (c + 2 < kCols) load(o, c + 2, ar, ag, ab);
+                else if (row + 1 < row1) load(o + w4, 0, ar, ag, ab);
+                k1_item(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
+                store(o, c + 1, wl, wa, wb);
+            }
+            ++row;
+            o += w4;
+        }
+        __syncwarp();
+
+        // warp-local reduction: lane l sums bin groups 2l and 2l+1 (bins 8l .. 8l+7) over the warp's 32 counter columns
+        // and clears them; 16-byte chunks are visited in an order rotated by the lane (4 lanes per bank group: the minimum)
+        unsigned tot[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tot[j] = 0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            uint4* rowp = reinterpret_cast<uint4*>(wcnt + (2 * lane + q) * 1024);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int ch = (k + lane) & 7;
+                const uint4 v = rowp[ch];
+                rowp[ch] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const unsigned sel = 1u << (8 * b);
+                    tot[4 * q + b] = __dp4a(v.x, sel, tot[4 * q + b]);
+                    tot[4 * q + b] = __dp4a(v.y, sel, tot[4 * q + b]);
+                    tot[4 * q + b] = __dp4a(v.z, sel, tot[4 * q + b]);
+                    tot[4 * q + b] = __dp4a(v.w, sel, tot[4 * q + b]);
+                }
+            }
+        }
+        const size_t t_idx = size_t(f) * ntiles + size_t(ty) * g.tiles_x + tx;
+        int32_t* hg = hist_g + t_idx * 256 + 8 * lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (tot[j]) atomicAdd(hg + j, int(tot[j]));
+        __threadfence();
+        __syncwarp();
+        unsigned last = 0;
+        if (lane == 0) last = (atomicAdd(tickets + t_idx, 1u) == unsigned(g.nstrips - 1));
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence();
+            warp_tile_lut(hist_g + t_idx * 256, g.clip, g.lut_scale, lut_g + t_idx * 256, lane);
+        }
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1237,7 +1435,8 @@ static bool valid_shape(int n, int h, int w, int tiles_x, int tiles_y)
 
 // development switch (A/B timing on the GPU box, profiles/r2_clahe.md, r3_clahe.md): UPR_CLAHE_VARIANT bit 0 =
 // first-generation map kernel (k_map_vec), bit 1 = first-generation histogram kernel (k_hist_lab_vec), bit 2 = second-
-// generation histogram kernel (k_hist_lab_vec2) instead of the column-owner one.  Same results either way.
+// generation histogram kernel (k_hist_lab_vec2) instead of the column-owner one, bit 3 = column-owner tile kernel
+// (k_hist_lab_vec3) where the band kernel (k_hist_lab_band) would run.  Same results either way.
 static int variant()
 {
     const char* e = std::getenv("UPR_CLAHE_VARIANT");   // read per call so that tests can A/B within one process
@@ -1324,11 +1523,21 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             // (column-owner kernel: 63 iterations of kK1Threads / tw4 rows; the item-linear kernels allow slightly more)
             const int max_rows = tw4 <= kK1Threads ? 63 * (kK1Threads / tw4) : std::max(1, (63 * kK1Threads) / tw4);
             int nstrips = (g.th + max_rows - 1) / max_rows;
-            const int want = (3 * kNumSMsB200 + nf * ntiles - 1) / (nf * ntiles);  // fill the machine for tiny batches
+            int want = (3 * kNumSMsB200 + nf * ntiles - 1) / (nf * ntiles);  // fill the machine for tiny batches
+            // band kernel (one warp per tile column, one CTA per full-width band): 8 tiles across, tile width 240 or 480 px
+            const int bcols = (tiles_x == 8 && tw4 % 30 == 0) ? tw4 / 30 : 0;
+            // (batches with fewer than two bands per resident CTA stay with the tile kernels, which split finer)
+            const int bstrips = bcols ? (g.th + 255 / (4 * bcols) - 1) / (255 / (4 * bcols)) : 0;   // byte counters: <= 255 px per lane and band
+            const bool band = !rx && !(variant() & 14) && (bcols == 2 || bcols == 4) &&
+                              (long long)nf * tiles_y * bstrips >= 2LL * 3 * kNumSMsB200;
+            if (band) {
+                nstrips = bstrips;
+                want = 1;
+            }
             nstrips = std::min(std::max(nstrips, want), g.th);
             g.strip_rows = (g.th + nstrips - 1) / nstrips;
             g.nstrips = (g.th + g.strip_rows - 1) / g.strip_rows;
-            if (g.nstrips > 1 && (stage_mask & 1)) {
+            if ((g.nstrips > 1 || band) && (stage_mask & 1)) {
                 UPR_CUDA_TRY(cudaMemsetAsync(hist + ftile * 256, 0, size_t(nf) * ntiles * 256 * sizeof(int32_t), stream));
                 UPR_CUDA_TRY(cudaMemsetAsync(tickets + ftile, 0, size_t(nf) * ntiles * sizeof(unsigned), stream));
             }
@@ -1341,7 +1550,19 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             // the column-owner kernel wants (almost) every thread to own a column: 240 of 256 at 1080p and 4K
             const bool col_owner = tw4 <= kK1Threads && (kK1Threads / tw4) * tw4 * 8 >= kK1Threads * 7;
             if (stage_mask & 1) {
-                if (rx) {
+                if (band) {
+                    static unsigned long long mb2 = 0, mb4 = 0;
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_band<2>, smem1, mb2));
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_band<4>, smem1, mb4));
+                    const long long items = (long long)nf * tiles_y * g.nstrips;
+                    const dim3 gridb(unsigned(std::min<long long>(items, 3 * kNumSMsB200)));
+                    if (bcols == 2)
+                        k_hist_lab_band<2><<<gridb, kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
+                                                                                 lut + ftile * 256, tickets + ftile, g, int(items));
+                    else
+                        k_hist_lab_band<4><<<gridb, kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
+                                                                                 lut + ftile * 256, tickets + ftile, g, int(items));
+                } else if (rx) {
                     const RetinexIn rxf{rx->illu + size_t(f0) * h * w, rx->e + fplane, rx->eps};
                     k_hist_lab_vec2<true><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
                         in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
