@@ -66,6 +66,7 @@ struct MapGeom {
     int tiles_x, tiles_y;
     float inv_tw, inv_th;
     int nstrips;
+    uint32_t ay_bias;  // 0 - 0x4B400000 * 128 as a parameter (see ClaheGeom::gam_bias)
     int bx[kMaxTiles + 2];  // cell c covers x in [bx[c], bx[c+1]); raw tile index of the cell is c-1
     int by[kMaxTiles + 2];
 };
@@ -825,200 +826,6 @@ k_hist_lab_vec3(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1 fast path, band kernel (8 tiles across, tile width a multiple of 120 px): one WARP per tile column, one CTA per
-// full-width band of <= 31 rows, persistent.  Why (profiles/r3_clahe.md): the tile kernels stream eight unrelated 960-byte
-// row segments per CTA wave and a traffic-only kernel in that pattern is 12-18 % slower than one that walks whole image rows;
-// 10 % of their warp time is spent at the CTA barrier in front of the counter reduction; and every extra CTA costs ~5 us of
-// SM-slot time.  Here the eight warps of a CTA read one image row together (7680 contiguous bytes per plane at 1080p), the
-// byte counters are still private per thread, so a warp's 32 counter columns ARE its tile's partial histogram: each warp
-// reduces, clears and publishes its own counters (no CTA barrier after the prologue) and moves on to its next band.
-// Lane l < 30 owns the 4-pixel columns l, l + 30, ... of its tile (kCols per row); lanes 30 and 31 only take part in the
-// reduction.  Partial histograms are added into the global histogram with RED; the warp that completes a tile builds its LUT.
-// Same arithmetic as the other generations (k1_item): bit-identical Lab planes, histograms and LUTs.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_tile_lut(const int32_t* __restrict__ hg, int clip, float lut_scale, uint8_t* __restrict__ lut_out, int lane)
-{
-    // lane l owns bins 8l .. 8l+7 (Appendix A.3 steps 3-4; same integer recipe as tile_lut_256)
-    int hb[8];
-    {
-        const int4 a = __ldcg(reinterpret_cast<const int4*>(hg) + 2 * lane), b = __ldcg(reinterpret_cast<const int4*>(hg) + 2 * lane + 1);
-        hb[0] = a.x; hb[1] = a.y; hb[2] = a.z; hb[3] = a.w; hb[4] = b.x; hb[5] = b.y; hb[6] = b.z; hb[7] = b.w;
-    }
-    if (clip > 0) {
-        int excess = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { excess += max(hb[j] - clip, 0); hb[j] = min(hb[j], clip); }
-        const int clipped = warp_sum(excess);
-        const int batch = clipped >> 8, resid = clipped & 255;
-        const int step = resid ? max(256 / resid, 1) : 1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int i = 8 * lane + j;
-            hb[j] += batch;
-            if (resid != 0 && i % step == 0 && i / step < resid) ++hb[j];
-        }
-    }
-    int run = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { run += hb[j]; hb[j] = run; }
-    int incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int excl = incl - run;
-    uint32_t w0 = 0, w1 = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int r = __float2int_rn(__fmul_rn(__int2float_rn(hb[j] + excl), lut_scale));
-        const uint32_t b = uint32_t(min(max(r, 0), 255));
-        if (j < 4) w0 |= b << (8 * j); else w1 |= b << (8 * (j - 4));
-    }
-    reinterpret_cast<uint2*>(lut_out)[lane] = make_uint2(w0, w1);
-}
-
-template <int kCols>   // 4-pixel columns per lane and row: tile width = 120 * kCols pixels
-__global__ void __launch_bounds__(kK1Threads, 3)
-k_hist_lab_band(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
-                uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g, int total_items)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
-    float* s_gammaf = reinterpret_cast<float*>(smem + 256 * kK1Threads);           // 256 x f32
-    uint16_t* s_cbrt = reinterpret_cast<uint16_t*>(s_gammaf + UPR_TAB_GAMMA_LEN);  // 2048 x u16
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ntiles = g.tiles_x * g.tiles_y;
-    {
-        uint4* z = reinterpret_cast<uint4*>(s_cnt);
-#pragma unroll
-        for (int i = 0; i < 256 * kK1Threads / 16 / kK1Threads; ++i) z[tid + i * kK1Threads] = make_uint4(0, 0, 0, 0);
-        s_gammaf[tid] = float(d_gamma[tid]);
-        reinterpret_cast<uint4*>(s_cbrt)[tid] = reinterpret_cast<const uint4*>(d_cbrt)[tid];  // 256 x 16 B = 4 KB
-    }
-    __syncthreads();   // the only CTA-wide barrier
-
-    const uint32_t zero = blockIdx.z;  // always 0
-    K1Tables t;
-    t.gam = uint32_t(__cvta_generic_to_shared(s_gammaf));
-    t.gam_q = t.gam + g.gam_bias;
-    t.cbr_q = opaque(uint32_t(__cvta_generic_to_shared(s_cbrt)) - 2u * 0x4B000000u);
-    t.four = opaque(4u + zero);
-    t.sixteen = opaque(16u + zero);
-
-    const uint32_t w4 = uint32_t(g.w) >> 2;
-    const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;      // fast path: 3 * plane < 2^32
-    const uint32_t tid4 = uint32_t(tid) * 4u;
-    const bool active = lane < 30;
-    const int tx = warp;                              // host guarantees tiles_x == 8 == warps per CTA
-    constexpr int kPf = 4;                            // L2 prefetch distance in rows
-    // this warp's counter rows: group gq lives at s_cnt + gq * 1024 + warp * 128 (32 lanes x 4 bins)
-    unsigned char* wcnt = s_cnt + warp * 128;
-
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int strip = item % g.nstrips;
-        const int fty = item / g.nstrips;             // frame * tiles_y + ty
-        const int f = fty / g.tiles_y, ty = fty - f * g.tiles_y;
-        const int row0 = ty * g.th + strip * g.strip_rows;
-        const int row1 = active ? min(row0 + g.strip_rows, (ty + 1) * g.th) : 0;
-        // per-thread plane bases in vector registers (see k_hist_lab_vec3); offsets count 4-pixel groups
-        const size_t b4 = size_t(f) * 3 * plane4 + uint32_t(tx * (30 * kCols) + lane);
-        const float4* inR = opaque_ptr(reinterpret_cast<const float4*>(in) + b4);
-        const float4* inG = opaque_ptr(inR + plane4);
-        const float4* inB = opaque_ptr(inG + plane4);
-        uint32_t* labL = opaque_ptr(reinterpret_cast<uint32_t*>(lab) + b4);
-        uint32_t* labA = opaque_ptr(labL + plane4);
-        uint32_t* labB = opaque_ptr(labA + plane4);
-
-        auto load = [&](uint32_t o, int c, float4& r, float4& gch, float4& b) {
-            r = ld_nc_f4(inR + o + 30 * c);
-            gch = ld_nc_f4(inG + o + 30 * c);
-            b = ld_nc_f4(inB + o + 30 * c);
-        };
-        auto prefetch_row = [&](uint32_t o) {
-#pragma unroll
-            for (int c = 0; c < kCols; ++c) {
-                prefetch_l2(inR + o + 30 * c);
-                prefetch_l2(inG + o + 30 * c);
-                prefetch_l2(inB + o + 30 * c);
-            }
-        };
-        auto store = [&](uint32_t o, int c, uint32_t wl, uint32_t wa, uint32_t wb) {
-            st_global_u32(labL + o + 30 * c, wl);
-            st_global_u32(labA + o + 30 * c, wa);
-            st_global_u32(labB + o + 30 * c, wb);
-        };
-
-        int row = row0;
-        uint32_t o = uint32_t(row) * w4;
-        float4 ar, ag, ab, br, bg, bb;
-        if (row < row1) {
-            load(o, 0, ar, ag, ab);
-#pragma unroll 1
-            for (int k = 1; k < kPf; ++k)
-                if (row + k < row1) prefetch_row(o + uint32_t(k) * w4);
-        }
-        while (row < row1) {
-            uint32_t wl, wa, wb;
-            if (row + kPf < row1) prefetch_row(o + uint32_t(kPf) * w4);
-#pragma unroll
-            for (int c = 0; c < kCols; c += 2) {
-                load(o, c + 1, br, bg, bb);
-                k1_item(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
-                store(o, c, wl, wa, wb);
-                if (c + 2 < kCols) load(o, c + 2, ar, ag, ab);
-                else if (row + 1 < row1) load(o + w4, 0, ar, ag, ab);
-                k1_item(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
-                store(o, c + 1, wl, wa, wb);
-            }
-            ++row;
-            o += w4;
-        }
-        __syncwarp();
-
-        // warp-local reduction: lane l sums bin groups 2l and 2l+1 (bins 8l .. 8l+7) over the warp's 32 counter columns
-        // and clears them; 16-byte chunks are visited in an order rotated by the lane (4 lanes per bank group: the minimum)
-        unsigned tot[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) tot[j] = 0;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            uint4* rowp = reinterpret_cast<uint4*>(wcnt + (2 * lane + q) * 1024);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int ch = (k + lane) & 7;
-                const uint4 v = rowp[ch];
-                rowp[ch] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const unsigned sel = 1u << (8 * b);
-                    tot[4 * q + b] = __dp4a(v.x, sel, tot[4 * q + b]);
-                    tot[4 * q + b] = __dp4a(v.y, sel, tot[4 * q + b]);
-                    tot[4 * q + b] = __dp4a(v.z, sel, tot[4 * q + b]);
-                    tot[4 * q + b] = __dp4a(v.w, sel, tot[4 * q + b]);
-                }
-            }
-        }
-        const size_t t_idx = size_t(f) * ntiles + size_t(ty) * g.tiles_x + tx;
-        int32_t* hg = hist_g + t_idx * 256 + 8 * lane;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (tot[j]) atomicAdd(hg + j, int(tot[j]));
-        __threadfence();
-        __syncwarp();
-        unsigned last = 0;
-        if (lane == 0) last = (atomicAdd(tickets + t_idx, 1u) == unsigned(g.nstrips - 1));
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            __threadfence();
-            warp_tile_lut(hist_g + t_idx * 256, g.clip, g.lut_scale, lut_g + t_idx * 256, lane);
-        }
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // K1 generic path: any size (including OpenCV's reflect-101 padding quirk, Appendix A.3 step 1).
 // One CTA per (frame, tile); per-warp shared histograms with atomics.  Correctness path for
 // ragged shapes -- the named workloads all take the vector path.
@@ -1200,6 +1007,7 @@ __device__ __forceinline__ int ab_to_xz5(int i, uint32_t lin)
     return x;
 }
 
+template <uint32_t kAyStride>
 __device__ __forceinline__ void map_pixel5(uint32_t Lv, int av, int bv, float xa, float xa1, float ya, float ya1,
                                            const Map5Tables& t, float& r, float& g, float& b)
 {
@@ -1210,7 +1018,7 @@ __device__ __forceinline__ void map_pixel5(uint32_t Lv, int av, int bv, float xa
     const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
     // rint via 1.5*2^23 (round-half-even == cvRound); 0 <= res < 255.5, so the sum's bits are 0x4B400000 + L'
     int A, y;
-    asm("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(A), "=r"(y) : "r"(__float_as_uint(__fadd_rn(res, 12582912.0f)) * 8u + t.ay_lp));
+    asm("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(A), "=r"(y) : "r"(__float_as_uint(__fadd_rn(res, 12582912.0f)) * kAyStride + t.ay_lp));
     // ix = ify + adiv(a);  iz = ify - bdiv(b) = A + 14678 - ((b*41943+16) >> 9)  with  -(u >> 9) == (511 - u) >> 9
     const int x = ab_to_xz5(A + ((av * 268435 + 128) >> 13), t.lin);
     const int z = ab_to_xz5(A + ((bv * -41943 + (495 + 14678 * 512)) >> 9), t.lin);
@@ -1222,6 +1030,10 @@ __device__ __forceinline__ void map_pixel5(uint32_t Lv, int av, int bv, float xa
     b = lds_f32(uint32_t(bo) * t.four + t.outf);
 }
 
+// kAyRep: the {A, y} table is replicated 16 times ([grey level][lane & 15], 32 KB): its 64-bit gather is served half a
+// warp at a time, so with one copy per lane of a half-warp it is conflict-free (measured 4.4 wavefronts per gather with
+// the plain table).
+template <bool kAyRep>
 __global__ void __launch_bounds__(kK5MaxThreads, 2)
 k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out, const MapGeom g,
            unsigned* __restrict__ work, int nitems)
@@ -1230,7 +1042,7 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
     int16_t* s_lin = reinterpret_cast<int16_t*>(smem5);
     float* s_outf = reinterpret_cast<float*>(smem5 + kXzLinBytes);
     int* s_ay = reinterpret_cast<int*>(s_outf + 4096);             // {A, y}[256]
-    uint32_t* s_quad = reinterpret_cast<uint32_t*>(s_ay + 512);    // [2][256]
+    uint32_t* s_quad = reinterpret_cast<uint32_t*>(s_ay + 512 * (kAyRep ? 16 : 1));    // [2][256]
     __shared__ int s_nxt[2];
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -1252,10 +1064,18 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
     {
         for (int i = tid; i < kXzLinBytes / 16; i += nthr) reinterpret_cast<uint4*>(s_lin)[i] = reinterpret_cast<const uint4*>(d_xzlin)[i];
         for (int i = tid; i < 1024; i += nthr) reinterpret_cast<uint4*>(s_outf)[i] = reinterpret_cast<const uint4*>(d_outf_bits)[i];
+        if constexpr (kAyRep) {
+            for (int i = tid; i < 256 * 16; i += nthr) {
+                const uint32_t yf = d_labyf[i >> 4];
+                reinterpret_cast<int2*>(s_ay)[i] = make_int2(int(yf & 0xffffu) - 4194, int(yf >> 16));
+            }
+        }
         if (tid < 256) {
-            const uint32_t yf = d_labyf[tid];
-            s_ay[tid * 2 + 0] = int(yf & 0xffffu) - 4194;
-            s_ay[tid * 2 + 1] = int(yf >> 16);
+            if constexpr (!kAyRep) {
+                const uint32_t yf = d_labyf[tid];
+                s_ay[tid * 2 + 0] = int(yf & 0xffffu) - 4194;
+                s_ay[tid * 2 + 1] = int(yf >> 16);
+            }
             if (cur < nitems) build_quad(cur, s_quad);
         }
         if (tid == 0) s_nxt[0] = int(gridDim.x + atomicAdd(work, 1u));
@@ -1265,7 +1085,9 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
     Map5Tables t;
     const uint32_t zero = blockIdx.z;  // always 0
     t.four = opaque(4u + zero);
-    t.ay_lp = opaque(uint32_t(__cvta_generic_to_shared(s_ay)) - 0x4B400000u * 8u);
+    constexpr uint32_t kAyStride = kAyRep ? 128u : 8u;
+    t.ay_lp = kAyRep ? uint32_t(__cvta_generic_to_shared(s_ay)) + uint32_t(tid & 15) * 8u + g.ay_bias
+                     : opaque(uint32_t(__cvta_generic_to_shared(s_ay)) - 0x4B400000u * 8u);
     t.outf = opaque(uint32_t(__cvta_generic_to_shared(s_outf)));
     t.lin = opaque(uint32_t(__cvta_generic_to_shared(s_lin)) - 2u * uint32_t(kXzLinMin));
     const uint32_t sixteen = opaque(16u + zero);
@@ -1324,7 +1146,7 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
                 float o[3][4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    map_pixel5(__byte_perm(wl, 0u, 0x4440u | uint32_t(k)), int(__byte_perm(wa, 0u, 0x4440u | uint32_t(k))),
+                    map_pixel5<kAyStride>(__byte_perm(wl, 0u, 0x4440u | uint32_t(k)), int(__byte_perm(wa, 0u, 0x4440u | uint32_t(k))),
                                int(__byte_perm(wb, 0u, 0x4440u | uint32_t(k))), xa[k], xa1[k], ya, ya1, t, o[0][k], o[1][k], o[2][k]);
                 __stcs(reinterpret_cast<float4*>(p), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
                 __stcs(reinterpret_cast<float4*>(const_cast<char*>(wide_imm<16>(p, plane4))), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
@@ -1435,8 +1257,8 @@ static bool valid_shape(int n, int h, int w, int tiles_x, int tiles_y)
 
 // development switch (A/B timing on the GPU box, profiles/r2_clahe.md, r3_clahe.md): UPR_CLAHE_VARIANT bit 0 =
 // first-generation map kernel (k_map_vec), bit 1 = first-generation histogram kernel (k_hist_lab_vec), bit 2 = second-
-// generation histogram kernel (k_hist_lab_vec2) instead of the column-owner one, bit 3 = column-owner tile kernel
-// (k_hist_lab_vec3) where the band kernel (k_hist_lab_band) would run.  Same results either way.
+// generation histogram kernel (k_hist_lab_vec2) instead of the column-owner one, bit 3 = map kernel without the
+// replicated {A, y} table.  Same results either way.
 static int variant()
 {
     const char* e = std::getenv("UPR_CLAHE_VARIANT");   // read per call so that tests can A/B within one process
@@ -1490,6 +1312,7 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
     bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && aligned16(in) && aligned16(out) &&
                 size_t(h) * w * 3 < (size_t(1) << 32) && (!rx || (aligned16(rx->illu) && aligned16(rx->e)));
     if (fast) {
+        m.ay_bias = 0u - 0x4B400000u * 128u;
         m.n = n; m.h = h; m.w = w; m.tiles_x = tiles_x; m.tiles_y = tiles_y; m.inv_tw = inv_tw; m.inv_th = inv_th;
         int c = 0;
         m.bx[0] = 0;
@@ -1523,21 +1346,11 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             // (column-owner kernel: 63 iterations of kK1Threads / tw4 rows; the item-linear kernels allow slightly more)
             const int max_rows = tw4 <= kK1Threads ? 63 * (kK1Threads / tw4) : std::max(1, (63 * kK1Threads) / tw4);
             int nstrips = (g.th + max_rows - 1) / max_rows;
-            int want = (3 * kNumSMsB200 + nf * ntiles - 1) / (nf * ntiles);  // fill the machine for tiny batches
-            // band kernel (one warp per tile column, one CTA per full-width band): 8 tiles across, tile width 240 or 480 px
-            const int bcols = (tiles_x == 8 && tw4 % 30 == 0) ? tw4 / 30 : 0;
-            // (batches with fewer than two bands per resident CTA stay with the tile kernels, which split finer)
-            const int bstrips = bcols ? (g.th + 255 / (4 * bcols) - 1) / (255 / (4 * bcols)) : 0;   // byte counters: <= 255 px per lane and band
-            const bool band = !rx && !(variant() & 14) && (bcols == 2 || bcols == 4) &&
-                              (long long)nf * tiles_y * bstrips >= 2LL * 3 * kNumSMsB200;
-            if (band) {
-                nstrips = bstrips;
-                want = 1;
-            }
+            const int want = (3 * kNumSMsB200 + nf * ntiles - 1) / (nf * ntiles);  // fill the machine for tiny batches
             nstrips = std::min(std::max(nstrips, want), g.th);
             g.strip_rows = (g.th + nstrips - 1) / nstrips;
             g.nstrips = (g.th + g.strip_rows - 1) / g.strip_rows;
-            if ((g.nstrips > 1 || band) && (stage_mask & 1)) {
+            if (g.nstrips > 1 && (stage_mask & 1)) {
                 UPR_CUDA_TRY(cudaMemsetAsync(hist + ftile * 256, 0, size_t(nf) * ntiles * 256 * sizeof(int32_t), stream));
                 UPR_CUDA_TRY(cudaMemsetAsync(tickets + ftile, 0, size_t(nf) * ntiles * sizeof(unsigned), stream));
             }
@@ -1550,19 +1363,7 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             // the column-owner kernel wants (almost) every thread to own a column: 240 of 256 at 1080p and 4K
             const bool col_owner = tw4 <= kK1Threads && (kK1Threads / tw4) * tw4 * 8 >= kK1Threads * 7;
             if (stage_mask & 1) {
-                if (band) {
-                    static unsigned long long mb2 = 0, mb4 = 0;
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_band<2>, smem1, mb2));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_band<4>, smem1, mb4));
-                    const long long items = (long long)nf * tiles_y * g.nstrips;
-                    const dim3 gridb(unsigned(std::min<long long>(items, 3 * kNumSMsB200)));
-                    if (bcols == 2)
-                        k_hist_lab_band<2><<<gridb, kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
-                                                                                 lut + ftile * 256, tickets + ftile, g, int(items));
-                    else
-                        k_hist_lab_band<4><<<gridb, kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
-                                                                                 lut + ftile * 256, tickets + ftile, g, int(items));
-                } else if (rx) {
+                if (rx) {
                     const RetinexIn rxf{rx->illu + size_t(f0) * h * w, rx->e + fplane, rx->eps};
                     k_hist_lab_vec2<true><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
                         in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
@@ -1592,9 +1393,12 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                     const int cw4 = g.tw / 4;
                     int nthr = cw4 <= kK5MaxThreads ? (kK5MaxThreads / cw4) * cw4 : kK5MaxThreads;
                     if (nthr < 256) nthr = kK5MaxThreads;
-                    const size_t smem5 = size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4;
-                    static unsigned long long m5 = 0;
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5, smem5, m5));
+                    const bool ayrep = (variant() & 8) == 0;   // bit 3: plain {A, y} table (A/B timing)
+                    const size_t smem5r = size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 * 16 + 2 * 256 * 4;
+                    const size_t smem5 = ayrep ? smem5r : size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4;
+                    static unsigned long long m5 = 0, m5r = 0;
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<false>, size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4, m5));
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<true>, smem5r, m5r));
                     // items = (frame, cell, strip): ~4 items per resident CTA on small batches, strips of >= 16 rows (every item
                     // costs a barrier and a quad-table build: with 16 items per CTA and 8-row strips a 3-frame call took 99 us
                     // instead of 78 us for the first-generation kernel)
@@ -1605,8 +1409,12 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                     const long long nitems = (long long)nf * ncells * ks5;
                     if (nitems > 0x7fffffffLL / 2) return UPR_E_SHAPE;
                     UPR_CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(unsigned), stream));
-                    k_map_vec5<<<dim3(unsigned(std::min<long long>(nitems, resident))), nthr, smem5, stream>>>(
-                        lab + fplane, lut + ftile * 256, out + fplane, m, work, int(nitems));
+                    if (ayrep)
+                        k_map_vec5<true><<<dim3(unsigned(std::min<long long>(nitems, resident))), nthr, smem5, stream>>>(
+                            lab + fplane, lut + ftile * 256, out + fplane, m, work, int(nitems));
+                    else
+                        k_map_vec5<false><<<dim3(unsigned(std::min<long long>(nitems, resident))), nthr, smem5, stream>>>(
+                            lab + fplane, lut + ftile * 256, out + fplane, m, work, int(nitems));
                 }
                 UPR_LAUNCH_CHECK();
             }
