@@ -272,7 +272,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": base["kind"], "sample": base["sample"]},
             "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -478,7 +478,29 @@ def bench_c5(torch, dist, rank, world, local, args):
 WORKLOADS = {"c2": bench_c2, "c3": bench_c3, "c4": bench_c4, "c5": bench_c5}
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout at
+    NCCL_DEBUG=VERSION/WARN), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to a
+    duplicate of the original stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT_OUT
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -506,7 +528,7 @@ def main():
     try:
         line = WORKLOADS[args.workload](torch, dist, rank, world, local, args)
         if rank == 0:
-            print(json.dumps(line), flush=True)
+            emit(line)
     finally:
         if dist is not None:
             dist.destroy_process_group()
