@@ -1309,7 +1309,9 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
 
     // interpolation cell boundaries from the exact fp32 recipe (monotone in p)
     MapGeom m{};
-    bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && aligned16(in) && aligned16(out) &&
+    // (a one-row strip of a tile must fit the byte counters: <= 63 four-pixel items per thread, i.e. tiles <= 64512 px wide)
+    bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && g.tw / 4 <= 63 * kK1Threads &&
+                aligned16(in) && aligned16(out) &&
                 size_t(h) * w * 3 < (size_t(1) << 32) && (!rx || (aligned16(rx->illu) && aligned16(rx->e)));
     if (fast) {
         m.ay_bias = 0u - 0x4B400000u * 128u;

@@ -156,6 +156,16 @@ def test_kernel_generations_bit_identical(native, monkeypatch):
                 assert np.array_equal(a, b)
 
 
+def test_tiles_wider_than_the_byte_counters_allow(native):
+    """One row of a 65536-px tile is 64 four-pixel items per thread (> 63 = 252 px, the budget of the private byte counters
+    between flushes): such shapes must leave the vector path.  Strip geometry at the budget (tile 64512 px wide) stays on it."""
+    for w in (8 * 65536, 2 * 64512):
+        tiles = (8, 1) if w == 8 * 65536 else (2, 1)
+        x = O.kat_input(400, 4, w, "const")        # worst case: every pixel of a thread lands in one bin
+        x[0, :, 2:, : w // 2] = O.kat_input(401, 2, w // 2, "dark")[0]
+        compare(native, x, 2.0, tiles)
+
+
 @pytest.mark.parametrize("n,h,w,tiles", [(1, 1080, 1920, (8, 8)), (3, 480, 640, (8, 8)), (2, 256, 1024, (4, 2)), (5, 64, 64, (8, 8)),
                                           (1, 2160, 3840, (16, 16)), (2, 96, 2048, (1, 3))])
 def test_persistent_map_kernel_shapes(native, n, h, w, tiles):
