@@ -340,6 +340,21 @@ def bench_c2(torch, dist, rank, world, local, args):
            "api": "AdaptiveParameterAdjuster.apply_clahe_enhancement(host f32 [64,3,1080,1920]) -> host tensor "
                   "(upr_clahe_lab_f32_host, pinned buffers, 3-stream chunk pipeline)"}
 
+    # the same op at the packed u8 boundary (upr_clahe_lab_u8: what image files decode to / are saved as; 3 + 3 B/px instead of
+    # 12 + 12 over PCIe).  Reported beside the headline, which stays on the reference's f32 tensor API.
+    x8 = (x * 255.0).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    o8 = torch.empty_like(x8)
+    ku8 = statistics.median(event_time_ms(torch, lambda: native.clahe_lab_u8(x8, out=o8), 9))
+    hx8 = torch.empty(x8.shape, dtype=torch.uint8, pin_memory=True)
+    hx8.copy_(x8)
+    ho8 = torch.empty(x8.shape, dtype=torch.uint8, pin_memory=True)
+    ms_e2e8 = wall_steps(torch, dist, lambda: native.clahe_lab_u8_host(hx8, out=ho8), e2e_steps, 2) / e2e_steps
+    u8_boundary = {"api": "upr_clahe_lab_u8 / upr_clahe_lab_u8_host (packed u8 RGB, HWC)", "device_ms": ku8,
+                   "device_mpix_s": world * px / 1e6 / (ku8 / 1e3),
+                   "e2e": {"value": world * px / 1e6 / (ms_e2e8 / 1e3), "unit": UNIT, "ms_per_step": ms_e2e8,
+                           "h2d_bytes_per_step": hx8.numel(), "d2h_bytes_per_step": hx8.numel()}}
+    del x8, o8, hx8, ho8
+
     cpu = cpu_reference_rate(h, w, budget_s=args.cpu_budget) if rank == 0 and not args.no_cpu else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -348,7 +363,7 @@ def bench_c2(torch, dist, rank, world, local, args):
                                    "frames per GPU (BASELINE config 2)", "frames_per_gpu": n, "h": h, "w": w,
                        "l2": "inputs larger than L2 (1.59 GB read + 1.59 GB written per step vs 126 MB L2), no flush needed",
                        "sharding": "by frame, no collective"},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline}
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "u8_boundary": u8_boundary}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     return line

@@ -62,6 +62,19 @@ UPR_API size_t upr_clahe_workspace_bytes(int n, int h, int w, int tiles_x, int t
 UPR_API int upr_clahe_lab_f32(const float* in_nchw, float* out_nchw, int n, int h, int w,
                               double clip_limit, int tiles_x, int tiles_y,
                               void* workspace, size_t workspace_bytes, upr_stream_t stream);
+/* The same op at the PACKED u8 boundary: the frames are what an image file decodes to and what is written
+ * back -- u8 RGB, HWC -- i.e. exactly the OpenCV part of the reference (adaptive_params.py:145-161) without the float casts
+ * around it.  Equivalent to the f32 entry on x = u8 / 255.f followed by (y * 255.f) truncated to u8: both casts are exact
+ * (trunc(k / 255.f * 255.f) == k for k = 0..255, pinned in tests/test_oracle_pin.py).  6 instead of 24 bytes per pixel cross
+ * the boundary.  upr_clahe_lab_f32_u8 takes the reference's f32 NCHW tensor and writes the packed u8 frame that
+ * save_image (enhancers/simple_enhance.py:65-100) would store.  Same workspace as upr_clahe_lab_f32; in place is allowed
+ * for the u8 -> u8 entry. */
+UPR_API int upr_clahe_lab_u8(const unsigned char* in_nhwc_rgb, unsigned char* out_nhwc_rgb, int n, int h, int w,
+                             double clip_limit, int tiles_x, int tiles_y,
+                             void* workspace, size_t workspace_bytes, upr_stream_t stream);
+UPR_API int upr_clahe_lab_f32_u8(const float* in_nchw, unsigned char* out_nhwc_rgb, int n, int h, int w,
+                                 double clip_limit, int tiles_x, int tiles_y,
+                                 void* workspace, size_t workspace_bytes, upr_stream_t stream);
 /* Profiling hook: runs only the selected stages of upr_clahe_lab_f32 on a workspace that a full call has
  * already populated.  stage_mask bit 0 = K1 (quantise + Lab + tile histograms + clip/LUT), bit 1 = K3
  * (bilinear LUT map + Lab->RGB); bench.py uses it to time each kernel with CUDA events. */
@@ -96,6 +109,10 @@ UPR_API int upr_get_tables(uint16_t* gamma, uint16_t* cbrt, uint32_t* labyf, uin
  * frames_per_chunk <= 0 selects ~96 MB chunks.  upr_host_pool_release() frees the staging pool. */
 UPR_API int upr_clahe_lab_f32_host(const float* in_host, float* out_host, int n, int h, int w, double clip_limit,
                                    int tiles_x, int tiles_y, int frames_per_chunk);
+/* The packed u8 boundary with HOST buffers: u8 RGB (HWC) in host memory in and out, 3 + 3 instead of 12 + 12 bytes per pixel over
+ * PCIe.  Same pipeline, same chunking rule (frames per chunk as for the f32 entry). */
+UPR_API int upr_clahe_lab_u8_host(const unsigned char* in_host, unsigned char* out_host, int n, int h, int w, double clip_limit,
+                                  int tiles_x, int tiles_y, int frames_per_chunk);
 UPR_API int upr_host_pool_release(void);
 
 /* ---- a3: brightness histogram ---------------------------------------------------------

@@ -39,6 +39,7 @@ __device__ const uint16_t d_cbrt[UPR_TAB_CBRT_LEN] = UPR_TAB_CBRT_INIT;
 __device__ const uint32_t d_labyf[UPR_TAB_LABYF_LEN] = UPR_TAB_LABYF_INIT;
 __device__ const uint32_t d_outf_bits[UPR_TAB_INVGAMMA_F32BITS_LEN] = UPR_TAB_INVGAMMA_F32BITS_INIT;
 __device__ __align__(16) const int16_t d_xzlin[UPR_TAB_XZLIN_LEN + 8] = UPR_TAB_XZLIN_INIT;   // padded to a multiple of 16 bytes
+__device__ __align__(16) const uint8_t d_invgamma[UPR_TAB_INVGAMMA_LEN] = UPR_TAB_INVGAMMA_INIT;  // u8 outputs (packed u8 frames)
 
 static const uint16_t h_gamma[UPR_TAB_GAMMA_LEN] = UPR_TAB_GAMMA_INIT;
 static const uint16_t h_cbrt[UPR_TAB_CBRT_LEN] = UPR_TAB_CBRT_INIT;
@@ -391,6 +392,12 @@ __device__ __forceinline__ float4 ld_nc_f4(const void* p)
     asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint32_t ld_nc_u32p(const void* p)
+{
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
     uint32_t v;
@@ -404,6 +411,9 @@ struct K1Tables {
     uint32_t cbr_q;    // &s_cbrt[0] - 2 * 0x4B000000
     uint32_t four, sixteen;
 };
+
+__device__ __forceinline__ void k1_core(const float (&R)[4], const float (&G)[4], const float (&B)[4], const K1Tables& t,
+                                        unsigned char* s_cnt, uint32_t tid4, uint32_t& wl, uint32_t& wa, uint32_t& wb);
 
 // 12 floats (4 px x RGB) -> three Lab words + four counter increments
 __device__ __forceinline__ void k1_item(const float4 vr, const float4 vg, const float4 vb, const K1Tables& t,
@@ -434,9 +444,30 @@ __device__ __forceinline__ void k1_item(const float4 vr, const float4 vg, const 
             B[k] = lds_f32(uint32_t(quantize_u8(pb[k])) * 4u + t.gam);
         }
     }
+    k1_core(R, G, B, t, s_cnt, tid4, wl, wa, wb);
+}
+
+// 12 packed bytes (4 px x RGB, HWC order: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3) -> three Lab words + four counter increments
+__device__ __forceinline__ void k1_item_u8(uint32_t w0, uint32_t w1, uint32_t w2, const K1Tables& t, unsigned char* s_cnt,
+                                           uint32_t tid4, uint32_t& wl, uint32_t& wa, uint32_t& wb)
+{
+    // byte k of a word, times four, is ((w >> (8k - 2)) & 0x3FC): the gamma table is indexed by the byte itself
+    auto gam = [&](uint32_t w, int k) {
+        const uint32_t off = k == 0 ? (w << 2) & 0x3FCu : (w >> (8 * k - 2)) & 0x3FCu;
+        return lds_f32(off + t.gam);
+    };
+    const float R[4] = {gam(w0, 0), gam(w0, 3), gam(w1, 2), gam(w2, 1)};
+    const float G[4] = {gam(w0, 1), gam(w1, 0), gam(w1, 3), gam(w2, 2)};
+    const float B[4] = {gam(w0, 2), gam(w1, 1), gam(w2, 0), gam(w2, 3)};
+    k1_core(R, G, B, t, s_cnt, tid4, wl, wa, wb);
+}
+
+// gamma-table values of 4 pixels (exact small integers in fp32) -> three Lab words + four counter increments
+__device__ __forceinline__ void k1_core(const float (&R)[4], const float (&G)[4], const float (&B)[4], const K1Tables& t,
+                                        unsigned char* s_cnt, uint32_t tid4, uint32_t& wl, uint32_t& wa, uint32_t& wb)
+{
     int vL[4], vA[4], vB[4], fY[4];
-    // Y first: L only needs fY, and the four dependent read-modify-writes of the private counters then overlap the
-    // X/Z arithmetic instead of trailing it
+    // Y first: L only needs fY, and the four counter updates then overlap the X/Z arithmetic instead of trailing it
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         // S = c0 R + c1 G + c2 B + 2048 is an exact integer < 2^24; RZ(S / 4096 + 2^23) carries floor(S / 4096)
@@ -701,8 +732,11 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
 // loop trip (two items), 263 M instead of 293 M executed warp instructions per 64 x 1080p -- at the SAME 0.402 ms: the
 // kernel is bound by its memory streams, not by issue (profiles/r3_clahe.md).  Same arithmetic (k1_item): bit-identical.
 // ---------------------------------------------------------------------------------------------
+// kU8In: the frame is packed u8 RGB (HWC, upr_clahe_lab_u8): a 4-pixel group is 12 contiguous bytes, three 32-bit loads;
+// the bytes index the gamma table directly (no quantisation), everything after that is shared with the f32 kernel.
+template <bool kU8In>
 __global__ void __launch_bounds__(kK1Threads, 3)
-k_hist_lab_vec3(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
+k_hist_lab_vec3(const void* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
                 uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -756,19 +790,36 @@ k_hist_lab_vec3(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
     const float4* inR = opaque_ptr(reinterpret_cast<const float4*>(in) + (size_t(f) * 3 * plane4 + uint32_t(tx * tw4 + lc)));
     const float4* inG = opaque_ptr(inR + plane4);
     const float4* inB = opaque_ptr(inG + plane4);
+    struct Px4 { uint32_t w[3]; };   // one 4-pixel group of a packed u8 frame
+    const Px4* in8 = opaque_ptr(reinterpret_cast<const Px4*>(in) + (size_t(f) * plane4 + uint32_t(tx * tw4 + lc)));
     uint32_t* labL = opaque_ptr(reinterpret_cast<uint32_t*>(lab) + (size_t(f) * 3 * plane4 + uint32_t(tx * tw4 + lc)));
     uint32_t* labA = opaque_ptr(labL + plane4);
     uint32_t* labB = opaque_ptr(labA + plane4);
 
+    // (u8 frames: the three words of a group travel in the .x lanes of the three float4 registers)
     auto load = [&](uint32_t o, float4& r, float4& gch, float4& b) {
-        r = ld_nc_f4(inR + o);
-        gch = ld_nc_f4(inG + o);
-        b = ld_nc_f4(inB + o);
+        if constexpr (kU8In) {
+            r.x = __uint_as_float(ld_nc_u32p(&in8[o].w[0]));
+            gch.x = __uint_as_float(ld_nc_u32p(&in8[o].w[1]));
+            b.x = __uint_as_float(ld_nc_u32p(&in8[o].w[2]));
+        } else {
+            r = ld_nc_f4(inR + o);
+            gch = ld_nc_f4(inG + o);
+            b = ld_nc_f4(inB + o);
+        }
     };
     auto prefetch = [&](uint32_t o) {
-        prefetch_l2(inR + o);
-        prefetch_l2(inG + o);
-        prefetch_l2(inB + o);
+        if constexpr (kU8In) {
+            prefetch_l2(in8 + o);
+        } else {
+            prefetch_l2(inR + o);
+            prefetch_l2(inG + o);
+            prefetch_l2(inB + o);
+        }
+    };
+    auto item = [&](const float4& r, const float4& gch, const float4& b, uint32_t& wl, uint32_t& wa, uint32_t& wb) {
+        if constexpr (kU8In) k1_item_u8(__float_as_uint(r.x), __float_as_uint(gch.x), __float_as_uint(b.x), t, s_cnt, tid4, wl, wa, wb);
+        else k1_item(r, gch, b, t, s_cnt, tid4, wl, wa, wb);
     };
     auto store = [&](uint32_t o, uint32_t wl, uint32_t wa, uint32_t wb) {
         st_global_u32(labL + o, wl);
@@ -791,14 +842,14 @@ k_hist_lab_vec3(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
         uint32_t wl, wa, wb;
         if (row < row_ld) load(o + step, br, bg, bb);
         if (row < row_pf) prefetch(o + pfo);
-        k1_item(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
+        item(ar, ag, ab, wl, wa, wb);
         store(o, wl, wa, wb);
         row += rpi;
         o += step;
         if (row >= row1) break;
         if (row < row_ld) load(o + step, ar, ag, ab);
         if (row < row_pf) prefetch(o + pfo);
-        k1_item(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
+        item(br, bg, bb, wl, wa, wb);
         store(o, wl, wa, wb);
         row += rpi;
         o += step;
@@ -837,8 +888,9 @@ __device__ __forceinline__ int reflect101(int p, int len)
     return p;
 }
 
+template <bool kU8In>
 __global__ void __launch_bounds__(256)
-k_hist_lab_generic(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
+k_hist_lab_generic(const void* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
                    uint8_t* __restrict__ lut_g, const ClaheGeom g)
 {
     __shared__ int s_hist[8][256];
@@ -857,7 +909,8 @@ k_hist_lab_generic(const float* __restrict__ in, uint8_t* __restrict__ lab, int3
     __syncthreads();
 
     const size_t plane = size_t(g.h) * g.w;
-    const float* inR = in + size_t(f) * 3 * plane;
+    const float* inR = reinterpret_cast<const float*>(in) + size_t(f) * 3 * plane;
+    const uint8_t* in8 = reinterpret_cast<const uint8_t*>(in) + size_t(f) * 3 * plane;   // kU8In: packed RGB (HWC)
     uint8_t* labL = lab + size_t(f) * 3 * plane;
     const int area = g.tw * g.th;
     const uint64_t pol_stream = policy_evict_first();
@@ -865,9 +918,14 @@ k_hist_lab_generic(const float* __restrict__ in, uint8_t* __restrict__ lab, int3
         const int py = ty * g.th + i / g.tw, px = tx * g.tw + i % g.tw;
         const bool inside = py < g.h && px < g.w;
         const size_t off = size_t(reflect101(py, g.h)) * g.w + reflect101(px, g.w);
-        const int qr = quantize_u8(ld_stream_f1(inR + off, pol_stream));
-        const int qg = quantize_u8(ld_stream_f1(inR + plane + off, pol_stream));
-        const int qb = quantize_u8(ld_stream_f1(inR + 2 * plane + off, pol_stream));
+        int qr, qg, qb;
+        if constexpr (kU8In) {
+            qr = in8[3 * off + 0]; qg = in8[3 * off + 1]; qb = in8[3 * off + 2];
+        } else {
+            qr = quantize_u8(ld_stream_f1(inR + off, pol_stream));
+            qg = quantize_u8(ld_stream_f1(inR + plane + off, pol_stream));
+            qb = quantize_u8(ld_stream_f1(inR + 2 * plane + off, pol_stream));
+        }
         int L;
         if (inside) {
             int a, b;
@@ -1007,7 +1065,8 @@ __device__ __forceinline__ int ab_to_xz5(int i, uint32_t lin)
     return x;
 }
 
-template <uint32_t kAyStride>
+// kU8Out: the three results are the u8 channel values (integers in the bit patterns of r, g, b) instead of value / 255
+template <uint32_t kAyStride, bool kU8Out>
 __device__ __forceinline__ void map_pixel5(uint32_t Lv, int av, int bv, float xa, float xa1, float ya, float ya1,
                                            const Map5Tables& t, float& r, float& g, float& b)
 {
@@ -1025,17 +1084,27 @@ __device__ __forceinline__ void map_pixel5(uint32_t Lv, int av, int bv, float xa
     const int ro = __vimin_s32_relu((12615 * x - 6296 * y - 2223 * z + 8192) >> 14, 4095);
     const int go = __vimin_s32_relu((-3773 * x + 7684 * y + 185 * z + 8192) >> 14, 4095);
     const int bo = __vimin_s32_relu((217 * x - 836 * y + 4715 * z + 8192) >> 14, 4095);
-    r = lds_f32(uint32_t(ro) * t.four + t.outf);
-    g = lds_f32(uint32_t(go) * t.four + t.outf);
-    b = lds_f32(uint32_t(bo) * t.four + t.outf);
+    if constexpr (kU8Out) {
+        uint32_t ur, ug, ub;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(ur) : "r"(uint32_t(ro) + t.outf));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(ug) : "r"(uint32_t(go) + t.outf));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(ub) : "r"(uint32_t(bo) + t.outf));
+        r = __uint_as_float(ur); g = __uint_as_float(ug); b = __uint_as_float(ub);
+    } else {
+        r = lds_f32(uint32_t(ro) * t.four + t.outf);
+        g = lds_f32(uint32_t(go) * t.four + t.outf);
+        b = lds_f32(uint32_t(bo) * t.four + t.outf);
+    }
 }
 
 // kAyRep: the {A, y} table is replicated 16 times ([grey level][lane & 15], 32 KB): its 64-bit gather is served half a
 // warp at a time, so with one copy per lane of a half-warp it is conflict-free (measured 4.4 wavefronts per gather with
 // the plain table).
-template <bool kAyRep>
+// kU8Out: the result is a packed u8 RGB frame (HWC; upr_clahe_lab_u8 / upr_clahe_lab_f32_u8): u8 inverse-gamma table, 12 bytes per
+// 4-pixel group in three 32-bit stores.
+template <bool kAyRep, bool kU8Out>
 __global__ void __launch_bounds__(kK5MaxThreads, 2)
-k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out, const MapGeom g,
+k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, void* __restrict__ out, const MapGeom g,
            unsigned* __restrict__ work, int nitems)
 {
     extern __shared__ __align__(16) unsigned char smem5[];
@@ -1063,7 +1132,11 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
     int cur = blockIdx.x;
     {
         for (int i = tid; i < kXzLinBytes / 16; i += nthr) reinterpret_cast<uint4*>(s_lin)[i] = reinterpret_cast<const uint4*>(d_xzlin)[i];
-        for (int i = tid; i < 1024; i += nthr) reinterpret_cast<uint4*>(s_outf)[i] = reinterpret_cast<const uint4*>(d_outf_bits)[i];
+        if constexpr (kU8Out) {   // u8 results: the 4 KB inverse-gamma table itself (first quarter of the same slot)
+            for (int i = tid; i < 256; i += nthr) reinterpret_cast<uint4*>(s_outf)[i] = reinterpret_cast<const uint4*>(d_invgamma)[i];
+        } else {
+            for (int i = tid; i < 1024; i += nthr) reinterpret_cast<uint4*>(s_outf)[i] = reinterpret_cast<const uint4*>(d_outf_bits)[i];
+        }
         if constexpr (kAyRep) {
             for (int i = tid; i < 256 * 16; i += nthr) {
                 const uint32_t yf = d_labyf[i >> 4];
@@ -1112,7 +1185,9 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
         const int y1 = min(y0 + srows, g.by[cy + 1]);
 
         const uint32_t* labL = reinterpret_cast<const uint32_t*>(lab) + size_t(f) * 3 * plane4;
-        float4* outR = reinterpret_cast<float4*>(out) + size_t(f) * 3 * plane4;
+        // bytes per 4-pixel group of the result: 16 (one float4 per plane) or 12 (packed u8 RGB)
+        constexpr uint32_t kOB = kU8Out ? 12u : 16u;
+        char* outF = reinterpret_cast<char*>(out) + size_t(f) * (kU8Out ? 1 : 3) * plane4 * kOB;
         const float txbase = float(cx - 1), tybase = float(cy - 1);
         const int cw4 = (x1 - x0) >> 2;
 
@@ -1131,7 +1206,7 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
             }
             // per-thread 64-bit row pointers, advanced by a constant byte stride (2 instructions per plane and row)
             const char* pl = reinterpret_cast<const char*>(labL + (uint32_t(y0 + lr) * w4 + (uint32_t(x) >> 2)));
-            char* po = reinterpret_cast<char*>(outR + (uint32_t(y0 + lr) * w4 + (uint32_t(x) >> 2)));
+            char* po = outF + size_t(uint32_t(y0 + lr) * w4 + (uint32_t(x) >> 2)) * kOB;
             const uint32_t step4 = uint32_t(rpi) * w4;   // row stride of this thread in 4-pixel groups
 
             auto load3 = [&](const char* p, uint32_t& l, uint32_t& a, uint32_t& b) {
@@ -1146,11 +1221,22 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
                 float o[3][4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    map_pixel5<kAyStride>(__byte_perm(wl, 0u, 0x4440u | uint32_t(k)), int(__byte_perm(wa, 0u, 0x4440u | uint32_t(k))),
+                    map_pixel5<kAyStride, kU8Out>(__byte_perm(wl, 0u, 0x4440u | uint32_t(k)), int(__byte_perm(wa, 0u, 0x4440u | uint32_t(k))),
                                int(__byte_perm(wb, 0u, 0x4440u | uint32_t(k))), xa[k], xa1[k], ya, ya1, t, o[0][k], o[1][k], o[2][k]);
-                __stcs(reinterpret_cast<float4*>(p), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
-                __stcs(reinterpret_cast<float4*>(const_cast<char*>(wide_imm<16>(p, plane4))), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
-                __stcs(reinterpret_cast<float4*>(const_cast<char*>(wide_imm<32>(p, plane4))), make_float4(o[2][0], o[2][1], o[2][2], o[2][3]));
+                if constexpr (kU8Out) {
+                    // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+                    auto u = [&](int c, int k) { return __float_as_uint(o[c][k]); };
+                    const uint32_t w0 = u(0, 0) | (u(1, 0) << 8) | (u(2, 0) << 16) | (u(0, 1) << 24);
+                    const uint32_t w1 = u(1, 1) | (u(2, 1) << 8) | (u(0, 2) << 16) | (u(1, 2) << 24);
+                    const uint32_t w2 = u(2, 2) | (u(0, 3) << 8) | (u(1, 3) << 16) | (u(2, 3) << 24);
+                    __stcs(reinterpret_cast<uint32_t*>(p), w0);
+                    __stcs(reinterpret_cast<uint32_t*>(p) + 1, w1);
+                    __stcs(reinterpret_cast<uint32_t*>(p) + 2, w2);
+                } else {
+                    __stcs(reinterpret_cast<float4*>(p), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
+                    __stcs(reinterpret_cast<float4*>(const_cast<char*>(wide_imm<16>(p, plane4))), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
+                    __stcs(reinterpret_cast<float4*>(const_cast<char*>(wide_imm<32>(p, plane4))), make_float4(o[2][0], o[2][1], o[2][2], o[2][3]));
+                }
             };
 
             // three register sets, loads two rows ahead of their use: the ncu source view of the one-row-ahead version
@@ -1166,14 +1252,14 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
                 y += rpi;
                 if (y >= y1) break;
                 if (y + 2 * rpi < y1) load3(wide_imm<12>(pl, step4), al, aa, ab);
-                map_row(y, const_cast<char*>(wide_imm<16>(po, step4)), bl, ba, bb);
+                map_row(y, const_cast<char*>(wide_imm<kOB>(po, step4)), bl, ba, bb);
                 y += rpi;
                 if (y >= y1) break;
                 if (y + 2 * rpi < y1) load3(wide_imm<16>(pl, step4), bl, ba, bb);
-                map_row(y, const_cast<char*>(wide_imm<32>(po, step4)), cl, ca, cb);
+                map_row(y, const_cast<char*>(wide_imm<2 * kOB>(po, step4)), cl, ca, cb);
                 y += rpi;
                 pl = wide_imm<12>(pl, step4);
-                po = const_cast<char*>(wide_imm<48>(po, step4));
+                po = const_cast<char*>(wide_imm<3 * kOB>(po, step4));
             }
         }
         __syncthreads();
@@ -1185,8 +1271,9 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, f
 // ---------------------------------------------------------------------------------------------
 // K3 generic path: one thread per pixel, LUTs read through L1/L2.
 // ---------------------------------------------------------------------------------------------
+template <bool kU8Out>
 __global__ void __launch_bounds__(256)
-k_map_generic(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out,
+k_map_generic(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, void* __restrict__ out,
               int h, int w, int tiles_x, int tiles_y, float inv_tw, float inv_th)
 {
     __shared__ uint32_t s_yf[256];
@@ -1200,7 +1287,8 @@ k_map_generic(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g
     const size_t plane = size_t(h) * w;
     const uint8_t* labL = lab + size_t(f) * 3 * plane;
     const uint8_t* lf = lut_g + size_t(f) * tiles_x * tiles_y * 256;
-    float* outR = out + size_t(f) * 3 * plane;
+    float* outR = reinterpret_cast<float*>(out) + size_t(f) * 3 * plane;
+    uint8_t* out8 = reinterpret_cast<uint8_t*>(out) + size_t(f) * 3 * plane;   // kU8Out: packed RGB (HWC)
     const uint64_t pol_stream = policy_evict_first();
     for (size_t p = size_t(blockIdx.x) * 256 + tid; p < plane; p += size_t(gridDim.x) * 256) {
         const int y = int(p / w), x = int(p - size_t(y) * w);
@@ -1223,9 +1311,16 @@ k_map_generic(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g
         const int Lc = min(max(__float2int_rn(res), 0), 255);
         float r, gch, b;
         lab_to_rgb_f32(Lc, labL[plane + p], labL[2 * plane + p], s_yf, s_outf, r, gch, b);
-        st_stream_f1(outR + p, r, pol_stream);
-        st_stream_f1(outR + plane + p, gch, pol_stream);
-        st_stream_f1(outR + 2 * plane + p, b, pol_stream);
+        if constexpr (kU8Out) {
+            // value / 255 back to the u8 value: k / 255.f * 255.f truncates to k for every k in 0..255 (tests/test_oracle_pin.py)
+            out8[3 * p + 0] = uint8_t(__float2int_rz(__fmul_rn(r, 255.0f)));
+            out8[3 * p + 1] = uint8_t(__float2int_rz(__fmul_rn(gch, 255.0f)));
+            out8[3 * p + 2] = uint8_t(__float2int_rz(__fmul_rn(b, 255.0f)));
+        } else {
+            st_stream_f1(outR + p, r, pol_stream);
+            st_stream_f1(outR + plane + p, gch, pol_stream);
+            st_stream_f1(outR + 2 * plane + p, b, pol_stream);
+        }
     }
 }
 
@@ -1276,12 +1371,18 @@ static inline int raw_tile(int p, float inv)
 // stage_mask: bit 0 = K1 (Lab + histograms + LUTs), bit 1 = K3 (map); 3 = the whole op
 constexpr int kNeedUnfused = -100;   // internal: the fused Retinex prologue exists on the vector path only
 
-static int clahe_run(const float* in, float* out, int n, int h, int w, double clip_limit, int tiles_x, int tiles_y,
-                     void* ws, size_t ws_bytes, cudaStream_t stream, int stage_mask = 3, const RetinexIn* rx = nullptr)
+// in_u8 / out_u8: the frame on that side is packed u8 RGB (HWC) instead of planar f32 (NCHW)
+static int clahe_run(const void* in_v, void* out_v, int n, int h, int w, double clip_limit, int tiles_x, int tiles_y,
+                     void* ws, size_t ws_bytes, cudaStream_t stream, int stage_mask = 3, const RetinexIn* rx = nullptr,
+                     bool in_u8 = false, bool out_u8 = false)
 {
     if (!valid_shape(n, h, w, tiles_x, tiles_y)) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
-    if (!in || !out || !ws) return UPR_E_NULL;
+    if (!in_v || !out_v || !ws) return UPR_E_NULL;
+    if (rx && (in_u8 || out_u8)) return UPR_E_PARAM;
+    const float* in = static_cast<const float*>(in_v);      // valid when !in_u8
+    float* out = static_cast<float*>(out_v);                // valid when !out_u8
+    const size_t in_es = in_u8 ? 1 : sizeof(float), out_es = out_u8 ? 1 : sizeof(float);
     if (!(clip_limit == clip_limit)) return UPR_E_PARAM;
     const ClaheLayout lay = clahe_layout(n, h, w, tiles_x, tiles_y);
     if (ws_bytes < lay.total || (reinterpret_cast<uintptr_t>(ws) & 255u)) return UPR_E_WORKSPACE;
@@ -1310,8 +1411,12 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
     // interpolation cell boundaries from the exact fp32 recipe (monotone in p)
     MapGeom m{};
     // (a one-row strip of a tile must fit the byte counters: <= 63 four-pixel items per thread, i.e. tiles <= 64512 px wide)
+    // the column-owner histogram kernel wants (almost) every thread to own a column: 240 of 256 at 1080p and 4K; it is
+    // the only vector kernel for packed u8 frames
+    const bool col_owner = g.tw / 4 <= kK1Threads && g.tw >= 4 && (kK1Threads / (g.tw / 4)) * (g.tw / 4) * 8 >= kK1Threads * 7;
     bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && g.tw / 4 <= 63 * kK1Threads &&
-                aligned16(in) && aligned16(out) &&
+                (in_u8 ? ((reinterpret_cast<uintptr_t>(in_v) & 3u) == 0 && col_owner) : aligned16(in_v)) &&
+                (out_u8 ? (reinterpret_cast<uintptr_t>(out_v) & 3u) == 0 : aligned16(out_v)) &&
                 size_t(h) * w * 3 < (size_t(1) << 32) && (!rx || (aligned16(rx->illu) && aligned16(rx->e)));
     if (fast) {
         m.ay_bias = 0u - 0x4B400000u * 128u;
@@ -1361,11 +1466,14 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec, smem1, m1));
             UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<false>, smem1, m2));
             UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<true>, smem1, m3));
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3, smem1, m4));
-            // the column-owner kernel wants (almost) every thread to own a column: 240 of 256 at 1080p and 4K
-            const bool col_owner = tw4 <= kK1Threads && (kK1Threads / tw4) * tw4 * 8 >= kK1Threads * 7;
+            static unsigned long long m4u = 0;
+            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3<false>, smem1, m4));
+            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3<true>, smem1, m4u));
             if (stage_mask & 1) {
-                if (rx) {
+                if (in_u8) {
+                    k_hist_lab_vec3<true><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
+                        static_cast<const uint8_t*>(in_v) + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g);
+                } else if (rx) {
                     const RetinexIn rxf{rx->illu + size_t(f0) * h * w, rx->e + fplane, rx->eps};
                     k_hist_lab_vec2<true><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
                         in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
@@ -1373,7 +1481,7 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                     k_hist_lab_vec<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
                                                                                                 lut + ftile * 256, tickets + ftile, g);
                 } else if (col_owner && !(variant() & 4)) {
-                    k_hist_lab_vec3<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
+                    k_hist_lab_vec3<false><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
                         in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g);
                 } else {
                     k_hist_lab_vec2<false><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
@@ -1388,7 +1496,7 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
             ks = std::min(std::max(ks, want3), std::max(cell_rows / 4, 1));
             m.nstrips = ks;
             if (stage_mask & 2) {
-                if (variant() & 1) {
+                if ((variant() & 1) && !out_u8) {
                     k_map_vec<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
                 } else {
                     // thread count: the largest multiple of the interior cell width (in 4-px columns) <= 512
@@ -1398,9 +1506,11 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                     const bool ayrep = (variant() & 8) == 0;   // bit 3: plain {A, y} table (A/B timing)
                     const size_t smem5r = size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 * 16 + 2 * 256 * 4;
                     const size_t smem5 = ayrep ? smem5r : size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4;
-                    static unsigned long long m5 = 0, m5r = 0;
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<false>, size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4, m5));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<true>, smem5r, m5r));
+                    static unsigned long long m5 = 0, m5r = 0, m5u = 0, m5ru = 0;
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<false, false>, size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4, m5));
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<true, false>, smem5r, m5r));
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<false, true>, size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4, m5u));
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<true, true>, smem5r, m5ru));
                     // items = (frame, cell, strip): ~4 items per resident CTA on small batches, strips of >= 16 rows (every item
                     // costs a barrier and a quad-table build: with 16 items per CTA and 8-row strips a 3-frame call took 99 us
                     // instead of 78 us for the first-generation kernel)
@@ -1411,25 +1521,28 @@ static int clahe_run(const float* in, float* out, int n, int h, int w, double cl
                     const long long nitems = (long long)nf * ncells * ks5;
                     if (nitems > 0x7fffffffLL / 2) return UPR_E_SHAPE;
                     UPR_CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(unsigned), stream));
-                    if (ayrep)
-                        k_map_vec5<true><<<dim3(unsigned(std::min<long long>(nitems, resident))), nthr, smem5, stream>>>(
-                            lab + fplane, lut + ftile * 256, out + fplane, m, work, int(nitems));
-                    else
-                        k_map_vec5<false><<<dim3(unsigned(std::min<long long>(nitems, resident))), nthr, smem5, stream>>>(
-                            lab + fplane, lut + ftile * 256, out + fplane, m, work, int(nitems));
+                    const dim3 grid5(unsigned(std::min<long long>(nitems, resident)));
+                    void* outf = static_cast<char*>(out_v) + fplane * out_es;
+                    auto* kfn = out_u8 ? (ayrep ? k_map_vec5<true, true> : k_map_vec5<false, true>)
+                                       : (ayrep ? k_map_vec5<true, false> : k_map_vec5<false, false>);
+                    kfn<<<grid5, nthr, smem5, stream>>>(lab + fplane, lut + ftile * 256, outf, m, work, int(nitems));
                 }
                 UPR_LAUNCH_CHECK();
             }
         } else {
             g.nstrips = 1; g.strip_rows = g.th;
             if (stage_mask & 1) {
-                k_hist_lab_generic<<<dim3(ntiles, nf), 256, 0, stream>>>(in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, g);
+                const void* inf = static_cast<const char*>(in_v) + fplane * in_es;
+                if (in_u8) k_hist_lab_generic<true><<<dim3(ntiles, nf), 256, 0, stream>>>(inf, lab + fplane, hist + ftile * 256, lut + ftile * 256, g);
+                else k_hist_lab_generic<false><<<dim3(ntiles, nf), 256, 0, stream>>>(inf, lab + fplane, hist + ftile * 256, lut + ftile * 256, g);
                 UPR_LAUNCH_CHECK();
             }
             const size_t plane = size_t(h) * w;
             const int gx = int(std::min<size_t>((plane + 255) / 256, 4096));
             if (stage_mask & 2) {
-                k_map_generic<<<dim3(gx, nf), 256, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, h, w, tiles_x, tiles_y, inv_tw, inv_th);
+                void* outf = static_cast<char*>(out_v) + fplane * out_es;
+                if (out_u8) k_map_generic<true><<<dim3(gx, nf), 256, 0, stream>>>(lab + fplane, lut + ftile * 256, outf, h, w, tiles_x, tiles_y, inv_tw, inv_th);
+                else k_map_generic<false><<<dim3(gx, nf), 256, 0, stream>>>(lab + fplane, lut + ftile * 256, outf, h, w, tiles_x, tiles_y, inv_tw, inv_th);
                 UPR_LAUNCH_CHECK();
             }
         }
@@ -1471,6 +1584,20 @@ int upr_retinex_clahe_f32(const float* x, const float* illu, const float* e, flo
     if (rc) return rc;
     return upr::clahe_run(out_nchw, out_nchw, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
                           static_cast<cudaStream_t>(stream));
+}
+
+int upr_clahe_lab_u8(const unsigned char* in_nhwc, unsigned char* out_nhwc, int n, int h, int w, double clip_limit, int tiles_x,
+                     int tiles_y, void* workspace, size_t workspace_bytes, upr_stream_t stream)
+{
+    return upr::clahe_run(in_nhwc, out_nhwc, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream), 3, nullptr, true, true);
+}
+
+int upr_clahe_lab_f32_u8(const float* in_nchw, unsigned char* out_nhwc, int n, int h, int w, double clip_limit, int tiles_x,
+                         int tiles_y, void* workspace, size_t workspace_bytes, upr_stream_t stream)
+{
+    return upr::clahe_run(in_nchw, out_nhwc, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream), 3, nullptr, false, true);
 }
 
 int upr_clahe_lab_stages_f32(const float* in_nchw, float* out_nchw, int n, int h, int w, double clip_limit, int tiles_x,

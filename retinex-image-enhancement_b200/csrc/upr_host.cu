@@ -22,8 +22,8 @@ constexpr size_t kChunkTargetBytes = size_t(96) << 20;  // f32 input bytes per c
 struct HostSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    float* d_in = nullptr;
-    float* d_out = nullptr;
+    void* d_in = nullptr;
+    void* d_out = nullptr;
     void* ws = nullptr;
     size_t img_bytes = 0, ws_bytes = 0;
     bool busy = false;
@@ -61,22 +61,18 @@ static int slot_reserve(HostSlot& s, size_t img_bytes, size_t ws_bytes)
     return UPR_OK;
 }
 
-}  // namespace upr
-
-extern "C" {
-
-int upr_clahe_lab_f32_host(const float* in_host, float* out_host, int n, int h, int w, double clip_limit, int tiles_x,
-                           int tiles_y, int frames_per_chunk)
+// mode 0: f32 NCHW -> f32 NCHW (upr_clahe_lab_f32); mode 1: packed u8 HWC -> packed u8 HWC (upr_clahe_lab_u8)
+static int host_pipeline(int mode, const void* in_host, void* out_host, int n, int h, int w, double clip_limit, int tiles_x,
+                         int tiles_y, int frames_per_chunk)
 {
-    using namespace upr;
     if (n < 0 || h <= 0 || w <= 0 || tiles_x <= 0 || tiles_y <= 0) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
     if (!in_host || !out_host) return UPR_E_NULL;
     int dev = 0;
     UPR_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= kMaxDevices) return UPR_E_DEVICE;
-    const size_t frame_bytes = size_t(3) * h * w * sizeof(float);
-    int chunk = frames_per_chunk > 0 ? frames_per_chunk : int(std::max<size_t>(1, kChunkTargetBytes / frame_bytes));
+    const size_t frame_bytes = size_t(3) * h * w * (mode == 0 ? sizeof(float) : 1);
+    int chunk = frames_per_chunk > 0 ? frames_per_chunk : int(std::max<size_t>(1, kChunkTargetBytes / (size_t(3) * h * w * sizeof(float))));
     chunk = std::min(chunk, n);
     const size_t ws_bytes = upr_clahe_workspace_bytes(chunk, h, w, tiles_x, tiles_y);
     if (ws_bytes == 0) return UPR_E_SHAPE;
@@ -98,13 +94,15 @@ int upr_clahe_lab_f32_host(const float* in_host, float* out_host, int n, int h, 
             if (e != cudaSuccess) { rc = int(e); break; }
             s.busy = false;
         }
-        cudaError_t e = cudaMemcpyAsync(s.d_in, reinterpret_cast<const char*>(in_host) + size_t(f0) * frame_bytes, bytes,
+        cudaError_t e = cudaMemcpyAsync(s.d_in, static_cast<const char*>(in_host) + size_t(f0) * frame_bytes, bytes,
                                         cudaMemcpyHostToDevice, s.stream);
         if (e != cudaSuccess) { rc = int(e); break; }
-        rc = upr_clahe_lab_f32(s.d_in, s.d_out, nf, h, w, clip_limit, tiles_x, tiles_y, s.ws, s.ws_bytes, s.stream);
+        rc = mode == 0 ? upr_clahe_lab_f32(static_cast<const float*>(s.d_in), static_cast<float*>(s.d_out), nf, h, w, clip_limit,
+                                           tiles_x, tiles_y, s.ws, s.ws_bytes, s.stream)
+                       : upr_clahe_lab_u8(static_cast<const unsigned char*>(s.d_in), static_cast<unsigned char*>(s.d_out), nf, h, w,
+                                          clip_limit, tiles_x, tiles_y, s.ws, s.ws_bytes, s.stream);
         if (rc) break;
-        e = cudaMemcpyAsync(reinterpret_cast<char*>(out_host) + size_t(f0) * frame_bytes, s.d_out, bytes,
-                            cudaMemcpyDeviceToHost, s.stream);
+        e = cudaMemcpyAsync(static_cast<char*>(out_host) + size_t(f0) * frame_bytes, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream);
         if (e != cudaSuccess) { rc = int(e); break; }
         e = cudaEventRecord(s.done, s.stream);
         if (e != cudaSuccess) { rc = int(e); break; }
@@ -118,6 +116,22 @@ int upr_clahe_lab_f32_host(const float* in_host, float* out_host, int n, int h, 
         }
     }
     return rc;
+}
+
+}  // namespace upr
+
+extern "C" {
+
+int upr_clahe_lab_f32_host(const float* in_host, float* out_host, int n, int h, int w, double clip_limit, int tiles_x,
+                           int tiles_y, int frames_per_chunk)
+{
+    return upr::host_pipeline(0, in_host, out_host, n, h, w, clip_limit, tiles_x, tiles_y, frames_per_chunk);
+}
+
+int upr_clahe_lab_u8_host(const unsigned char* in_host, unsigned char* out_host, int n, int h, int w, double clip_limit, int tiles_x,
+                          int tiles_y, int frames_per_chunk)
+{
+    return upr::host_pipeline(1, in_host, out_host, n, h, w, clip_limit, tiles_x, tiles_y, frames_per_chunk);
 }
 
 int upr_host_pool_release(void)

@@ -39,6 +39,10 @@ def _declare(lib):
     lib.upr_clahe_workspace_bytes.argtypes = [i32] * 5
     lib.upr_clahe_lab_f32.restype = i32
     lib.upr_clahe_lab_f32.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, vp, sz, vp]
+    lib.upr_clahe_lab_u8.restype = i32
+    lib.upr_clahe_lab_u8.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, vp, sz, vp]
+    lib.upr_clahe_lab_f32_u8.restype = i32
+    lib.upr_clahe_lab_f32_u8.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, vp, sz, vp]
     lib.upr_retinex_clahe_f32.restype = i32
     lib.upr_retinex_clahe_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, C.c_float, f64, i32, i32, vp, sz, vp]
     lib.upr_clahe_lab_stages_f32.restype = i32
@@ -50,6 +54,8 @@ def _declare(lib):
     f32 = C.c_float
     lib.upr_clahe_lab_f32_host.restype = i32
     lib.upr_clahe_lab_f32_host.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, i32]
+    lib.upr_clahe_lab_u8_host.restype = i32
+    lib.upr_clahe_lab_u8_host.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, i32]
     lib.upr_host_pool_release.restype = i32
     lib.upr_brightness_hist_f32.restype = i32
     lib.upr_brightness_hist_f32.argtypes = [vp, i32, i32, i32, vp, vp]
@@ -188,6 +194,54 @@ def clahe_lab(x: torch.Tensor, clip_limit: float = 2.0, tiles: Tuple[int, int] =
     return out
 
 
+def clahe_lab_u8(x: torch.Tensor, clip_limit: float = 2.0, tiles: Tuple[int, int] = (8, 8),
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [N,H,W,3] uint8 CUDA (packed RGB, what an image file decodes to) -> [N,H,W,3] uint8 CUDA (upr_clahe_lab_u8)."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError("x must live on a CUDA device (upretinex-b200 has no CPU path)")
+    if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 3:
+        raise TypeError(f"expected uint8 [N,H,W,3], got {x.dtype} {tuple(x.shape)}")
+    x = x.contiguous()
+    n, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous uint8 CUDA tensor shaped like x")
+    L = lib()
+    tx, ty = int(tiles[0]), int(tiles[1])
+    with torch.cuda.device(x.device):
+        nbytes = L.upr_clahe_workspace_bytes(n, h, w, tx, ty)
+        if nbytes == 0:
+            raise UprError(-2, "upr_clahe_workspace_bytes")
+        ws = workspace(nbytes, x.device)
+        check(L.upr_clahe_lab_u8(x.data_ptr(), out.data_ptr(), n, h, w, float(clip_limit), tx, ty, ws.data_ptr(), ws.numel(),
+                                 _stream()), "upr_clahe_lab_u8")
+    return out
+
+
+def clahe_lab_f32_u8(x: torch.Tensor, clip_limit: float = 2.0, tiles: Tuple[int, int] = (8, 8),
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [N,3,H,W] f32 CUDA -> [N,H,W,3] uint8 CUDA: upr_clahe_lab_f32 followed by the quantisation of save_image, in one op."""
+    x = _require_cuda_f32(x, "x")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"expected [N,3,H,W], got {tuple(x.shape)}")
+    n, _, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=x.device)
+    elif tuple(out.shape) != (n, h, w, 3) or not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous uint8 CUDA tensor [N,H,W,3]")
+    L = lib()
+    tx, ty = int(tiles[0]), int(tiles[1])
+    with torch.cuda.device(x.device):
+        nbytes = L.upr_clahe_workspace_bytes(n, h, w, tx, ty)
+        if nbytes == 0:
+            raise UprError(-2, "upr_clahe_workspace_bytes")
+        ws = workspace(nbytes, x.device)
+        check(L.upr_clahe_lab_f32_u8(x.data_ptr(), out.data_ptr(), n, h, w, float(clip_limit), tx, ty, ws.data_ptr(), ws.numel(),
+                                     _stream()), "upr_clahe_lab_f32_u8")
+    return out
+
+
 def clahe_debug(x_shape, tiles: Tuple[int, int] = (8, 8), device=None, want_lab: bool = True):
     """Histograms / LUTs / Lab intermediate of the last clahe_lab() call on this stream."""
     n, _, h, w = x_shape
@@ -232,6 +286,26 @@ def clahe_lab_host(x: torch.Tensor, clip_limit: float = 2.0, tiles: Tuple[int, i
         raise ValueError("out must be a contiguous float32 host tensor shaped like x")
     check(lib().upr_clahe_lab_f32_host(x.data_ptr(), out.data_ptr(), n, h, w, float(clip_limit), int(tiles[0]),
                                        int(tiles[1]), int(frames_per_chunk)), "upr_clahe_lab_f32_host")
+    return out
+
+
+def clahe_lab_u8_host(x: torch.Tensor, clip_limit: float = 2.0, tiles: Tuple[int, int] = (8, 8),
+                      out: Optional[torch.Tensor] = None, frames_per_chunk: int = 0) -> torch.Tensor:
+    """x: [N,H,W,3] uint8 HOST tensor (decoded image files) -> [N,H,W,3] uint8 HOST (pinned) tensor (upr_clahe_lab_u8_host)."""
+    if x.is_cuda or x.dtype != torch.uint8:
+        raise TypeError("clahe_lab_u8_host expects a uint8 host tensor")
+    if x.dim() != 4 or x.shape[3] != 3:
+        raise ValueError(f"expected [N,H,W,3], got {tuple(x.shape)}")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: upretinex-b200 has no CPU path")
+    x = x.contiguous()
+    n, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.uint8, pin_memory=True)
+    elif out.is_cuda or out.shape != x.shape or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous uint8 host tensor shaped like x")
+    check(lib().upr_clahe_lab_u8_host(x.data_ptr(), out.data_ptr(), n, h, w, float(clip_limit), int(tiles[0]),
+                                      int(tiles[1]), int(frames_per_chunk)), "upr_clahe_lab_u8_host")
     return out
 
 

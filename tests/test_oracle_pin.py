@@ -66,6 +66,29 @@ def test_quantize_matches_numpy_cast():
     assert np.array_equal(O.quantize_u8(x), ref)
 
 
+def test_u8_boundary_casts_are_exact():
+    """The packed u8 entries (upr_clahe_lab_u8 / upr_clahe_lab_f32_u8) rest on two identities of the reference's own casts:
+    the quantiser of adaptive_params.py:142 is the identity on k / 255 (what ToTensor makes of a decoded file), and
+    save_image's (y * 255).astype(u8) (enhancers/simple_enhance.py:91-93) recovers k from the op's output k / 255."""
+    import torch
+    k = np.arange(256, dtype=np.float32)
+    assert np.array_equal(O.quantize_u8(k / np.float32(255)), np.arange(256, dtype=np.uint8))
+    assert np.array_equal(((k / np.float32(255)) * 255).astype(np.uint8), np.arange(256, dtype=np.uint8))
+    t = torch.arange(256, dtype=torch.uint8).float().div(255)      # torchvision ToTensor
+    assert np.array_equal(O.quantize_u8(t.numpy()), np.arange(256, dtype=np.uint8))
+    # and the reference's cv2 chain on a u8 image equals the oracle on u8 / 255, truncated back
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, size=(96, 120, 3), dtype=np.uint8)            # RGB, HWC
+    bgr = np.ascontiguousarray(img[:, :, ::-1])
+    lab = cv2.cvtColor(bgr, cv2.COLOR_BGR2LAB)
+    l, a, b = cv2.split(lab)
+    l = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(l)
+    want = cv2.cvtColor(cv2.merge((l, a, b)), cv2.COLOR_LAB2BGR)[:, :, ::-1]
+    xf = np.ascontiguousarray((img.astype(np.float32) / np.float32(255)).transpose(2, 0, 1)[None])
+    got = (O.clahe_lab(xf)[0] * np.float32(255)).astype(np.uint8).transpose(1, 2, 0)
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("shape", [(400, 600), (1080, 1920), (403, 601), (400, 601), (401, 600), (64, 64),
                                    (17, 23), (135, 240), (9, 9)])
 @pytest.mark.parametrize("kind", ["uniform", "dark", "const", "ramp"])
