@@ -353,6 +353,28 @@ def bench_c2(torch, dist, rank, world, local, args):
                    "device_mpix_s": world * px / 1e6 / (ku8 / 1e3),
                    "e2e": {"value": world * px / 1e6 / (ms_e2e8 / 1e3), "unit": UNIT, "ms_per_step": ms_e2e8,
                            "h2d_bytes_per_step": hx8.numel(), "d2h_bytes_per_step": hx8.numel()}}
+    if rank == 0 and not args.no_cpu:
+        # the CPU chain at the same boundary: the OpenCV calls alone on u8 frames (no float casts), every host core
+        try:
+            from oracle import cv2_chain
+            if cv2_chain.available():
+                import cv2
+                cores = os.cpu_count() or 1
+                workers = max(1, min(cores, 32))
+                cv2.setNumThreads(max(1, cores // workers))
+                sample = hx8[: max(workers, 8)].numpy()
+                cv2_chain.clahe_lab_batch_u8(sample[:workers], workers=workers)
+                best = None
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    cv2_chain.clahe_lab_batch_u8(sample, workers=workers)
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                u8_boundary["cpu_baseline"] = {"value": sample.shape[0] * h * w / 1e6 / best, "unit": UNIT, "cores": cores, "kind": "port",
+                                               "sample": f"{sample.shape[0]} u8 frames, best of 3, {workers} worker threads; "
+                                                         "oracle/cv2_chain.py clahe_lab_batch_u8 (the reference's OpenCV calls alone)"}
+        except Exception as e:  # pragma: no cover
+            u8_boundary["cpu_baseline"] = {"error": repr(e)}
     del x8, o8, hx8, ho8
 
     cpu = cpu_reference_rate(h, w, budget_s=args.cpu_budget) if rank == 0 and not args.no_cpu else None

@@ -36,6 +36,25 @@ def clahe_lab_frame(chw: np.ndarray, clip_limit: float = 2.0, tiles=(8, 8)) -> n
     return np.transpose(rgb.astype(np.float32) / 255.0, (2, 0, 1))
 
 
+def clahe_lab_frame_u8(hwc_rgb: np.ndarray, clip_limit: float = 2.0, tiles=(8, 8)) -> np.ndarray:
+    """The OpenCV part of the chain alone (adaptive_params.py:142-161) on a packed u8 RGB frame [H,W,3] -> [H,W,3] u8: the CPU
+    counterpart of upr_clahe_lab_u8 (the float casts on either side of it are exact on such frames)."""
+    import cv2
+    bgr = cv2.cvtColor(hwc_rgb, cv2.COLOR_RGB2BGR)
+    l, a, b = cv2.split(cv2.cvtColor(bgr, cv2.COLOR_BGR2LAB))
+    l2 = cv2.createCLAHE(clipLimit=clip_limit, tileGridSize=tuple(tiles)).apply(l)
+    return cv2.cvtColor(cv2.cvtColor(cv2.merge((l2, a, b)), cv2.COLOR_LAB2BGR), cv2.COLOR_BGR2RGB)
+
+
+def clahe_lab_batch_u8(frames: np.ndarray, workers: int = 1) -> list:
+    """[N,H,W,3] u8 -> list of N u8 results (thread pool like clahe_lab_batch)."""
+    if workers <= 1:
+        return [clahe_lab_frame_u8(f) for f in frames]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(clahe_lab_frame_u8, frames))
+
+
 def clahe_lab_batch(frames: np.ndarray, workers: int = 1) -> list:
     """[N,3,H,W] -> list of N results.  workers > 1 runs frames on a thread pool (NumPy and OpenCV release
     the GIL), which is how the CPU arm uses every host core; the reference itself loops serially

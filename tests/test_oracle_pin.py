@@ -87,6 +87,8 @@ def test_u8_boundary_casts_are_exact():
     xf = np.ascontiguousarray((img.astype(np.float32) / np.float32(255)).transpose(2, 0, 1)[None])
     got = (O.clahe_lab(xf)[0] * np.float32(255)).astype(np.uint8).transpose(1, 2, 0)
     assert np.array_equal(got, want)
+    from oracle import cv2_chain
+    assert np.array_equal(cv2_chain.clahe_lab_frame_u8(img), want)     # bench.py's CPU arm at the u8 boundary
 
 
 @pytest.mark.parametrize("shape", [(400, 600), (1080, 1920), (403, 601), (400, 601), (401, 600), (64, 64),
