@@ -148,6 +148,9 @@ def dist_setup(torch, n_gpus):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
+        if os.environ.get("UPR_NO_NUMA_BIND", "") == "":
+            from retinex_image_enhancement_b200 import native
+            native.bind_to_gpu_numa_node(local)     # host buffers of the e2e leg land on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         return dist, rank, world, local
     if n_gpus > 1:
