@@ -465,6 +465,22 @@ def bench_c4(torch, dist, rank, world, local, args):
         fused_us = timed_steps(torch, dist, lambda: dsw(x), args.steps, args.warmup) / args.steps * 1e3
     except Exception as e:  # pragma: no cover
         fused_us = f"fused path failed: {e!r}"
+    # the term that weight multiplies: EdgeAwareSmoothnessLoss forward + gradient w.r.t. the illumination map in
+    # three launches, beside the reference's own sequence of torch ops (forward + autograd backward) on the same GPU
+    smooth = None
+    try:
+        illu = torch.rand((b, 1, h, w), device=dev, generator=torch.Generator(device=dev).manual_seed(21 + rank))
+        mod = L.EdgeAwareSmoothnessLoss()
+        ours = statistics.median(event_time_ms(torch, lambda: native.edge_smooth_loss(illu, x), 20)) * 1e3
+
+        def stock():
+            a = illu.detach().requires_grad_(True)
+            mod._stock(a, x).backward()
+
+        theirs = statistics.median(event_time_ms(torch, stock, 20)) * 1e3
+        smooth = {"us_per_step": ours, "us_per_step_torch_ops_same_gpu": theirs, "api": "upr_edge_smooth_loss_f32 (loss + d loss / d illu)"}
+    except Exception as e:  # pragma: no cover
+        smooth = {"error": repr(e)}
     k_tv = statistics.mean(event_time_ms(torch, lambda: native.texture_complexity(x, "tv"), 20))
     k_ed = statistics.mean(event_time_ms(torch, lambda: native.texture_complexity(x, "edge_density"), 20))
     px = b * h * w
@@ -473,7 +489,7 @@ def bench_c4(torch, dist, rank, world, local, args):
     return {"metric": "Mpix/s, texture statistics + dynamic smoothness weight (losses/loss.py:523-583,704-720)",
             "value": world * px / 1e6 / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "us_per_step": ms_step * 1e3, "us_per_step_cuda_graph": graph_us,
-            "us_per_step_fused_peer_kernel": fused_us, "higher_is_better": True,
+            "us_per_step_fused_peer_kernel": fused_us, "smooth_loss": smooth, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp64 accumulators)", "data": "synthetic",
             "config": {"workload": f"c4: upr_texture_tv_f32 on {b}x{c}x{h}x{w} per rank + all-reduce(SUM) of [sum, count] + weight kernel",
                        "l2": "latency-bound config (6.3 MB input is L2 resident by construction); reported in us/step"},

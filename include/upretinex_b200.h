@@ -184,6 +184,19 @@ UPR_API int upr_texture_edge_density_f32(const float* x, int n, int c, int h, in
                                          upr_stream_t stream);
 UPR_API int upr_dynamic_smooth_weight_f32(const float* batch_stats2, float weight_smooth, float* weight_out,
                                           upr_stream_t stream);
+/* ---- N3: the smoothness term the dynamic weight multiplies ---------------------------------------
+ * EdgeAwareSmoothnessLoss.forward(illu_map, img_low) (losses/loss.py:136-176; scaled by the a10 weight at :724):
+ *   loss = mean(wh * fh * |dx I|) + mean(wv * fv * |dy I|),  wh/wv = exp(-lambda * mean_c |dx/dy S|),
+ *   fh/fv = 1 + alpha * (row / column means of the Sobel edge map of mean_c S; that is what the reference's avg_pool2d
+ *   windows (1, W-1) and (H-1, 1) followed by [..., :-1] select).
+ * illu: [n][ci][h][w], img_low: [n][cs][h][w] f32.  loss3[0..2] = {loss, horizontal term, vertical term} (device).
+ * grad_illu (nullable): d loss / d illu, same shape as illu (sign(0) = 0 like torch.abs).  img_low gets no gradient.
+ * Everything derived from img_low is a no-grad image statistic.  Deterministic (ordered fp64 sums).  h, w >= 2. */
+UPR_API size_t upr_smooth_loss_workspace_bytes(int n, int h, int w);
+UPR_API int upr_edge_smooth_loss_f32(const float* illu, const float* img_low, int n, int ci, int cs, int h, int w,
+                                     float lambda_val, float alpha, float* loss3, float* grad_illu,
+                                     void* workspace, size_t workspace_bytes, upr_stream_t stream);
+
 /* a9 + the data-parallel batch mean + a10 in ONE kernel per rank: the texture statistics kernel exchanges its
  * [sum c, B] pair with every peer through NVLink-mapped symmetric memory (P2P stores + system-scope flags) and writes
  * the all-rank statistics and the dynamic smoothness weight itself -- no NCCL call, no second launch.

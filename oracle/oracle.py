@@ -264,6 +264,40 @@ def dynamic_smooth_weight(complexity, weight_smooth=1.0) -> float:
     return float(lib().orc_dynamic_smooth_weight(_p(c), int(c.size), C.c_float(weight_smooth)))
 
 
+def edge_smooth_loss(illu, img_low, lambda_val=10.0, alpha=1.0):
+    """EdgeAwareSmoothnessLoss.forward (losses/loss.py:136-176) and d loss / d illu, restated in NumPy (fp32 element-wise like
+    the reference, fp64 sums).  illu [B,Ci,H,W], img_low [B,Cs,H,W] -> (loss, loss_h, loss_v, grad [B,Ci,H,W])."""
+    I = np.ascontiguousarray(illu, np.float32)
+    S = np.ascontiguousarray(img_low, np.float32)
+    b, ci, h, w = I.shape
+    f32 = np.float32
+    # edge map (:110-136): channel mean, reflect pad 1, Sobel cross-correlation, magnitude
+    gray = S.mean(axis=1, dtype=np.float32, keepdims=True) if S.shape[1] > 1 else S
+    p = np.pad(gray, ((0, 0), (0, 0), (1, 1), (1, 1)), mode="reflect")
+    gx = (p[..., :-2, 2:] - p[..., :-2, :-2]) + f32(2) * (p[..., 1:-1, 2:] - p[..., 1:-1, :-2]) + (p[..., 2:, 2:] - p[..., 2:, :-2])
+    gy = (p[..., 2:, :-2] - p[..., :-2, :-2]) + f32(2) * (p[..., 2:, 1:-1] - p[..., :-2, 1:-1]) + (p[..., 2:, 2:] - p[..., :-2, 2:])
+    edge = np.sqrt(gx * gx + gy * gy).astype(np.float32)                                       # [B,1,H,W]
+    # avg_pool2d((1, W-1), stride 1)[..., :-1] is the mean of the first W-1 columns; likewise for rows (:163-164)
+    fh = (f32(1) + f32(alpha) * edge[..., : w - 1].mean(axis=3, dtype=np.float64, keepdims=True).astype(np.float32))   # [B,1,H,1]
+    fv = (f32(1) + f32(alpha) * edge[..., : h - 1, :].mean(axis=2, dtype=np.float64, keepdims=True).astype(np.float32))  # [B,1,1,W]
+    wh = np.exp(f32(-lambda_val) * np.abs(S[..., :-1] - S[..., 1:]).mean(axis=1, dtype=np.float32, keepdims=True)).astype(np.float32)
+    wv = np.exp(f32(-lambda_val) * np.abs(S[..., :-1, :] - S[..., 1:, :]).mean(axis=1, dtype=np.float32, keepdims=True)).astype(np.float32)
+    dh = I[..., :-1] - I[..., 1:]
+    dv = I[..., :-1, :] - I[..., 1:, :]
+    ch = (wh * fh).astype(np.float32)          # [B,1,H,W-1]
+    cv = (wv * fv).astype(np.float32)          # [B,1,H-1,W]
+    loss_h = f32((ch * np.abs(dh)).sum(dtype=np.float64) / dh.size)
+    loss_v = f32((cv * np.abs(dv)).sum(dtype=np.float64) / dv.size)
+    grad = np.zeros_like(I)
+    gh_ = (ch * np.sign(dh)).astype(np.float32) * f32(1.0 / dh.size)
+    gv_ = (cv * np.sign(dv)).astype(np.float32) * f32(1.0 / dv.size)
+    grad[..., :-1] += gh_
+    grad[..., 1:] -= gh_
+    grad[..., :-1, :] += gv_
+    grad[..., 1:, :] -= gv_
+    return f32(loss_h + loss_v), loss_h, loss_v, grad
+
+
 # --------------------------------------------------------------------------- #
 # Deterministic KAT inputs (SURVEY.md section 8c)
 # --------------------------------------------------------------------------- #

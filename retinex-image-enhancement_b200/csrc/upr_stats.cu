@@ -306,6 +306,138 @@ k_texture_edge(const float* __restrict__ x, int c, int h, int w, double* __restr
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// N3: EdgeAwareSmoothnessLoss.forward (losses/loss.py:136-176), the term the dynamic weight of a10 multiplies
+// (:724), with its gradient w.r.t. the illumination map.  Only illu_map carries a gradient; everything derived from
+// img_low is a no-grad image statistic:
+//     wh = exp(-lambda * mean_c |S[..., :-1] - S[..., 1:]|)          [B,1,H,W-1]     (wv likewise, [B,1,H-1,W])
+//     E  = Sobel magnitude of mean_c S, reflect padding              [B,1,H,W]       (sobel_mag above: same as a9)
+//     fh = 1 + alpha * mean(E[..., :W-1], dim=-1)                    [B,1,H,1]       avg_pool2d((1,W-1), stride 1)[..., :-1]
+//     fv = 1 + alpha * mean(E[..., :H-1, :], dim=-2)                 [B,1,1,W]
+//     loss = mean(wh * fh * |I[..., :-1] - I[..., 1:]|) + mean(wv * fv * |I[..., :-1, :] - I[..., 1:, :]|)
+// (yes: the reference's pooling windows make the edge factors ROW and COLUMN means of the edge map).
+// Three launches: edge map + row means, column means, loss + d loss / d I in one pass over S and I.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStThreads)
+k_smooth_edge_rows(const float* __restrict__ s_img, int cs, int h, int w, float* __restrict__ edge, float* __restrict__ rowmean)
+{
+    // one warp per image row
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int y = blockIdx.x * (kStThreads / 32) + wid, f = blockIdx.y;
+    if (y >= h) return;
+    const long long plane = (long long)h * w;
+    const float* img = s_img + (long long)f * cs * plane;
+    float* e = edge + (long long)f * plane + (long long)y * w;
+    double acc = 0.0;
+    for (int x = lane; x < w; x += 32) {
+        const float m = sobel_mag(img, plane, cs, h, w, y, x);
+        e[x] = m;
+        if (x < w - 1) acc += double(m);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) rowmean[(long long)f * h + y] = float(acc / double(w - 1));
+}
+
+__global__ void __launch_bounds__(kStThreads)
+k_smooth_edge_cols(const float* __restrict__ edge, int h, int w, float* __restrict__ colmean)
+{
+    const int x = blockIdx.x * kStThreads + threadIdx.x, f = blockIdx.y;
+    if (x >= w) return;
+    const float* e = edge + (long long)f * h * w + x;
+    double acc = 0.0;
+    for (int y = 0; y < h - 1; ++y) acc += double(__ldg(e + (long long)y * w));
+    colmean[(long long)f * w + x] = float(acc / double(h - 1));
+}
+
+__device__ __forceinline__ float sgnf(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+
+// exp(-lambda * mean_c |S(p) - S(q)|)
+__device__ __forceinline__ float smooth_weight(const float* __restrict__ img, long long plane, int cs, long long p, long long q, float lambda)
+{
+    float s = 0.0f;
+    for (int c = 0; c < cs; ++c) s = __fadd_rn(s, fabsf(__fsub_rn(__ldg(img + c * plane + p), __ldg(img + c * plane + q))));
+    return expf(__fmul_rn(-lambda, __fdiv_rn(s, float(cs))));
+}
+
+__global__ void __launch_bounds__(kStThreads)
+k_smooth_loss(const float* __restrict__ illu, const float* __restrict__ s_img, int n, int ci, int cs, int h, int w, float lambda,
+              float alpha, const float* __restrict__ rowmean, const float* __restrict__ colmean, float* __restrict__ grad,
+              double* __restrict__ partial, unsigned* __restrict__ tickets, float* __restrict__ loss3)
+{
+    __shared__ double s_red[kStThreads / 32];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    const int f = blockIdx.y, parts = gridDim.x;
+    const long long plane = (long long)h * w;
+    const float* img = s_img + (long long)f * cs * plane;
+    const float* il = illu + (long long)f * ci * plane;
+    float* gr = grad ? grad + (long long)f * ci * plane : nullptr;
+    const double inv_nh = 1.0 / (double(n) * ci * h * (w - 1)), inv_nv = 1.0 / (double(n) * ci * (h - 1) * w);
+    const float g_h = float(inv_nh), g_v = float(inv_nv);
+    double sh = 0.0, sv = 0.0;
+    const long long stride = (long long)parts * kStThreads;
+    for (long long p = (long long)blockIdx.x * kStThreads + tid; p < plane; p += stride) {
+        const int y = int(p / w), x = int(p - (long long)y * w);
+        const float fh = __fadd_rn(1.0f, __fmul_rn(alpha, __ldg(rowmean + (long long)f * h + y)));
+        const float fv = __fadd_rn(1.0f, __fmul_rn(alpha, __ldg(colmean + (long long)f * w + x)));
+        // the four edges that touch this pixel: right (y,x), left (y,x-1), down (y,x), up (y-1,x)
+        const bool has_r = x + 1 < w, has_l = x > 0, has_d = y + 1 < h, has_u = y > 0;
+        const float wr = has_r ? __fmul_rn(smooth_weight(img, plane, cs, p, p + 1, lambda), fh) : 0.0f;
+        const float wd = has_d ? __fmul_rn(smooth_weight(img, plane, cs, p, p + w, lambda), fv) : 0.0f;
+        float wl = 0.0f, wu = 0.0f;
+        if (gr) {
+            wl = has_l ? __fmul_rn(smooth_weight(img, plane, cs, p - 1, p, lambda), fh) : 0.0f;
+            wu = has_u ? __fmul_rn(smooth_weight(img, plane, cs, p - w, p, lambda), fv) : 0.0f;
+        }
+        for (int c = 0; c < ci; ++c) {
+            const float* ic = il + c * plane;
+            const float v = __ldg(ic + p);
+            const float dr = has_r ? __fsub_rn(v, __ldg(ic + p + 1)) : 0.0f;
+            const float dd = has_d ? __fsub_rn(v, __ldg(ic + p + w)) : 0.0f;
+            sh += double(__fmul_rn(wr, fabsf(dr)));
+            sv += double(__fmul_rn(wd, fabsf(dd)));
+            if (gr) {
+                const float dl = has_l ? __fsub_rn(__ldg(ic + p - 1), v) : 0.0f;
+                const float du = has_u ? __fsub_rn(__ldg(ic + p - w), v) : 0.0f;
+                const float gh = __fsub_rn(__fmul_rn(wr, sgnf(dr)), __fmul_rn(wl, sgnf(dl)));
+                const float gv = __fsub_rn(__fmul_rn(wd, sgnf(dd)), __fmul_rn(wu, sgnf(du)));
+                gr[c * plane + p] = __fadd_rn(__fmul_rn(gh, g_h), __fmul_rn(gv, g_v));
+            }
+        }
+    }
+    sh = block_sum(sh, s_red);
+    sv = block_sum(sv, s_red);
+    if (tid == 0) {
+        partial[((long long)f * parts + blockIdx.x) * 2 + 0] = sh;
+        partial[((long long)f * parts + blockIdx.x) * 2 + 1] = sv;
+    }
+    if (!last_cta_of(tickets + f, parts, &s_flag)) return;
+    if (tid == 0) {
+        // image totals into the first slot of the image (ordered sum), then the image that finishes last adds the images in order
+        double th = 0.0, tv = 0.0;
+        for (int k = 0; k < parts; ++k) {
+            th += __ldcg(&partial[((long long)f * parts + k) * 2 + 0]);
+            tv += __ldcg(&partial[((long long)f * parts + k) * 2 + 1]);
+        }
+        partial[(long long)f * parts * 2 + 0] = th;
+        partial[(long long)f * parts * 2 + 1] = tv;
+        __threadfence();
+        unsigned* batch_ticket = tickets + n;
+        if (atomicAdd(batch_ticket, 1u) != unsigned(n - 1)) return;
+        *batch_ticket = 0;
+        __threadfence();
+        double ah = 0.0, av = 0.0;
+        for (int i = 0; i < n; ++i) {
+            ah += __ldcg(&partial[(long long)i * parts * 2 + 0]);
+            av += __ldcg(&partial[(long long)i * parts * 2 + 1]);
+        }
+        const float lh = float(ah * inv_nh), lv = float(av * inv_nv);
+        loss3[0] = __fadd_rn(lh, lv);
+        loss3[1] = lh;
+        loss3[2] = lv;
+    }
+}
+
 __global__ void k_dynamic_weight(const float* __restrict__ stats2, float w0, float* __restrict__ out)
 {
     out[0] = dyn_weight(stats2[0], stats2[1], w0);
@@ -416,6 +548,47 @@ int upr_texture_edge_density_f32(const float* x, int n, int c, int h, int w, flo
 {
     return texture_run(1, x, n, c, h, w, per_image, batch_stats2, workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream));
+}
+
+size_t upr_smooth_loss_workspace_bytes(int n, int h, int w)
+{
+    if (n < 0 || h < 2 || w < 2) return 0;
+    const size_t nn = size_t(std::max(n, 1));
+    return upr::align_up(nn * 1024 * 2 * sizeof(double), 256) + upr::align_up((nn + 1) * sizeof(unsigned), 256) +
+           upr::align_up(nn * h * sizeof(float), 256) + upr::align_up(nn * w * sizeof(float), 256) +
+           upr::align_up(nn * size_t(h) * w * sizeof(float), 256);
+}
+
+int upr_edge_smooth_loss_f32(const float* illu, const float* img_low, int n, int ci, int cs, int h, int w, float lambda_val, float alpha,
+                             float* loss3, float* grad_illu, void* workspace, size_t workspace_bytes, upr_stream_t stream)
+{
+    using namespace upr;
+    if (n <= 0 || n > 65535 || ci <= 0 || cs <= 0 || h < 2 || w < 2) return UPR_E_SHAPE;
+    if (!illu || !img_low || !loss3 || !workspace) return UPR_E_NULL;
+    if (workspace_bytes < upr_smooth_loss_workspace_bytes(n, h, w) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return UPR_E_WORKSPACE;
+    auto s = static_cast<cudaStream_t>(stream);
+    auto* base = static_cast<unsigned char*>(workspace);
+    auto* partial = reinterpret_cast<double*>(base);
+    size_t off = align_up(size_t(n) * 1024 * 2 * sizeof(double), 256);
+    auto* tickets = reinterpret_cast<unsigned*>(base + off);
+    off += align_up((size_t(n) + 1) * sizeof(unsigned), 256);
+    auto* rowmean = reinterpret_cast<float*>(base + off);
+    off += align_up(size_t(n) * h * sizeof(float), 256);
+    auto* colmean = reinterpret_cast<float*>(base + off);
+    off += align_up(size_t(n) * w * sizeof(float), 256);
+    auto* edge = reinterpret_cast<float*>(base + off);
+    // the tickets are self-cleaning, but this workspace is not required to arrive zero-filled: clear them (n + 1 words)
+    UPR_CUDA_TRY(cudaMemsetAsync(tickets, 0, (size_t(n) + 1) * sizeof(unsigned), s));
+    const int rows_per_cta = kStThreads / 32;
+    k_smooth_edge_rows<<<dim3((h + rows_per_cta - 1) / rows_per_cta, n), kStThreads, 0, s>>>(img_low, cs, h, w, edge, rowmean);
+    UPR_LAUNCH_CHECK();
+    k_smooth_edge_cols<<<dim3((w + kStThreads - 1) / kStThreads, n), kStThreads, 0, s>>>(edge, h, w, colmean);
+    UPR_LAUNCH_CHECK();
+    const int parts = tex_parts(n, (long long)h * w);
+    k_smooth_loss<<<dim3(parts, n), kStThreads, 0, s>>>(illu, img_low, n, ci, cs, h, w, lambda_val, alpha, rowmean, colmean, grad_illu,
+                                                         partial, tickets, loss3);
+    UPR_LAUNCH_CHECK();
+    return UPR_OK;
 }
 
 size_t upr_peer_stats_buffer_bytes(void) { return upr::kPeerBufBytes; }

@@ -106,3 +106,58 @@ class DynamicSmoothWeight:
         _per_image, stats = batch_texture_stats(img_low, self.texture_method)
         all_reduce_batch_stats(stats, self.group)
         return weight_from_stats(stats, self.weight_smooth)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the smoothness term itself (the loss the dynamic weight above multiplies, losses/loss.py:724)
+# ---------------------------------------------------------------------------------------------------
+class _EdgeSmoothFn(torch.autograd.Function):
+    """loss = EdgeAwareSmoothnessLoss(illu_map, img_low); only illu_map carries a gradient.  The kernel that forms the loss
+    also writes d loss / d illu (the weights and edge factors are no-grad statistics of img_low), so backward is one scale."""
+
+    @staticmethod
+    def forward(ctx, illu_map, img_low, lambda_val, alpha):
+        need = illu_map.requires_grad
+        loss3, grad = native.edge_smooth_loss(illu_map.detach(), img_low.detach(), lambda_val, alpha, want_grad=need)
+        ctx.save_for_backward(grad if need else torch.empty(0, device=illu_map.device))
+        ctx.has_grad = need
+        return loss3[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (g,) = ctx.saved_tensors
+        return (g * grad_out if ctx.has_grad else None), None, None, None
+
+
+class EdgeAwareSmoothnessLoss(torch.nn.Module):
+    """Drop-in for losses/loss.py:61-176 (same constructor arguments, ``forward(illu_map, img_low)`` -> scalar).
+
+    CUDA tensors go through ``upr_edge_smooth_loss_f32`` (forward value and the gradient w.r.t. ``illu_map`` from one pass
+    over the batch).  If ``img_low`` itself requires a gradient (it never does in the reference's trainer: it is the input
+    image) the stock formulation below runs instead, so autograd still reaches it; CPU tensors raise like every op here."""
+
+    def __init__(self, lambda_val: float = 10.0, alpha: float = 1.0):
+        super().__init__()
+        self.lambda_val = lambda_val
+        self.alpha = alpha
+
+    def forward(self, illu_map: torch.Tensor, img_low: torch.Tensor) -> torch.Tensor:
+        if img_low.requires_grad:
+            return self._stock(illu_map, img_low)
+        return _EdgeSmoothFn.apply(illu_map, img_low, float(self.lambda_val), float(self.alpha))
+
+    def _stock(self, illu_map, img_low):
+        # the reference's own sequence of torch ops (losses/loss.py:118-176)
+        import torch.nn.functional as F
+        gh = lambda t: t[:, :, :, :-1] - t[:, :, :, 1:]      # noqa: E731
+        gv = lambda t: t[:, :, :-1, :] - t[:, :, 1:, :]      # noqa: E731
+        gray = torch.mean(img_low, dim=1, keepdim=True) if img_low.shape[1] > 1 else img_low
+        padded = F.pad(gray, (1, 1, 1, 1), mode="reflect")
+        kx = torch.tensor([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], dtype=torch.float32, device=img_low.device).view(1, 1, 3, 3)
+        ky = torch.tensor([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], dtype=torch.float32, device=img_low.device).view(1, 1, 3, 3)
+        edge = torch.sqrt(F.conv2d(padded, kx) ** 2 + F.conv2d(padded, ky) ** 2)
+        wh = torch.exp(-self.lambda_val * torch.mean(torch.abs(gh(img_low)), dim=1, keepdim=True))
+        wv = torch.exp(-self.lambda_val * torch.mean(torch.abs(gv(img_low)), dim=1, keepdim=True))
+        fh = 1 + self.alpha * F.avg_pool2d(edge, kernel_size=(1, wh.shape[3]), stride=1)[:, :, :, :-1]
+        fv = 1 + self.alpha * F.avg_pool2d(edge, kernel_size=(wv.shape[2], 1), stride=1)[:, :, :-1, :]
+        return torch.mean(wh * fh * torch.abs(gh(illu_map))) + torch.mean(wv * fv * torch.abs(gv(illu_map)))

@@ -93,6 +93,10 @@ def _declare(lib):
     lib.upr_texture_tv_f32.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     lib.upr_texture_edge_density_f32.restype = i32
     lib.upr_texture_edge_density_f32.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.upr_smooth_loss_workspace_bytes.restype = sz
+    lib.upr_smooth_loss_workspace_bytes.argtypes = [i32] * 3
+    lib.upr_edge_smooth_loss_f32.restype = i32
+    lib.upr_edge_smooth_loss_f32.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp, sz, vp]
     lib.upr_peer_stats_buffer_bytes.restype = sz
     lib.upr_texture_weight_peer_f32.restype = i32
     lib.upr_texture_weight_peer_f32.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, i32, i32, C.c_uint, f32, vp, vp]
@@ -537,6 +541,30 @@ def texture_complexity(x: torch.Tensor, method: str = "tv", want_batch_stats: bo
         check(fn(x.data_ptr(), b, c, h, w, out.data_ptr(), stats.data_ptr() if stats is not None else None,
                  ws.data_ptr(), ws.numel(), _stream()), f"upr_texture_{method}_f32")
     return (out, stats) if want_batch_stats else out
+
+
+def edge_smooth_loss(illu: torch.Tensor, img_low: torch.Tensor, lambda_val: float = 10.0, alpha: float = 1.0, want_grad: bool = True):
+    """EdgeAwareSmoothnessLoss.forward (losses/loss.py:136-176) and its gradient w.r.t. illu in three launches
+    (upr_edge_smooth_loss_f32).  illu [B,Ci,H,W], img_low [B,Cs,H,W] f32 CUDA -> (loss3 [3] = loss, horizontal, vertical terms;
+    d loss / d illu or None)."""
+    illu = _require_cuda_f32(illu, "illu")
+    img_low = _require_cuda_f32(img_low, "img_low")
+    if illu.dim() != 4 or img_low.dim() != 4 or illu.shape[0] != img_low.shape[0] or illu.shape[2:] != img_low.shape[2:]:
+        raise ValueError(f"illu {tuple(illu.shape)} and img_low {tuple(img_low.shape)} must be [B,C,H,W] with equal B, H, W")
+    b, ci, h, w = illu.shape
+    cs = img_low.shape[1]
+    loss3 = torch.empty((3,), dtype=torch.float32, device=illu.device)
+    grad = torch.empty_like(illu) if want_grad else None
+    L = lib()
+    with torch.cuda.device(illu.device):
+        nbytes = L.upr_smooth_loss_workspace_bytes(b, h, w)
+        if nbytes == 0:
+            raise UprError(-2, "upr_smooth_loss_workspace_bytes")
+        ws = workspace(nbytes, illu.device)
+        check(L.upr_edge_smooth_loss_f32(illu.data_ptr(), img_low.data_ptr(), b, ci, cs, h, w, float(lambda_val), float(alpha),
+                                         loss3.data_ptr(), grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(),
+                                         _stream()), "upr_edge_smooth_loss_f32")
+    return loss3, grad
 
 
 def texture_weight_peer(x: torch.Tensor, method: str, weight_smooth: float, peer_table: Optional[torch.Tensor], rank: int,

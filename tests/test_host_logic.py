@@ -82,6 +82,15 @@ def test_hot_path_ops_refuse_cpu_tensors():
                native.texture_complexity):
         with pytest.raises(RuntimeError):
             fn(x)
+    with pytest.raises(RuntimeError):
+        native.clahe_lab_u8(torch.zeros((1, 16, 16, 3), dtype=torch.uint8))
+    with pytest.raises(RuntimeError):
+        native.clahe_lab_f32_u8(x)
+    with pytest.raises(RuntimeError):
+        native.edge_smooth_loss(torch.rand(1, 1, 16, 16), x)
+    from retinex_image_enhancement_b200.losses.loss import EdgeAwareSmoothnessLoss
+    with pytest.raises(RuntimeError):
+        EdgeAwareSmoothnessLoss()(torch.rand(1, 1, 16, 16), x)
 
 
 # ---- world_size 2 over gloo: the batch statistics of the dynamic smoothness weight -------------------

@@ -6,11 +6,14 @@ Two independent anchors:
     exhaustive 2^24 sweeps for RGB->Lab, Lab->RGB, RGB->Gray and CLAHE on ragged shapes.
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
 
 from oracle import oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 cv2 = pytest.importorskip("cv2")
 
@@ -228,3 +231,24 @@ def test_letterbox_ref_is_the_reference_function():
         got, ratio, pad = cv2_chain.letterbox_ref(x, new_shape, auto=True, scaleup=scaleup)
         exp, ratio2, pad2 = ref.letterbox_tensor(torch.from_numpy(x), new_shape=new_shape, auto=True, scaleup=scaleup)
         assert np.array_equal(got, exp.numpy()) and ratio == ratio2 and tuple(pad) == tuple(pad2)
+
+
+# ---- smoothness term against the unmodified reference ----------------------------------------------
+def _smooth_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_smooth", os.path.join(GOLDEN_DIR, "make_golden_smooth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.smooth_cases
+
+
+def test_golden_smooth_loss():
+    """oracle.edge_smooth_loss == losses/loss.py EdgeAwareSmoothnessLoss + torch autograd (tests/golden/make_golden_smooth.py)."""
+    smooth_cases = _smooth_cases()
+    gold = np.load(os.path.join(GOLDEN_DIR, "smooth_loss.npz"))
+    for name, illu, img, lam, alpha in smooth_cases():
+        loss, _lh, _lv, grad = O.edge_smooth_loss(illu, img, lam, alpha)
+        assert abs(float(loss) - float(gold[f"{name}_loss"])) <= 2e-6 * abs(float(gold[f"{name}_loss"])), name
+        g = gold[f"{name}_grad"]
+        assert np.abs(grad - g).max() <= 1e-6 * np.abs(g).max() + 1e-12, name
+        assert np.array_equal(grad == 0, g == 0), name      # sign(0) = 0 on plateaus
