@@ -78,7 +78,8 @@ def test_autograd_drop_in_matches_stock_formulation(native):
     assert not mod(illu, img).requires_grad
     s = img.clone().requires_grad_(True)
     mod(illu, s).backward()
-    assert s.grad is not None and s.grad.abs().sum() > 0
+    # (the reference's formulation itself yields NaN there wherever the Sobel response is exactly zero: d sqrt(0))
+    assert s.grad is not None and torch.nan_to_num(s.grad).abs().sum() > 0
 
 
 def test_argument_errors(native):
