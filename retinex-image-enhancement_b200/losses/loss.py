@@ -161,3 +161,39 @@ class EdgeAwareSmoothnessLoss(torch.nn.Module):
         fh = 1 + self.alpha * F.avg_pool2d(edge, kernel_size=(1, wh.shape[3]), stride=1)[:, :, :, :-1]
         fv = 1 + self.alpha * F.avg_pool2d(edge, kernel_size=(wv.shape[2], 1), stride=1)[:, :, :-1, :]
         return torch.mean(wh * fh * torch.abs(gh(illu_map))) + torch.mean(wv * fv * torch.abs(gv(illu_map)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# The reference's TotalLoss (losses/loss.py:607-760) with the hot-path pieces swapped in
+# ---------------------------------------------------------------------------------------------------
+def accelerate_reference_total_loss(total_loss, group=None):
+    """Route the pieces of an instance of the REFERENCE ``TotalLoss`` that this package implements through the kernels, in
+    place, and return it.  The constructor, ``forward(img_low, img_enhanced, illu_map, reflectance=None, epoch=0)`` and the
+    ``(total, dict)`` result stay the reference's own:
+
+      * ``smoothness_loss`` (losses/loss.py:623, called at :673) becomes ``EdgeAwareSmoothnessLoss`` above with the same
+        ``lambda_val`` / ``alpha`` (loss and gradient from ``upr_edge_smooth_loss_f32``);
+      * ``calculate_texture_complexity`` as seen by ``TotalLoss.forward`` (:707) becomes the kernel version; under data
+        parallelism (torch.distributed initialised, world > 1) it returns the ALL-RANK batch mean in every element, so that
+        ``torch.mean`` at :710 -- and hence the weight of :716-717 -- is the single-process value on every rank (one
+        all-reduce of two floats).
+
+    The other six terms (exposure, colour, spatial, decoupling, perceptual, frequency) are the reference's own modules."""
+    import sys
+
+    old = total_loss.smoothness_loss
+    total_loss.smoothness_loss = EdgeAwareSmoothnessLoss(getattr(old, "lambda_val", 10.0), getattr(old, "alpha", 1.0))
+
+    def complexity_for_batch_mean(img, method="tv"):
+        per_image, stats = batch_texture_stats(img, method)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            all_reduce_batch_stats(stats, group)
+            return (stats[0] / stats[1]).expand(per_image.shape[0])
+        return per_image
+
+    mod = sys.modules.get(type(total_loss).__module__)
+    if mod is not None and hasattr(mod, "calculate_texture_complexity"):
+        mod.calculate_texture_complexity = complexity_for_batch_mean
+    total_loss._upr_complexity = complexity_for_batch_mean
+    return total_loss

@@ -126,3 +126,27 @@ def test_dp_batch_stats_world2_gloo(tmp_path):
     r0, r1 = np.load(tmp_path / "w0.npy"), np.load(tmp_path / "w1.npy")
     assert np.array_equal(r0, r1)                                # every rank derives the same weight
     assert r0[2] == 8.0 and abs(r0[0] - ref) <= 1e-6
+
+
+def test_accelerate_reference_total_loss_patches_the_real_class(monkeypatch):
+    """With the reference tree at hand (build container only): the names accelerate_reference_total_loss relies on exist in
+    the unmodified losses/loss.py -- TotalLoss().smoothness_loss and the module-level calculate_texture_complexity."""
+    ref = os.environ.get("UPR_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "losses")):
+        pytest.skip("reference tree not present")
+    import importlib.util
+    import sys
+    import types
+    monkeypatch.setitem(sys.modules, "matplotlib", types.ModuleType("matplotlib"))
+    spec = importlib.util.spec_from_file_location("upr_ref_losses", os.path.join(ref, "losses", "loss.py"))
+    mod = importlib.util.module_from_spec(spec)
+    monkeypatch.setitem(sys.modules, "upr_ref_losses", mod)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(mod, "PerceptualLoss", lambda *a, **k: torch.nn.Identity())      # the real one downloads VGG19
+    total = mod.TotalLoss()
+    lam, alpha = total.smoothness_loss.lambda_val, total.smoothness_loss.alpha
+    from retinex_image_enhancement_b200.losses import loss as L
+    out = L.accelerate_reference_total_loss(total)
+    assert out is total and isinstance(total.smoothness_loss, L.EdgeAwareSmoothnessLoss)
+    assert (total.smoothness_loss.lambda_val, total.smoothness_loss.alpha) == (lam, alpha)
+    assert mod.calculate_texture_complexity is total._upr_complexity

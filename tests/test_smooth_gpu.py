@@ -89,3 +89,45 @@ def test_argument_errors(native):
         native.edge_smooth_loss(torch.zeros((1, 1, 8, 8), device="cuda"), torch.zeros((1, 3, 8, 9), device="cuda"))
     with pytest.raises(native.UprError):
         native.edge_smooth_loss(torch.zeros((1, 1, 1, 8), device="cuda"), torch.zeros((1, 3, 1, 8), device="cuda"))   # h < 2
+
+
+def test_accelerate_reference_total_loss_stand_in(native):
+    """accelerate_reference_total_loss on a stand-in that looks up the same names as losses/loss.py:673 and :707-717."""
+    import sys
+    import types
+    from retinex_image_enhancement_b200.losses import loss as L
+
+    mod = types.ModuleType("fake_reference_losses")
+    mod.calculate_texture_complexity = lambda img, method="tv": (_ for _ in ()).throw(AssertionError("stock path used"))
+
+    class Smooth(torch.nn.Module):
+        lambda_val, alpha = 6.0, 0.5
+
+        def forward(self, illu, img):
+            raise AssertionError("stock smoothness used")
+
+    def forward(self, img_low, illu_map):
+        loss_smooth = self.smoothness_loss(illu_map, img_low)
+        c = mod.calculate_texture_complexity(img_low, method=self.texture_method)      # module-global lookup, like :707
+        w = torch.clamp(self.weight_smooth * (1.0 - torch.mean(c) * 0.8), 0.1, 5.0)
+        return w * loss_smooth, w
+
+    Total = type("TotalLoss", (torch.nn.Module,), {"forward": forward, "__module__": mod.__name__})
+    sys.modules[mod.__name__] = mod
+    try:
+        t = Total()
+        t.smoothness_loss, t.texture_method, t.weight_smooth = Smooth(), "tv", 1.0
+        t = L.accelerate_reference_total_loss(t)
+        rng = np.random.default_rng(8)
+        img = rng.random((4, 3, 64, 96), dtype=np.float32)
+        illu = rng.random((4, 1, 64, 96), dtype=np.float32)
+        it = torch.from_numpy(illu).cuda().requires_grad_(True)
+        total, w = t(torch.from_numpy(img).cuda(), it)
+        total.backward()
+        want_w = O.dynamic_smooth_weight(O.texture_tv(img), 1.0)
+        want_loss, _h, _v, want_grad = O.edge_smooth_loss(illu, img, 6.0, 0.5)
+        assert abs(float(w) - want_w) <= 1e-6
+        assert abs(float(total) - want_w * float(want_loss)) <= 5e-6 * abs(want_w * float(want_loss))
+        assert np.abs(it.grad.cpu().numpy() - want_w * want_grad).max() <= 2e-6 * np.abs(want_w * want_grad).max()
+    finally:
+        del sys.modules[mod.__name__]
