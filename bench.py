@@ -479,6 +479,29 @@ def bench_c4(torch, dist, rank, world, local, args):
 
         theirs = statistics.median(event_time_ms(torch, stock, 20)) * 1e3
         smooth = {"us_per_step": ours, "us_per_step_torch_ops_same_gpu": theirs, "api": "upr_edge_smooth_loss_f32 (loss + d loss / d illu)"}
+        # exposure + colour + spatial-consistency losses of the enhanced image, forward + backward of their weighted sum
+        import torch.nn.functional as F
+        enh = torch.rand((b, 3, h, w), device=dev, generator=torch.Generator(device=dev).manual_seed(31 + rank))
+        fused = L.EnhancedImageLosses()
+        t_exp, t_col, t_spa = fused.exposure(), fused.color(), fused.spatial()
+
+        def ours3():
+            a = enh.detach().requires_grad_(True)
+            (10.0 * t_exp(a, x) + 5.0 * t_col(a) + 1.0 * t_spa(a, x)).backward()
+
+        def stock3():
+            a = enh.detach().requires_grad_(True)
+            gm = torch.mean(torch.mean(x, dim=1, keepdim=True))
+            l_exp = torch.mean(torch.abs(F.avg_pool2d(torch.mean(a, dim=1, keepdim=True), 16, 16) - (0.6 + 0.2 * (1 - gm))))
+            mr, mg, mb = (torch.mean(a[:, k]) for k in range(3))
+            l_col = (mr - mg) ** 2 + (mr - mb) ** 2 + (mg - mb) ** 2
+            dh = (a[..., :-1] - a[..., 1:]) - (x[..., :-1] - x[..., 1:])
+            dv = (a[..., :-1, :] - a[..., 1:, :]) - (x[..., :-1, :] - x[..., 1:, :])
+            (10.0 * l_exp + 5.0 * l_col + 1.0 * (torch.mean(dh ** 2) + torch.mean(dv ** 2))).backward()
+
+        smooth["enhanced_image_losses"] = {"us_per_step": statistics.median(event_time_ms(torch, ours3, 20)) * 1e3,
+                                           "us_per_step_torch_ops_same_gpu": statistics.median(event_time_ms(torch, stock3, 20)) * 1e3,
+                                           "api": "upr_enh_losses_f32 + upr_enh_losses_grad_f32 through torch.autograd (exposure + colour + spatial)"}
     except Exception as e:  # pragma: no cover
         smooth = {"error": repr(e)}
     k_tv = statistics.mean(event_time_ms(torch, lambda: native.texture_complexity(x, "tv"), 20))

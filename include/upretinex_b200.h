@@ -192,6 +192,19 @@ UPR_API int upr_dynamic_smooth_weight_f32(const float* batch_stats2, float weigh
  * illu: [n][ci][h][w], img_low: [n][cs][h][w] f32.  loss3[0..2] = {loss, horizontal term, vertical term} (device).
  * grad_illu (nullable): d loss / d illu, same shape as illu (sign(0) = 0 like torch.abs).  img_low gets no gradient.
  * Everything derived from img_low is a no-grad image statistic.  Deterministic (ordered fp64 sums).  h, w >= 2. */
+/* The three statistics losses of the enhanced image from ONE read of (enhanced, img_low), both [n][3][h][w] f32:
+ *   losses3[0] = AdaptiveExposureLoss(enhanced, img_low)   (losses/loss.py:29-58; patch = 16, base_target = 0.6 there)
+ *   losses3[1] = ColorLoss(enhanced)                        (:351-368)
+ *   losses3[2] = SpatialConsistencyLoss(enhanced, img_low)  (:404-427)
+ * `saved` (upr_enh_losses_saved_floats floats, device) keeps the channel means, the adaptive target, the scales and the
+ * patch means for the backward entry, which writes  upstream3[0] d exp + upstream3[1] d col + upstream3[2] d spa  w.r.t.
+ * `enhanced` in one pass (upstream3: three device floats).  img_low gets no gradient.  h, w >= patch. */
+UPR_API size_t upr_enh_losses_workspace_bytes(int n);
+UPR_API size_t upr_enh_losses_saved_floats(int n, int h, int w, int patch);
+UPR_API int upr_enh_losses_f32(const float* enhanced, const float* img_low, int n, int h, int w, double base_target, int patch,
+                               float* losses3, float* saved, void* workspace, size_t workspace_bytes, upr_stream_t stream);
+UPR_API int upr_enh_losses_grad_f32(const float* enhanced, const float* img_low, int n, int h, int w, int patch,
+                                    const float* saved, const float* upstream3, float* grad_enhanced, upr_stream_t stream);
 UPR_API size_t upr_smooth_loss_workspace_bytes(int n, int h, int w);
 UPR_API int upr_edge_smooth_loss_f32(const float* illu, const float* img_low, int n, int ci, int cs, int h, int w,
                                      float lambda_val, float alpha, float* loss3, float* grad_illu,

@@ -298,6 +298,46 @@ def edge_smooth_loss(illu, img_low, lambda_val=10.0, alpha=1.0):
     return f32(loss_h + loss_v), loss_h, loss_v, grad
 
 
+def enhanced_image_losses(enhanced, img_low, base_target=0.6, patch=16):
+    """AdaptiveExposureLoss (losses/loss.py:29-58), ColorLoss (:351-368), SpatialConsistencyLoss (:404-427) and their gradients
+    w.r.t. the enhanced image, restated in NumPy.  [B,3,H,W] each -> ((exp, col, spa), (g_exp, g_col, g_spa))."""
+    R = np.ascontiguousarray(enhanced, np.float32)
+    S = np.ascontiguousarray(img_low, np.float32)
+    b, c, h, w = R.shape
+    f32 = np.float32
+    # exposure
+    gray_r = R.mean(axis=1, dtype=np.float32)                                     # [B,H,W]
+    gmean = f32(S.mean(axis=1, dtype=np.float32).mean(dtype=np.float64))
+    target = f32(base_target) + f32(0.8 - base_target) * (f32(1) - gmean)
+    hp, wp = h // patch, w // patch
+    pm = gray_r[:, : hp * patch, : wp * patch].reshape(b, hp, patch, wp, patch).mean(axis=(2, 4), dtype=np.float64).astype(np.float32)
+    l_exp = f32(np.abs(pm - target).mean(dtype=np.float64))
+    g_exp = np.zeros_like(R)
+    sg = (np.sign(pm - target) * f32(1.0 / (pm.size * patch * patch * c))).astype(np.float32)
+    g_exp[:, :, : hp * patch, : wp * patch] = np.repeat(np.repeat(sg, patch, axis=1), patch, axis=2)[:, None]
+    # colour
+    m = R.mean(axis=(0, 2, 3), dtype=np.float64).astype(np.float32)
+    drg, drb, dgb = m[0] - m[1], m[0] - m[2], m[1] - m[2]
+    l_col = f32(drg * drg + drb * drb + dgb * dgb)
+    g_col = np.zeros_like(R)
+    npix = f32(1.0 / (b * h * w))
+    g_col[:, 0] = f32(2) * (drg + drb) * npix
+    g_col[:, 1] = f32(2) * (dgb - drg) * npix
+    g_col[:, 2] = f32(-2) * (drb + dgb) * npix
+    # spatial consistency
+    dh = (R[..., :-1] - R[..., 1:]) - (S[..., :-1] - S[..., 1:])
+    dv = (R[..., :-1, :] - R[..., 1:, :]) - (S[..., :-1, :] - S[..., 1:, :])
+    l_spa = f32(f32((dh * dh).mean(dtype=np.float64)) + f32((dv * dv).mean(dtype=np.float64)))
+    g_spa = np.zeros_like(R)
+    gh_ = dh * f32(2.0 / dh.size)
+    gv_ = dv * f32(2.0 / dv.size)
+    g_spa[..., :-1] += gh_
+    g_spa[..., 1:] -= gh_
+    g_spa[..., :-1, :] += gv_
+    g_spa[..., 1:, :] -= gv_
+    return (l_exp, l_col, l_spa), (g_exp, g_col, g_spa)
+
+
 # --------------------------------------------------------------------------- #
 # Deterministic KAT inputs (SURVEY.md section 8c)
 # --------------------------------------------------------------------------- #

@@ -438,6 +438,160 @@ k_smooth_loss(const float* __restrict__ illu, const float* __restrict__ s_img, i
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// N3, second part: the three statistics losses of the ENHANCED image in one read of (enhanced, low):
+//   exposure  (AdaptiveExposureLoss, losses/loss.py:29-58):  mean |avg_pool16(mean_c R) - E|,  E = base + (0.8 - base)(1 - mean(mean_c S))
+//   colour    (ColorLoss, :351-368):                         (mr-mg)^2 + (mr-mb)^2 + (mg-mb)^2 of the batch channel means of R
+//   spatial   (SpatialConsistencyLoss, :404-427):            mean((dx R - dx S)^2) + mean((dy R - dy S)^2)
+// Forward: one pass for the sums, one warp per 16x16 patch for the patch means, a one-CTA finish.  Backward: one pass that
+// forms  u_exp * d exp + u_col * d col + u_spa * d spa  per pixel from the saved statistics (u = upstream gradients).
+// saved[0..7] = {mr, mg, mb, mean(gray S), E, dx residual scale 2/Nh, dy residual scale 2/Nv, 1/(M*P*P*3)}, then the patch means.
+// -----------------------------------------------------------------------------------------
+constexpr int kEnhSums = 6;   // sum R, sum G, sum B (enhanced), sum of mean_c S, sum (dx R - dx S)^2, sum (dy R - dy S)^2
+
+__global__ void __launch_bounds__(kStThreads)
+k_enh_sums(const float* __restrict__ enh, const float* __restrict__ low, int n, int h, int w, double* __restrict__ partial,
+           unsigned* __restrict__ tickets, float base_target, float target_coef, int hp, int wp, int patch, float* __restrict__ saved,
+           float* __restrict__ losses3)
+{
+    __shared__ double s_red[kStThreads / 32];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    const int f = blockIdx.y, parts = gridDim.x;
+    const long long plane = (long long)h * w;
+    const float* e = enh + (long long)f * 3 * plane;
+    const float* l = low + (long long)f * 3 * plane;
+    double acc[kEnhSums] = {0, 0, 0, 0, 0, 0};
+    const long long stride = (long long)parts * kStThreads;
+    for (long long p = (long long)blockIdx.x * kStThreads + tid; p < plane; p += stride) {
+        const int y = int(p / w), x = int(p - (long long)y * w);
+        const bool has_r = x + 1 < w, has_d = y + 1 < h;
+        float lsum = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float ev = __ldg(e + c * plane + p), lv = __ldg(l + c * plane + p);
+            acc[c] += double(ev);
+            lsum = __fadd_rn(lsum, lv);
+            if (has_r) {
+                const float d = __fsub_rn(__fsub_rn(ev, __ldg(e + c * plane + p + 1)), __fsub_rn(lv, __ldg(l + c * plane + p + 1)));
+                acc[4] += double(__fmul_rn(d, d));
+            }
+            if (has_d) {
+                const float d = __fsub_rn(__fsub_rn(ev, __ldg(e + c * plane + p + w)), __fsub_rn(lv, __ldg(l + c * plane + p + w)));
+                acc[5] += double(__fmul_rn(d, d));
+            }
+        }
+        acc[3] += double(__fdiv_rn(lsum, 3.0f));
+    }
+#pragma unroll
+    for (int k = 0; k < kEnhSums; ++k) {
+        const double t = block_sum(acc[k], s_red);
+        if (tid == 0) partial[((long long)f * parts + blockIdx.x) * kEnhSums + k] = t;
+    }
+    if (!last_cta_of(tickets + f, parts, &s_flag)) return;
+    if (tid == 0) {
+        double tot[kEnhSums] = {0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < parts; ++q)
+            for (int k = 0; k < kEnhSums; ++k) tot[k] += __ldcg(&partial[((long long)f * parts + q) * kEnhSums + k]);
+        for (int k = 0; k < kEnhSums; ++k) partial[(long long)f * parts * kEnhSums + k] = tot[k];
+        __threadfence();
+        unsigned* batch_ticket = tickets + n;
+        if (atomicAdd(batch_ticket, 1u) != unsigned(n - 1)) return;
+        *batch_ticket = 0;
+        __threadfence();
+        double all[kEnhSums] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < kEnhSums; ++k) all[k] += __ldcg(&partial[(long long)i * parts * kEnhSums + k]);
+        const double npix = double(n) * h * w;
+        const float mr = float(all[0] / npix), mg = float(all[1] / npix), mb = float(all[2] / npix);
+        const float gmean = float(all[3] / npix);
+        // base + (0.8 - base) * (1 - mean): the coefficient is formed in double on the host, as Python does at loss.py:47
+        const float target = __fadd_rn(base_target, __fmul_rn(target_coef, __fsub_rn(1.0f, gmean)));
+        const double nh = double(n) * 3 * h * (w - 1), nv = double(n) * 3 * (h - 1) * w;
+        const float drg = __fsub_rn(mr, mg), drb = __fsub_rn(mr, mb), dgb = __fsub_rn(mg, mb);
+        saved[0] = mr; saved[1] = mg; saved[2] = mb; saved[3] = gmean; saved[4] = target;
+        saved[5] = float(2.0 / nh); saved[6] = float(2.0 / nv);
+        saved[7] = float(1.0 / (double(n) * hp * wp * patch * patch * 3));
+        losses3[1] = __fadd_rn(__fadd_rn(__fmul_rn(drg, drg), __fmul_rn(drb, drb)), __fmul_rn(dgb, dgb));
+        losses3[2] = __fadd_rn(float(all[4] / nh), float(all[5] / nv));
+    }
+}
+
+// one warp per patch: pm = avg_pool(mean_c R)
+__global__ void __launch_bounds__(kStThreads)
+k_enh_patch_means(const float* __restrict__ enh, int h, int w, int hp, int wp, int patch, float* __restrict__ pm)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long k = (long long)blockIdx.x * (kStThreads / 32) + wid;      // patch index inside the frame
+    const int f = blockIdx.y;
+    if (k >= (long long)hp * wp) return;
+    const int py = int(k / wp), px = int(k - (long long)py * wp);
+    const long long plane = (long long)h * w;
+    const float* e = enh + (long long)f * 3 * plane + (long long)py * patch * w + px * patch;
+    double acc = 0.0;
+    for (int i = lane; i < patch * patch; i += 32) {
+        const int yy = i / patch, xx = i - yy * patch;
+        const long long o = (long long)yy * w + xx;
+        const float g = __fdiv_rn(__fadd_rn(__fadd_rn(__ldg(e + o), __ldg(e + plane + o)), __ldg(e + 2 * plane + o)), 3.0f);
+        acc += double(g);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) pm[(long long)f * hp * wp + k] = float(acc / double(patch * patch));
+}
+
+__global__ void __launch_bounds__(kStThreads)
+k_enh_exposure_finish(const float* __restrict__ pm, long long m, const float* __restrict__ saved, float* __restrict__ losses3)
+{
+    __shared__ double s_red[kStThreads / 32];
+    const float target = __ldcg(saved + 4);
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < m; i += kStThreads) acc += double(fabsf(__fsub_rn(__ldg(pm + i), target)));
+    acc = block_sum(acc, s_red);
+    if (threadIdx.x == 0) losses3[0] = float(acc / double(m));
+}
+
+__global__ void __launch_bounds__(kStThreads)
+k_enh_grad(const float* __restrict__ enh, const float* __restrict__ low, int h, int w, int hp, int wp, int patch,
+           const float* __restrict__ saved, const float* __restrict__ pm, const float* __restrict__ upstream3, float* __restrict__ grad)
+{
+    const int f = blockIdx.y;
+    const long long plane = (long long)h * w;
+    const float* e = enh + (long long)f * 3 * plane;
+    const float* l = low + (long long)f * 3 * plane;
+    float* g = grad + (long long)f * 3 * plane;
+    const float u_exp = __ldg(upstream3 + 0), u_col = __ldg(upstream3 + 1), u_spa = __ldg(upstream3 + 2);
+    const float mr = __ldg(saved + 0), mg = __ldg(saved + 1), mb = __ldg(saved + 2), target = __ldg(saved + 4);
+    const float sh = __ldg(saved + 5), sv = __ldg(saved + 6), se = __ldg(saved + 7);
+    const float inv_npix = float(1.0 / (double(gridDim.y) * h * w));
+    const float drg = __fsub_rn(mr, mg), drb = __fsub_rn(mr, mb), dgb = __fsub_rn(mg, mb);
+    // d colour / d mean_c, spread over the pixels of the channel
+    const float gc[3] = {__fmul_rn(__fmul_rn(2.0f, __fadd_rn(drg, drb)), inv_npix),
+                         __fmul_rn(__fmul_rn(2.0f, __fsub_rn(dgb, drg)), inv_npix),
+                         __fmul_rn(__fmul_rn(-2.0f, __fadd_rn(drb, dgb)), inv_npix)};
+    const long long stride = (long long)gridDim.x * kStThreads;
+    for (long long p = (long long)blockIdx.x * kStThreads + threadIdx.x; p < plane; p += stride) {
+        const int y = int(p / w), x = int(p - (long long)y * w);
+        const bool has_r = x + 1 < w, has_l = x > 0, has_d = y + 1 < h, has_u = y > 0;
+        float ge = 0.0f;
+        if (y < hp * patch && x < wp * patch) {
+            const float d = __fsub_rn(__ldg(pm + (long long)f * hp * wp + (long long)(y / patch) * wp + x / patch), target);
+            ge = __fmul_rn(d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f), se);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* ec = e + c * plane;
+            const float* lc = l + c * plane;
+            const float ev = __ldg(ec + p), lv = __ldg(lc + p);
+            float gs = 0.0f;
+            if (has_r) gs = __fadd_rn(gs, __fmul_rn(sh, __fsub_rn(__fsub_rn(ev, __ldg(ec + p + 1)), __fsub_rn(lv, __ldg(lc + p + 1)))));
+            if (has_l) gs = __fsub_rn(gs, __fmul_rn(sh, __fsub_rn(__fsub_rn(__ldg(ec + p - 1), ev), __fsub_rn(__ldg(lc + p - 1), lv))));
+            if (has_d) gs = __fadd_rn(gs, __fmul_rn(sv, __fsub_rn(__fsub_rn(ev, __ldg(ec + p + w)), __fsub_rn(lv, __ldg(lc + p + w)))));
+            if (has_u) gs = __fsub_rn(gs, __fmul_rn(sv, __fsub_rn(__fsub_rn(__ldg(ec + p - w), ev), __fsub_rn(__ldg(lc + p - w), lv))));
+            g[c * plane + p] = __fadd_rn(__fadd_rn(__fmul_rn(u_exp, ge), __fmul_rn(u_col, gc[c])), __fmul_rn(u_spa, gs));
+        }
+    }
+}
+
 __global__ void k_dynamic_weight(const float* __restrict__ stats2, float w0, float* __restrict__ out)
 {
     out[0] = dyn_weight(stats2[0], stats2[1], w0);
@@ -587,6 +741,58 @@ int upr_edge_smooth_loss_f32(const float* illu, const float* img_low, int n, int
     const int parts = tex_parts(n, (long long)h * w);
     k_smooth_loss<<<dim3(parts, n), kStThreads, 0, s>>>(illu, img_low, n, ci, cs, h, w, lambda_val, alpha, rowmean, colmean, grad_illu,
                                                          partial, tickets, loss3);
+    UPR_LAUNCH_CHECK();
+    return UPR_OK;
+}
+
+size_t upr_enh_losses_workspace_bytes(int n)
+{
+    if (n < 0) return 0;
+    const size_t nn = size_t(std::max(n, 1));
+    return upr::align_up(nn * 1024 * upr::kEnhSums * sizeof(double), 256) + upr::align_up((nn + 1) * sizeof(unsigned), 256);
+}
+
+size_t upr_enh_losses_saved_floats(int n, int h, int w, int patch)
+{
+    if (n < 0 || patch <= 0 || h < patch || w < patch) return 0;
+    return 8 + size_t(std::max(n, 1)) * (h / patch) * (w / patch);
+}
+
+int upr_enh_losses_f32(const float* enhanced, const float* img_low, int n, int h, int w, double base_target, int patch, float* losses3,
+                       float* saved, void* workspace, size_t workspace_bytes, upr_stream_t stream)
+{
+    using namespace upr;
+    if (n <= 0 || n > 65535 || patch <= 0 || h < patch || w < patch || h < 2 || w < 2) return UPR_E_SHAPE;
+    if (!enhanced || !img_low || !losses3 || !saved || !workspace) return UPR_E_NULL;
+    if (workspace_bytes < upr_enh_losses_workspace_bytes(n) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return UPR_E_WORKSPACE;
+    auto s = static_cast<cudaStream_t>(stream);
+    auto* base = static_cast<unsigned char*>(workspace);
+    auto* partial = reinterpret_cast<double*>(base);
+    auto* tickets = reinterpret_cast<unsigned*>(base + align_up(size_t(n) * 1024 * kEnhSums * sizeof(double), 256));
+    UPR_CUDA_TRY(cudaMemsetAsync(tickets, 0, (size_t(n) + 1) * sizeof(unsigned), s));
+    const int hp = h / patch, wp = w / patch;
+    const int parts = tex_parts(n, (long long)h * w);
+    k_enh_sums<<<dim3(parts, n), kStThreads, 0, s>>>(enhanced, img_low, n, h, w, partial, tickets, float(base_target), float(0.8 - base_target),
+                                                     hp, wp, patch, saved, losses3);
+    UPR_LAUNCH_CHECK();
+    const long long per = (long long)hp * wp;
+    const int wpc = kStThreads / 32;
+    k_enh_patch_means<<<dim3(unsigned((per + wpc - 1) / wpc), n), kStThreads, 0, s>>>(enhanced, h, w, hp, wp, patch, saved + 8);
+    UPR_LAUNCH_CHECK();
+    k_enh_exposure_finish<<<1, kStThreads, 0, s>>>(saved + 8, per * n, saved, losses3);
+    UPR_LAUNCH_CHECK();
+    return UPR_OK;
+}
+
+int upr_enh_losses_grad_f32(const float* enhanced, const float* img_low, int n, int h, int w, int patch, const float* saved,
+                            const float* upstream3, float* grad_enhanced, upr_stream_t stream)
+{
+    using namespace upr;
+    if (n <= 0 || n > 65535 || patch <= 0 || h < patch || w < patch || h < 2 || w < 2) return UPR_E_SHAPE;
+    if (!enhanced || !img_low || !saved || !upstream3 || !grad_enhanced) return UPR_E_NULL;
+    const int parts = tex_parts(n, (long long)h * w);
+    k_enh_grad<<<dim3(parts, n), kStThreads, 0, static_cast<cudaStream_t>(stream)>>>(enhanced, img_low, h, w, h / patch, w / patch, patch, saved,
+                                                                                     saved + 8, upstream3, grad_enhanced);
     UPR_LAUNCH_CHECK();
     return UPR_OK;
 }

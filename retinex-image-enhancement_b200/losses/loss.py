@@ -164,6 +164,69 @@ class EdgeAwareSmoothnessLoss(torch.nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------------
+# exposure / colour / spatial-consistency losses of the enhanced image from one read of (enhanced, low)
+# ---------------------------------------------------------------------------------------------------
+class _EnhLossesFn(torch.autograd.Function):
+    """(loss_exp, loss_col, loss_spa) = the three statistics losses of losses/loss.py:29-58, :351-368, :404-427.  Only
+    ``img_enhanced`` carries a gradient; backward is ONE pass that combines the three upstream gradients."""
+
+    @staticmethod
+    def forward(ctx, img_enhanced, img_low, base_target, patch):
+        e, l = img_enhanced.detach().contiguous(), img_low.detach().contiguous()
+        losses, saved = native.enhanced_image_losses(e, l, base_target, patch)
+        ctx.save_for_backward(e, l, saved)
+        ctx.patch = patch
+        return losses[0].clone(), losses[1].clone(), losses[2].clone()
+
+    @staticmethod
+    def backward(ctx, g_exp, g_col, g_spa):
+        e, l, saved = ctx.saved_tensors
+        zero = torch.zeros((), dtype=torch.float32, device=e.device)
+        up = torch.stack([g if g is not None else zero for g in (g_exp, g_col, g_spa)]).to(torch.float32)
+        return native.enhanced_image_losses_grad(e, l, saved, up, ctx.patch), None, None, None
+
+
+class EnhancedImageLosses:
+    """The three modules ``TotalLoss`` calls on the enhanced image (losses/loss.py:672, :674, :675) share one evaluation: the
+    first of ``exposure`` / ``color`` / ``spatial`` that sees a new ``img_enhanced`` runs the fused kernels, the other two
+    read the same result (keyed on the tensor objects and the version counter of ``img_enhanced``)."""
+
+    def __init__(self, patch_size: int = 16, base_target_exposure: float = 0.6):
+        self.patch_size, self.base_target_exposure = patch_size, base_target_exposure
+        self._key, self._val, self._low = None, None, None
+
+    def evaluate(self, img_enhanced, img_low=None):
+        if img_low is None:
+            img_low = self._low if self._low is not None and self._low.shape == img_enhanced.shape else img_enhanced
+        key = (id(img_enhanced), img_enhanced._version, id(img_low), img_low._version)
+        if key != self._key:
+            self._val = _EnhLossesFn.apply(img_enhanced, img_low, float(self.base_target_exposure), int(self.patch_size))
+            self._key, self._low = key, img_low
+        return self._val
+
+    class _Term(torch.nn.Module):
+        def __init__(self, owner, index, takes_low):
+            super().__init__()
+            self._owner, self._index, self._takes_low = [owner], index, takes_low   # list: keep the owner out of nn.Module's registry
+
+        def forward(self, img_enhanced, img_low=None):
+            return self._owner[0].evaluate(img_enhanced, img_low)[self._index]
+
+    def exposure(self):
+        """Drop-in for AdaptiveExposureLoss: forward(img_enhanced, img_low)."""
+        return self._Term(self, 0, True)
+
+    def color(self):
+        """Drop-in for ColorLoss: forward(img_enhanced) -- reuses the evaluation of the same tensor (TotalLoss calls the
+        exposure term first, loss.py:672-674); called on its own it pairs the image with itself, which the colour term ignores."""
+        return self._Term(self, 1, False)
+
+    def spatial(self):
+        """Drop-in for SpatialConsistencyLoss: forward(img_enhanced, img_low)."""
+        return self._Term(self, 2, True)
+
+
+# ---------------------------------------------------------------------------------------------------
 # The reference's TotalLoss (losses/loss.py:607-760) with the hot-path pieces swapped in
 # ---------------------------------------------------------------------------------------------------
 def accelerate_reference_total_loss(total_loss, group=None):
@@ -173,16 +236,22 @@ def accelerate_reference_total_loss(total_loss, group=None):
 
       * ``smoothness_loss`` (losses/loss.py:623, called at :673) becomes ``EdgeAwareSmoothnessLoss`` above with the same
         ``lambda_val`` / ``alpha`` (loss and gradient from ``upr_edge_smooth_loss_f32``);
+      * ``exposure_loss``, ``color_loss`` and ``spatial_loss`` (:622-625, called at :672-675) become the three views of ONE
+        fused evaluation (``EnhancedImageLosses``: ``upr_enh_losses_f32`` forward, ``upr_enh_losses_grad_f32`` backward);
       * ``calculate_texture_complexity`` as seen by ``TotalLoss.forward`` (:707) becomes the kernel version; under data
         parallelism (torch.distributed initialised, world > 1) it returns the ALL-RANK batch mean in every element, so that
         ``torch.mean`` at :710 -- and hence the weight of :716-717 -- is the single-process value on every rank (one
         all-reduce of two floats).
 
-    The other six terms (exposure, colour, spatial, decoupling, perceptual, frequency) are the reference's own modules."""
+    The remaining terms (decoupling, perceptual, frequency) are the reference's own modules."""
     import sys
 
     old = total_loss.smoothness_loss
     total_loss.smoothness_loss = EdgeAwareSmoothnessLoss(getattr(old, "lambda_val", 10.0), getattr(old, "alpha", 1.0))
+    if all(hasattr(total_loss, a) for a in ("exposure_loss", "color_loss", "spatial_loss")):
+        ex = total_loss.exposure_loss
+        fused = EnhancedImageLosses(getattr(ex, "patch_size", 16), getattr(ex, "base_target_exposure", 0.6))
+        total_loss.exposure_loss, total_loss.color_loss, total_loss.spatial_loss = fused.exposure(), fused.color(), fused.spatial()
 
     def complexity_for_batch_mean(img, method="tv"):
         per_image, stats = batch_texture_stats(img, method)

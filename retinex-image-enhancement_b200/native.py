@@ -93,6 +93,14 @@ def _declare(lib):
     lib.upr_texture_tv_f32.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     lib.upr_texture_edge_density_f32.restype = i32
     lib.upr_texture_edge_density_f32.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.upr_enh_losses_workspace_bytes.restype = sz
+    lib.upr_enh_losses_workspace_bytes.argtypes = [i32]
+    lib.upr_enh_losses_saved_floats.restype = sz
+    lib.upr_enh_losses_saved_floats.argtypes = [i32] * 4
+    lib.upr_enh_losses_f32.restype = i32
+    lib.upr_enh_losses_f32.argtypes = [vp, vp, i32, i32, i32, f64, i32, vp, vp, vp, sz, vp]
+    lib.upr_enh_losses_grad_f32.restype = i32
+    lib.upr_enh_losses_grad_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.upr_smooth_loss_workspace_bytes.restype = sz
     lib.upr_smooth_loss_workspace_bytes.argtypes = [i32] * 3
     lib.upr_edge_smooth_loss_f32.restype = i32
@@ -541,6 +549,41 @@ def texture_complexity(x: torch.Tensor, method: str = "tv", want_batch_stats: bo
         check(fn(x.data_ptr(), b, c, h, w, out.data_ptr(), stats.data_ptr() if stats is not None else None,
                  ws.data_ptr(), ws.numel(), _stream()), f"upr_texture_{method}_f32")
     return (out, stats) if want_batch_stats else out
+
+
+def enhanced_image_losses(enhanced: torch.Tensor, img_low: torch.Tensor, base_target: float = 0.6, patch: int = 16):
+    """(exposure, colour, spatial-consistency) losses of losses/loss.py:29-58, :351-368, :404-427 from one read of the two
+    images (upr_enh_losses_f32).  [B,3,H,W] f32 CUDA each -> (losses [3], saved statistics for enhanced_image_losses_grad)."""
+    enhanced = _require_cuda_f32(enhanced, "enhanced")
+    img_low = _require_cuda_f32(img_low, "img_low")
+    if enhanced.dim() != 4 or enhanced.shape[1] != 3 or enhanced.shape != img_low.shape:
+        raise ValueError(f"enhanced {tuple(enhanced.shape)} and img_low {tuple(img_low.shape)} must both be [B,3,H,W]")
+    b, _, h, w = enhanced.shape
+    L = lib()
+    nsaved = L.upr_enh_losses_saved_floats(b, h, w, int(patch))
+    if nsaved == 0:
+        raise UprError(-2, "upr_enh_losses_saved_floats")
+    losses = torch.empty((3,), dtype=torch.float32, device=enhanced.device)
+    saved = torch.empty((nsaved,), dtype=torch.float32, device=enhanced.device)
+    with torch.cuda.device(enhanced.device):
+        ws = workspace(L.upr_enh_losses_workspace_bytes(b), enhanced.device)
+        check(L.upr_enh_losses_f32(enhanced.data_ptr(), img_low.data_ptr(), b, h, w, float(base_target), int(patch), losses.data_ptr(),
+                                   saved.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "upr_enh_losses_f32")
+    return losses, saved
+
+
+def enhanced_image_losses_grad(enhanced: torch.Tensor, img_low: torch.Tensor, saved: torch.Tensor, upstream3: torch.Tensor,
+                               patch: int = 16) -> torch.Tensor:
+    """sum_k upstream3[k] * d loss_k / d enhanced in one pass (upr_enh_losses_grad_f32); upstream3: 3 f32 on the device."""
+    enhanced = _require_cuda_f32(enhanced, "enhanced")
+    img_low = _require_cuda_f32(img_low, "img_low")
+    upstream3 = _require_cuda_f32(upstream3, "upstream3")
+    b, _, h, w = enhanced.shape
+    grad = torch.empty_like(enhanced)
+    with torch.cuda.device(enhanced.device):
+        check(lib().upr_enh_losses_grad_f32(enhanced.data_ptr(), img_low.data_ptr(), b, h, w, int(patch), saved.data_ptr(),
+                                            upstream3.data_ptr(), grad.data_ptr(), _stream()), "upr_enh_losses_grad_f32")
+    return grad
 
 
 def edge_smooth_loss(illu: torch.Tensor, img_low: torch.Tensor, lambda_val: float = 10.0, alpha: float = 1.0, want_grad: bool = True):

@@ -5,9 +5,10 @@ Run in the build container only (needs /root/reference):
 
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_smooth.py
 
-Executes losses/loss.py EdgeAwareSmoothnessLoss.forward (:136-176) and torch autograd through it on seeded inputs and
-stores the loss values and d loss / d illu_map in tests/golden/smooth_loss.npz (committed).  Inputs are re-created from
-the seeds by smooth_cases() below, which the tests import.
+Executes losses/loss.py EdgeAwareSmoothnessLoss.forward (:136-176), AdaptiveExposureLoss (:29-58), ColorLoss (:351-368) and
+SpatialConsistencyLoss (:404-427) with torch autograd on seeded inputs and stores the loss values and the gradients w.r.t.
+illu_map / img_enhanced in tests/golden/smooth_loss.npz (committed).  Inputs are re-created from the seeds by smooth_cases()
+and enh_cases() below, which the tests import.
 """
 import os
 import sys
@@ -33,13 +34,26 @@ def smooth_cases():
     return out
 
 
+def enh_cases():
+    """(name, enhanced [B,3,H,W], img_low [B,3,H,W]) -- deterministic."""
+    out = []
+    rng = np.random.default_rng(81)
+    out.append(("e1", rng.random((2, 3, 48, 64), dtype=np.float32), rng.random((2, 3, 48, 64), dtype=np.float32) * np.float32(0.3)))
+    rng = np.random.default_rng(82)    # ragged: 37 x 53 -> 2 x 3 patches, border pixels outside every patch
+    out.append(("e2", rng.random((3, 3, 37, 53), dtype=np.float32) * np.float32(0.8), rng.random((3, 3, 37, 53), dtype=np.float32)))
+    rng = np.random.default_rng(83)    # one patch
+    out.append(("e3", rng.random((1, 3, 16, 16), dtype=np.float32), rng.random((1, 3, 16, 16), dtype=np.float32)))
+    return out
+
+
 def main():
     import torch
     ref = os.environ.get("UPR_REFERENCE", "/root/reference")
     sys.dont_write_bytecode = True
     sys.path.insert(0, ref)
     sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
-    from losses.loss import EdgeAwareSmoothnessLoss  # noqa: E402  (reference)
+    from losses.loss import (AdaptiveExposureLoss, ColorLoss, EdgeAwareSmoothnessLoss,  # noqa: E402  (reference)
+                             SpatialConsistencyLoss)
     torch.set_num_threads(1)
     store = {}
     for name, illu, img, lam, alpha in smooth_cases():
@@ -50,6 +64,16 @@ def main():
         store[f"{name}_loss"] = np.float32(loss.item())
         store[f"{name}_grad"] = it.grad.numpy().astype(np.float32)
         print(name, illu.shape, img.shape, float(loss))
+    for name, enh, low in enh_cases():
+        lt = torch.from_numpy(low)
+        for tag, fn in (("exp", lambda e: AdaptiveExposureLoss()(e, lt)), ("col", lambda e: ColorLoss()(e)),
+                        ("spa", lambda e: SpatialConsistencyLoss()(e, lt))):
+            et = torch.from_numpy(enh).clone().requires_grad_(True)
+            loss = fn(et)
+            loss.backward()
+            store[f"{name}_{tag}_loss"] = np.float32(loss.item())
+            store[f"{name}_{tag}_grad"] = et.grad.numpy().astype(np.float32)
+            print(name, tag, float(loss.item()))
     np.savez_compressed(os.path.join(HERE, "smooth_loss.npz"), **store)
 
 

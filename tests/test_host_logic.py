@@ -88,9 +88,13 @@ def test_hot_path_ops_refuse_cpu_tensors():
         native.clahe_lab_f32_u8(x)
     with pytest.raises(RuntimeError):
         native.edge_smooth_loss(torch.rand(1, 1, 16, 16), x)
-    from retinex_image_enhancement_b200.losses.loss import EdgeAwareSmoothnessLoss
+    from retinex_image_enhancement_b200.losses.loss import EdgeAwareSmoothnessLoss, EnhancedImageLosses
     with pytest.raises(RuntimeError):
         EdgeAwareSmoothnessLoss()(torch.rand(1, 1, 16, 16), x)
+    with pytest.raises(RuntimeError):
+        native.enhanced_image_losses(x, x)
+    with pytest.raises(RuntimeError):
+        EnhancedImageLosses().exposure()(x, x)
 
 
 # ---- world_size 2 over gloo: the batch statistics of the dynamic smoothness weight -------------------
@@ -150,3 +154,7 @@ def test_accelerate_reference_total_loss_patches_the_real_class(monkeypatch):
     assert out is total and isinstance(total.smoothness_loss, L.EdgeAwareSmoothnessLoss)
     assert (total.smoothness_loss.lambda_val, total.smoothness_loss.alpha) == (lam, alpha)
     assert mod.calculate_texture_complexity is total._upr_complexity
+    # the three statistics losses of the enhanced image are views of one fused evaluation
+    assert type(total.exposure_loss).__name__ == type(total.color_loss).__name__ == type(total.spatial_loss).__name__ == "_Term"
+    assert total.exposure_loss._owner[0] is total.color_loss._owner[0] is total.spatial_loss._owner[0]
+    assert (total.exposure_loss._owner[0].patch_size, total.exposure_loss._owner[0].base_target_exposure) == (16, 0.6)

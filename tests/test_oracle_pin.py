@@ -252,3 +252,22 @@ def test_golden_smooth_loss():
         g = gold[f"{name}_grad"]
         assert np.abs(grad - g).max() <= 1e-6 * np.abs(g).max() + 1e-12, name
         assert np.array_equal(grad == 0, g == 0), name      # sign(0) = 0 on plateaus
+
+
+def test_golden_enhanced_image_losses():
+    """oracle.enhanced_image_losses == AdaptiveExposureLoss / ColorLoss / SpatialConsistencyLoss of the unmodified reference
+    and torch autograd through them (tests/golden/make_golden_smooth.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_smooth", os.path.join(GOLDEN_DIR, "make_golden_smooth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(GOLDEN_DIR, "smooth_loss.npz"))
+    for name, enh, low in mod.enh_cases():
+        losses, grads = O.enhanced_image_losses(enh, low)
+        for k, tag in enumerate(("exp", "col", "spa")):
+            want, g = float(gold[f"{name}_{tag}_loss"]), gold[f"{name}_{tag}_grad"]
+            # the colour term squares differences of nearly equal channel means (|d| ~ 5e-3 of means ~ 0.5): the reference's
+            # own fp32 torch.mean rounds those means at 1e-7 relative, i.e. d at ~1e-5 relative -- hence the wider band
+            rtol = 2e-4 if tag == "col" else 1e-5
+            assert abs(float(losses[k]) - want) <= rtol * abs(want), (name, tag, float(losses[k]), want)
+            assert np.abs(grads[k] - g).max() <= rtol * np.abs(g).max() + 1e-12, (name, tag)

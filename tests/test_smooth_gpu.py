@@ -131,3 +131,93 @@ def test_accelerate_reference_total_loss_stand_in(native):
         assert np.abs(it.grad.cpu().numpy() - want_w * want_grad).max() <= 2e-6 * np.abs(want_w * want_grad).max()
     finally:
         del sys.modules[mod.__name__]
+
+
+# ---- exposure / colour / spatial-consistency losses of the enhanced image (one fused evaluation) ---------------------
+def _enh_cases():
+    spec = importlib.util.spec_from_file_location("make_golden_smooth", os.path.join(GOLDEN_DIR, "make_golden_smooth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.enh_cases()
+
+
+def _unit(k):
+    u = torch.zeros(3, device="cuda")
+    u[k] = 1.0
+    return u
+
+
+def test_enhanced_losses_golden_reference_vectors(native):
+    """Loss values and per-term gradients against AdaptiveExposureLoss / ColorLoss / SpatialConsistencyLoss of the unmodified
+    reference (colour: 2e-4 relative, limited by the reference's own fp32 channel means; the others 1e-5)."""
+    gold = np.load(os.path.join(GOLDEN_DIR, "smooth_loss.npz"))
+    for name, enh, low in _enh_cases():
+        e, l = torch.from_numpy(enh).cuda(), torch.from_numpy(low).cuda()
+        losses, saved = native.enhanced_image_losses(e, l)
+        for k, tag in enumerate(("exp", "col", "spa")):
+            rtol = 2e-4 if tag == "col" else 1e-5
+            want, g = float(gold[f"{name}_{tag}_loss"]), gold[f"{name}_{tag}_grad"]
+            assert abs(float(losses[k]) - want) <= rtol * abs(want), (name, tag)
+            got = native.enhanced_image_losses_grad(e, l, saved, _unit(k)).cpu().numpy()
+            assert np.abs(got - g).max() <= rtol * np.abs(g).max() + 1e-12, (name, tag)
+
+
+@pytest.mark.parametrize("b,h,w", [(8, 256, 256), (2, 640, 640), (3, 97, 131), (1, 16, 2048)])
+def test_enhanced_losses_against_oracle(native, b, h, w):
+    rng = np.random.default_rng(b * 7 + h)
+    enh = rng.random((b, 3, h, w), dtype=np.float32)
+    low = rng.random((b, 3, h, w), dtype=np.float32) * np.float32(0.4)
+    (l_exp, l_col, l_spa), grads = O.enhanced_image_losses(enh, low)
+    e, l = torch.from_numpy(enh).cuda(), torch.from_numpy(low).cuda()
+    losses, saved = native.enhanced_image_losses(e, l)
+    for k, want in enumerate((l_exp, l_col, l_spa)):
+        assert abs(float(losses[k]) - float(want)) <= 2e-6 * abs(float(want)) + 1e-12
+        got = native.enhanced_image_losses_grad(e, l, saved, _unit(k)).cpu().numpy()
+        assert np.abs(got - grads[k]).max() <= 2e-6 * np.abs(grads[k]).max() + 1e-12
+    # a weighted combination in one pass
+    up = torch.tensor([0.7, 2.5, 1.3], device="cuda")
+    got = native.enhanced_image_losses_grad(e, l, saved, up).cpu().numpy()
+    want = np.float32(0.7) * grads[0] + np.float32(2.5) * grads[1] + np.float32(1.3) * grads[2]
+    assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
+def test_enhanced_losses_autograd_and_total_loss_views(native):
+    """EnhancedImageLosses: the three drop-in modules share one evaluation; autograd through a weighted sum equals the stock
+    torch formulation of the three losses."""
+    import torch.nn.functional as F
+    from retinex_image_enhancement_b200.losses.loss import EnhancedImageLosses
+    g = torch.Generator(device="cuda").manual_seed(9)
+    enh = torch.rand((4, 3, 96, 128), device="cuda", generator=g)
+    low = torch.rand((4, 3, 96, 128), device="cuda", generator=g) * 0.3
+
+    def stock(e):
+        gm = torch.mean(torch.mean(low, dim=1, keepdim=True))
+        target = 0.6 + (0.8 - 0.6) * (1 - gm)
+        l_exp = torch.mean(torch.abs(F.avg_pool2d(torch.mean(e, dim=1, keepdim=True), 16, 16) - target))
+        mr, mg, mb = (torch.mean(e[:, c]) for c in range(3))
+        l_col = (mr - mg) ** 2 + (mr - mb) ** 2 + (mg - mb) ** 2
+        dh = (e[..., :-1] - e[..., 1:]) - (low[..., :-1] - low[..., 1:])
+        dv = (e[..., :-1, :] - e[..., 1:, :]) - (low[..., :-1, :] - low[..., 1:, :])
+        return l_exp, l_col, torch.mean(dh ** 2) + torch.mean(dv ** 2)
+
+    fused = EnhancedImageLosses()
+    exposure, color, spatial = fused.exposure(), fused.color(), fused.spatial()
+    a = enh.clone().requires_grad_(True)
+    le, lc, ls = exposure(a, low), color(a), spatial(a, low)          # the order TotalLoss.forward uses (loss.py:672-675)
+    assert fused._val is not None and le is fused._val[0] and lc is fused._val[1] and ls is fused._val[2]   # one evaluation
+    (10.0 * le + 5.0 * lc + 1.0 * ls).backward()
+    b = enh.clone().requires_grad_(True)
+    se, sc, ss = stock(b)
+    (10.0 * se + 5.0 * sc + 1.0 * ss).backward()
+    for got, want, rtol in ((le, se, 1e-5), (lc, sc, 2e-4), (ls, ss, 1e-5)):
+        assert abs(float(got) - float(want)) <= rtol * abs(float(want))
+    assert (a.grad - b.grad).abs().max() <= 2e-5 * b.grad.abs().max()
+    # a new tensor (or an in-place update) triggers a new evaluation
+    first = fused._val
+    a2 = enh.clone().requires_grad_(True)
+    exposure(a2, low)
+    assert fused._val is not first
+    with pytest.raises(ValueError):
+        native.enhanced_image_losses(torch.zeros((1, 1, 32, 32), device="cuda"), torch.zeros((1, 1, 32, 32), device="cuda"))
+    with pytest.raises(native.UprError):
+        native.enhanced_image_losses(torch.zeros((1, 3, 8, 32), device="cuda"), torch.zeros((1, 3, 8, 32), device="cuda"))
