@@ -193,16 +193,23 @@ class EnhancedImageLosses:
 
     def __init__(self, patch_size: int = 16, base_target_exposure: float = 0.6):
         self.patch_size, self.base_target_exposure = patch_size, base_target_exposure
-        self._key, self._val, self._low = None, None, None
+        self._enh, self._low, self._versions, self._val = None, None, None, None
 
     def evaluate(self, img_enhanced, img_low=None):
+        # the cache keeps the two tensor OBJECTS alive and compares by identity + version counter (an id() alone could be
+        # re-used by the next iteration's tensor once this one is freed)
+        same_enh = self._enh is img_enhanced
         if img_low is None:
-            img_low = self._low if self._low is not None and self._low.shape == img_enhanced.shape else img_enhanced
-        key = (id(img_enhanced), img_enhanced._version, id(img_low), img_low._version)
-        if key != self._key:
+            img_low = self._low if (same_enh and self._low is not None) else img_enhanced
+        hit = same_enh and self._low is img_low and self._versions == (img_enhanced._version, img_low._version)
+        if not hit:
             self._val = _EnhLossesFn.apply(img_enhanced, img_low, float(self.base_target_exposure), int(self.patch_size))
-            self._key, self._low = key, img_low
+            self._enh, self._low, self._versions = img_enhanced, img_low, (img_enhanced._version, img_low._version)
         return self._val
+
+    def clear(self):
+        """Drop the cached evaluation (and the references to its tensors and autograd graph)."""
+        self._enh, self._low, self._versions, self._val = None, None, None, None
 
     class _Term(torch.nn.Module):
         def __init__(self, owner, index, takes_low):

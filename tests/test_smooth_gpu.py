@@ -212,11 +212,17 @@ def test_enhanced_losses_autograd_and_total_loss_views(native):
     for got, want, rtol in ((le, se, 1e-5), (lc, sc, 2e-4), (ls, ss, 1e-5)):
         assert abs(float(got) - float(want)) <= rtol * abs(float(want))
     assert (a.grad - b.grad).abs().max() <= 2e-5 * b.grad.abs().max()
-    # a new tensor (or an in-place update) triggers a new evaluation
+    # a new tensor or an in-place update triggers a new evaluation; ColorLoss alone after that pairs with the same input image
     first = fused._val
     a2 = enh.clone().requires_grad_(True)
     exposure(a2, low)
-    assert fused._val is not first
+    second = fused._val
+    assert second is not first and color(a2) is second[1]
+    with torch.no_grad():
+        low.mul_(0.5)
+    assert spatial(a2, low) is not second[2]
+    fused.clear()
+    assert fused._val is None and fused._enh is None
     with pytest.raises(ValueError):
         native.enhanced_image_losses(torch.zeros((1, 1, 32, 32), device="cuda"), torch.zeros((1, 1, 32, 32), device="cuda"))
     with pytest.raises(native.UprError):
