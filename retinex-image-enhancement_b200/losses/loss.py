@@ -116,14 +116,16 @@ class _EdgeSmoothFn(torch.autograd.Function):
     also writes d loss / d illu (the weights and edge factors are no-grad statistics of img_low), so backward is one scale."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)   # the reference trainer runs the criterion under autocast
     def forward(ctx, illu_map, img_low, lambda_val, alpha):
-        need = illu_map.requires_grad
+        need = ctx.needs_input_grad[0]   # (not illu_map.requires_grad: under autocast illu_map is the fp32 copy made by custom_fwd)
         loss3, grad = native.edge_smooth_loss(illu_map.detach(), img_low.detach(), lambda_val, alpha, want_grad=need)
         ctx.save_for_backward(grad if need else torch.empty(0, device=illu_map.device))
         ctx.has_grad = need
         return loss3[0].clone()
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_out):
         (g,) = ctx.saved_tensors
         return (g * grad_out if ctx.has_grad else None), None, None, None
@@ -171,6 +173,7 @@ class _EnhLossesFn(torch.autograd.Function):
     ``img_enhanced`` carries a gradient; backward is ONE pass that combines the three upstream gradients."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)   # trainers/train.py:72 calls the criterion under autocast
     def forward(ctx, img_enhanced, img_low, base_target, patch):
         e, l = img_enhanced.detach().contiguous(), img_low.detach().contiguous()
         losses, saved = native.enhanced_image_losses(e, l, base_target, patch)
@@ -179,6 +182,7 @@ class _EnhLossesFn(torch.autograd.Function):
         return losses[0].clone(), losses[1].clone(), losses[2].clone()
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g_exp, g_col, g_spa):
         e, l, saved = ctx.saved_tensors
         zero = torch.zeros((), dtype=torch.float32, device=e.device)

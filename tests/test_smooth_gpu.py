@@ -227,3 +227,23 @@ def test_enhanced_losses_autograd_and_total_loss_views(native):
         native.enhanced_image_losses(torch.zeros((1, 1, 32, 32), device="cuda"), torch.zeros((1, 1, 32, 32), device="cuda"))
     with pytest.raises(native.UprError):
         native.enhanced_image_losses(torch.zeros((1, 3, 8, 32), device="cuda"), torch.zeros((1, 3, 8, 32), device="cuda"))
+
+
+def test_loss_terms_under_autocast_with_half_inputs(native):
+    """trainers/train.py:72-77 evaluates the criterion under torch.autocast: the CNN's outputs arrive as fp16.  The autograd
+    functions cast to fp32 on entry (custom_fwd), the gradients come back in the inputs' dtype."""
+    from retinex_image_enhancement_b200.losses.loss import EdgeAwareSmoothnessLoss, EnhancedImageLosses
+    g = torch.Generator(device="cuda").manual_seed(3)
+    low = torch.rand((2, 3, 64, 64), device="cuda", generator=g)
+    enh16 = torch.rand((2, 3, 64, 64), device="cuda", generator=g).half().requires_grad_(True)
+    illu16 = torch.rand((2, 1, 64, 64), device="cuda", generator=g).half().requires_grad_(True)
+    fused = EnhancedImageLosses()
+    with torch.autocast("cuda"):
+        total = EdgeAwareSmoothnessLoss()(illu16, low) + fused.exposure()(enh16, low) + fused.color()(enh16) + fused.spatial()(enh16, low)
+    total.backward()
+    assert total.dtype == torch.float32 and enh16.grad.dtype == torch.float16 and illu16.grad.dtype == torch.float16
+    want, _h, _v, gi = O.edge_smooth_loss(illu16.detach().float().cpu().numpy(), low.cpu().numpy())
+    (le, lc, ls), ge = O.enhanced_image_losses(enh16.detach().float().cpu().numpy(), low.cpu().numpy())
+    assert abs(float(total) - float(want + le + lc + ls)) <= 1e-5 * float(want + le + lc + ls)
+    assert np.abs(illu16.grad.float().cpu().numpy() - gi).max() <= 2e-3 * np.abs(gi).max()          # fp16 rounding of the result
+    assert np.abs(enh16.grad.float().cpu().numpy() - (ge[0] + ge[1] + ge[2])).max() <= 2e-3 * np.abs(ge[0] + ge[1] + ge[2]).max()
