@@ -2,9 +2,11 @@
 """Experiment: does running the histogram kernel (K1, L1/shared data pipe bound) of chunk i+1 concurrently with the map
 kernel (K3, issue bound) of chunk i beat running the two back to back?  Two streams, the K3 stream at high priority.
 
-    UPR_K3_CTAS=148 python scripts/overlap_bench.py --chunks 4
+    python scripts/overlap_bench.py --chunks 4
 
-Prints one JSON line: sequential op time vs. pipelined time on the same 64 x 1080p batch.
+Prints one JSON line: sequential op time vs. pipelined time on the same 64 x 1080p batch.  Result (profiles/r3_clahe.md): the
+pipelined schedule is slower (0.96-1.15 ms against 0.83 ms), also with the map kernel limited to one CTA per SM through a
+development switch (UPR_K3_CTAS, since removed from the library; the variable is ignored now).
 """
 import argparse
 import json
