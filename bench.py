@@ -299,8 +299,9 @@ def bench_c2(torch, dist, rank, world, local, args):
     value = world * px / 1e6 / (ms_step / 1e3)
 
     # per-kernel durations, live, CUDA events on the launching stream (profiling hook of the C ABI)
-    k1 = statistics.mean(event_time_ms(torch, lambda: native.clahe_lab(x, out=out, stage_mask=1), max(5, args.steps // 2)))
-    k3 = statistics.mean(event_time_ms(torch, lambda: native.clahe_lab(x, out=out, stage_mask=2), max(5, args.steps // 2)))
+    with ClockSampler(local) as clk_legs:
+        k1 = statistics.mean(event_time_ms(torch, lambda: native.clahe_lab(x, out=out, stage_mask=1), max(5, args.steps // 2)))
+        k3 = statistics.mean(event_time_ms(torch, lambda: native.clahe_lab(x, out=out, stage_mask=2), max(5, args.steps // 2)))
     peak, peak_src = measured_peak()
     # algorithmic bytes of each kernel: K1 reads the f32 frame (12 B/px); K3 writes the f32 frame (12 B/px);
     # the 3 B/px u8 Lab intermediate between them is NOT algorithmic (it is what `traffic` exposes)
@@ -311,7 +312,7 @@ def bench_c2(torch, dist, rank, world, local, args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": args.traffic if args.traffic is not None else committed_traffic(dom_name), "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "kernels_ms": {"k_hist_lab_vec3": k1, "k_map_vec5": k3},
+                "kernels_ms": {"k_hist_lab_vec3": k1, "k_map_vec5": k3}, "kernel_legs_clocks": clk_legs.summary(),
                 "op": {"algorithmic_bytes_per_px": 24, "achieved": op_achieved, "frac": op_achieved / peak,
                        "frac_of_nominal_8000": op_achieved / 8000.0}}
 

@@ -594,7 +594,7 @@ k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t
     // (every byte read once), and with only one item of register prefetch the loads were exposed to the full DRAM
     // latency (experiment: the kernel without its global loads ran in 0.26 ms instead of 0.44 ms).  Plain per-thread
     // prefetch.global.L2 measured faster than cp.async.bulk.prefetch.L2 per row segment (0.402 vs 0.414 ms).
-    constexpr int kPfAhead = 6;
+    constexpr int kPfAhead = 3;   // (was 6 until the sweep recorded at k_hist_lab_vec3: fused Retinex + CLAHE 1.30 -> 1.21 ms)
     int cpf = c;
     const char* ppf = pin;
     int ipf = tid;
@@ -778,7 +778,9 @@ k_hist_lab_vec3(const void* __restrict__ in, uint8_t* __restrict__ lab, int32_t*
     const uint32_t w4 = uint32_t(g.w) >> 2;
     const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;      // fast path: 3 * plane < 2^32
     const uint32_t step = uint32_t(rpi) * w4;
-    constexpr int kPf = 6;                          // L2 prefetch distance in iterations
+    // L2 prefetch distance in iterations (of rpi rows).  Swept on 64 x 1080p (rpi = 4): 1 -> 0.473 ms, 2 and 3 -> 0.381 ms,
+    // 4 -> 0.385, 6 -> 0.394, 8 -> 0.402, 14 -> 0.430, 20 -> 0.459; 16 x 4K (rpi = 2) is flat between 3 and 6
+    constexpr int kPf = 3;
     const uint32_t pfo = uint32_t(kPf) * step;
     const uint32_t tid4 = uint32_t(tid) * 4u;
 
