@@ -379,6 +379,17 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
             const bool inner = q >= q0 && q < q1;    // their statistics belong to this segment
             const bool prev_in = q > q0;             // rows 4q-1 / 2q-1 / q-1 belong to this segment
             float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;   // this step's contribution to the three scale totals
+            {   // L2 prefetch of the four rows of the NEXT step, all three channels (swept on 16 x 4K: none 0.400 ms, one step ahead
+                // 0.363, two 0.367, three 0.379, four 0.420, six 0.480); the register loads above run one (step, channel) ahead
+                const int qp = q + 1;
+                if (qp <= q1 && qp < Q) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(img + c * plane + (long long)(4 * qp + j) * w));
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float wsum = c == 0 ? 1.299f : (c == 1 ? 1.587f : 1.114f);   // 1 + luma weight

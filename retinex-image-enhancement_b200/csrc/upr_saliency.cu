@@ -233,6 +233,14 @@ k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_
 #pragma unroll
             for (int i = 0; i < 8; ++i) { r[i] = nr[i]; g[i] = ng[i]; b[i] = nb[i]; }
             if (k + 1 < r1 + 8) load_row(k + 1);
+            // L2 prefetch two rows ahead (row k+1 is already in registers).  Swept on 16 x 4K, saliency op: none 0.923 ms, 2 rows
+            // 0.847, 3 rows 0.850, 4 rows 0.859, 6 rows 0.904, 8 rows 0.967, 12 rows 1.025
+            if (vec && k + 2 < r1 + 8) {
+                const float* rp = img + (long long)reflect101_s(k + 2, h) * w + c0;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + plane));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 2 * plane));
+            }
             uint32_t m = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) m = __vimax3_u32(m, __float_as_uint(r[i]), __vimax3_u32(__float_as_uint(g[i]), __float_as_uint(b[i]), 0u));
