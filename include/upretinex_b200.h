@@ -75,9 +75,6 @@ UPR_API int upr_clahe_lab_u8(const unsigned char* in_nhwc_rgb, unsigned char* ou
 UPR_API int upr_clahe_lab_f32_u8(const float* in_nchw, unsigned char* out_nhwc_rgb, int n, int h, int w,
                                  double clip_limit, int tiles_x, int tiles_y,
                                  void* workspace, size_t workspace_bytes, upr_stream_t stream);
-/* Profiling hook: runs only the selected stages of upr_clahe_lab_f32 on a workspace that a full call has
- * already populated.  stage_mask bit 0 = K1 (quantise + Lab + tile histograms + clip/LUT), bit 1 = K3
- * (bilinear LUT map + Lab->RGB); bench.py uses it to time each kernel with CUDA events. */
 /* The enhance path after the CNN in one call: enhanced = R*e + (1-R)*e^2 with R = x/(illu+eps)
  * (models/model.py:405-413, :442) followed by apply_clahe_enhancement(enhanced) (adaptive_params.py:195,
  * :121-169).  x, e: [n][3][h][w]; illu: [n][1][h][w]; out: [n][3][h][w].  The recombined frame is formed in the
@@ -87,7 +84,17 @@ UPR_API int upr_clahe_lab_f32_u8(const float* in_nchw, unsigned char* out_nhwc_r
 UPR_API int upr_retinex_clahe_f32(const float* x_nchw, const float* illu_n1hw, const float* e_nchw, float* out_nchw,
                                   int n, int h, int w, float eps, double clip_limit, int tiles_x, int tiles_y,
                                   void* workspace, size_t workspace_bytes, upr_stream_t stream);
-
+/* Same, writing the packed u8 RGB (HWC) frame that save_image (enhancers/simple_enhance.py:65-100) would store: what the
+ * batch driver sends back over PCIe (3 instead of 12 bytes per pixel).  Bit-identical to upr_retinex_clahe_f32 followed by
+ * the truncating cast.  Ragged shapes (no vector path) need `enhanced_scratch`, an f32 [n][3][h][w] frame for the
+ * recombination; with a NULL scratch they return UPR_E_WORKSPACE. */
+UPR_API int upr_retinex_clahe_f32_u8(const float* x_nchw, const float* illu_n1hw, const float* e_nchw,
+                                     unsigned char* out_nhwc_rgb, float* enhanced_scratch, int n, int h, int w, float eps,
+                                     double clip_limit, int tiles_x, int tiles_y, void* workspace, size_t workspace_bytes,
+                                     upr_stream_t stream);
+/* Profiling hook: runs only the selected stages of upr_clahe_lab_f32 on a workspace that a full call has
+ * already populated.  stage_mask bit 0 = K1 (quantise + Lab + tile histograms + clip/LUT), bit 1 = K3
+ * (bilinear LUT map + Lab->RGB); bench.py uses it to time each kernel with CUDA events. */
 UPR_API int upr_clahe_lab_stages_f32(const float* in_nchw, float* out_nchw, int n, int h, int w, double clip_limit,
                                      int tiles_x, int tiles_y, void* workspace, size_t workspace_bytes, int stage_mask,
                                      upr_stream_t stream);
@@ -158,6 +165,11 @@ UPR_API int upr_attention_apply_f32(const float* enh, const float* att_n1hw, flo
  * upr_attention_f32 followed by upr_attention_apply_f32. */
 UPR_API int upr_content_aware_apply_f32(const float* x_nchw, const float* enh_nchw, float* out_nchw, float* att_n1hw, int n,
                                         int h, int w, void* workspace, size_t workspace_bytes, upr_stream_t stream);
+
+/* The quantiser of save_image (enhancers/simple_enhance.py:65-100), on the device: [n][c][h][w] f32 -> [n][h][w][c] u8 with
+ * (clip(x, 0, 1) * 255).astype(uint8) -- fp32 product, truncation; c = 1 (illumination maps) or 3 (frames).  What the batch
+ * driver sends back over PCIe instead of f32 planes (1 resp. 3 instead of 4 resp. 12 bytes per pixel). */
+UPR_API int upr_quantize_u8_f32(const float* x_nchw, unsigned char* out_nhwc, int n, int c, int h, int w, upr_stream_t stream);
 
 /* ---- a8: Retinex decomposition / recombination ------------------------------------------
  * models/model.py:405-413 (R = x / (illu + eps), illu broadcast over the 3 channels) and :442

@@ -14,14 +14,14 @@
 //                        that surround a cell are interleaved into one 32-bit word per grey level, so the bilinear
 //                        LUT interpolation costs ONE shared-memory lookup per pixel; fused with Lab -> sRGB (integer
 //                        path) and the /255 de-quantisation.
-//   (k_hist_lab_vec / k_map_vec are the first generations, k_hist_lab_vec2 the second one -- also the body of the fused
-//    Retinex prologue -- kept behind UPR_CLAHE_VARIANT for A/B timing;
-//    k_*_generic handle ragged shapes incl. OpenCV's padding quirk.)
+//   (k_*_generic handle ragged shapes incl. OpenCV's padding quirk; the retired kernel generations and what each change
+//    bought are recorded in profiles/r2_clahe.md and profiles/r3_clahe.md.)
 //
 // All fixed-point recipes follow SURVEY.md Appendix A (pinned against the cv2 binary by the
 // oracle tests).  fp32 products/sums of the interpolation use __fmul_rn/__fadd_rn so that ptxas
 // cannot contract them into FMAs: OpenCV evaluates them separately rounded (SURVEY finding 9).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -231,114 +231,9 @@ __device__ __forceinline__ bool publish_hist(int& total, int32_t* __restrict__ h
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1 fast path: W % tiles_x == 0, H % tiles_y == 0, tile width % 4 == 0, 16-byte aligned planes
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kK1Threads, 3)
-k_hist_lab_vec(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
-               uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
-    uint16_t* s_gamma = reinterpret_cast<uint16_t*>(smem + 256 * kK1Threads);      // 256
-    uint16_t* s_cbrt = s_gamma + UPR_TAB_GAMMA_LEN;                                // 2048
-    __shared__ int s_tmp[8];
-    __shared__ int s_flag;
-
-    const int tid = threadIdx.x;
-    const int strip = blockIdx.x % g.nstrips;
-    const int tile = blockIdx.x / g.nstrips;
-    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-    const int f = blockIdx.y;
-    const int ntiles = g.tiles_x * g.tiles_y;
-
-    {
-        uint4* z = reinterpret_cast<uint4*>(s_cnt);
-#pragma unroll
-        for (int i = 0; i < 256 * kK1Threads / 16 / kK1Threads; ++i) z[tid + i * kK1Threads] = make_uint4(0, 0, 0, 0);
-        s_gamma[tid] = d_gamma[tid];
-        reinterpret_cast<uint4*>(s_cbrt)[tid] = reinterpret_cast<const uint4*>(d_cbrt)[tid];  // 256 x 16 B = 4 KB
-    }
-    __syncthreads();
-
-    const int row0 = ty * g.th + strip * g.strip_rows;
-    const int row1 = min(row0 + g.strip_rows, (ty + 1) * g.th);
-    const int tw4 = g.tw >> 2;
-    const int nitems = max(row1 - row0, 0) * tw4;
-    const size_t plane = size_t(g.h) * g.w;
-    const float* inR = in + size_t(f) * 3 * plane + size_t(row0) * g.w + tx * g.tw;
-    uint8_t* labL = lab + size_t(f) * 3 * plane + size_t(row0) * g.w + tx * g.tw;
-
-    int r = tid / tw4, c = tid - r * tw4;
-    const int dr = kK1Threads / tw4, dc = kK1Threads - dr * tw4;
-    // counter of (bin L, thread t) lives at byte ((L>>2)*256 + t)*4 + (L&3): the four counters of one
-    // 32-bit word belong to the SAME thread, so a warp always touches 32 distinct banks whatever L is.
-    unsigned char* my_cnt = s_cnt + tid * 4;
-
-    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
-    float4 vr, vg, vb;
-    size_t off = size_t(r) * g.w + c * 4;
-    if (tid < nitems) {
-        vr = ld_stream_f4(inR + off, pol_stream);
-        vg = ld_stream_f4(inR + plane + off, pol_stream);
-        vb = ld_stream_f4(inR + 2 * plane + off, pol_stream);
-    }
-    for (int i = tid; i < nitems; i += kK1Threads) {
-        const float4 cr = vr, cg = vg, cb = vb;
-        const size_t coff = off;
-        c += dc;
-        r += dr;
-        if (c >= tw4) { c -= tw4; ++r; }
-        off = size_t(r) * g.w + c * 4;
-        if (i + kK1Threads < nitems) {
-            vr = ld_stream_f4(inR + off, pol_stream);
-            vg = ld_stream_f4(inR + plane + off, pol_stream);
-            vb = ld_stream_f4(inR + 2 * plane + off, pol_stream);
-        }
-        const float pr[4] = {cr.x, cr.y, cr.z, cr.w};
-        const float pg[4] = {cg.x, cg.y, cg.z, cg.w};
-        const float pb[4] = {cb.x, cb.y, cb.z, cb.w};
-        uint32_t wl = 0, wa = 0, wb = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int L, a, b;
-            rgb_to_lab(quantize_u8(pr[k]), quantize_u8(pg[k]), quantize_u8(pb[k]), s_gamma, s_cbrt, L, a, b);
-            my_cnt[((L & 0xfc) << 8) | (L & 3)] += 1;
-            wl |= uint32_t(L) << (8 * k);
-            wa |= uint32_t(a) << (8 * k);
-            wb |= uint32_t(b) << (8 * k);
-        }
-        st_hint_u32(labL + coff, wl, pol_keep);
-        st_hint_u32(labL + plane + coff, wa, pol_keep);
-        st_hint_u32(labL + 2 * plane + coff, wb, pol_keep);
-    }
-    __syncthreads();
-
-    // thread `tid` sums bin `tid`: byte (tid&3) of the 256 words of row (tid>>2).  The four threads of a
-    // row read the same 16-byte chunks (broadcast); chunk order is rotated by the row so that the eight
-    // rows of a warp hit disjoint banks.
-    unsigned total_u = 0;
-    {
-        const uint4* row = reinterpret_cast<const uint4*>(s_cnt + (tid >> 2) * (kK1Threads * 4));
-        const unsigned sel = 1u << (8 * (tid & 3));
-#pragma unroll 8
-        for (int k = 0; k < kK1Threads / 4; ++k) {
-            const uint4 v = row[(k + (tid >> 2)) & (kK1Threads / 4 - 1)];
-            total_u = __dp4a(v.x, sel, total_u);
-            total_u = __dp4a(v.y, sel, total_u);
-            total_u = __dp4a(v.z, sel, total_u);
-            total_u = __dp4a(v.w, sel, total_u);
-        }
-    }
-    int total = int(total_u);
-    const size_t t_idx = size_t(f) * ntiles + tile;
-    if (!publish_hist(total, hist_g + t_idx * 256, tickets + t_idx, g.nstrips, &s_flag)) return;
-    tile_lut_256(total, g.clip, g.lut_scale, lut_g + t_idx * 256, s_tmp);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1 fast path, second generation ("instruction diet": the first one ran 80 SASS instructions per pixel at 64 % issue
-// utilisation, and the ncu source view put 28 % of its stalls on the first use of loads issued only 0.6 iterations
-// ahead).  Same arithmetic (Appendix A.1), hence bit-identical Lab planes / histograms / LUTs:
+// K1 fast path (W % tiles_x == 0, H % tiles_y == 0, tile width % 4 == 0, 16-byte aligned planes): per-pixel arithmetic.
+// The first version ran 80 SASS instructions per pixel at 64 % issue utilisation; this is the "instruction diet" that
+// replaced it.  Same arithmetic as Appendix A.1, hence bit-identical Lab planes / histograms / LUTs:
 //   * quantisation on the FMA pipe: for 0 <= x <= 1 (checked once per 12 values with three-input integer maxima on
 //     the raw bit patterns) trunc(x*255) is the low mantissa of  RZ(x*255 + 2^23);  those bits times four plus a
 //     constant IS the shared address of the gamma entry.  Anything else (negative, > 1, NaN, inf) takes the exact
@@ -347,10 +242,8 @@ k_hist_lab_vec(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t*
 //     integer < 2^24, hence exact); floor(S / 4096) falls out of one more FFMA.RZ against 2^23, again as address bits;
 //   * L, a, b are produced pre-scaled so that the result sits in byte 2 of a register: one PRMT assembles a Lab word,
 //     no shifts, no masks;
-//   * the private-counter address ((L >> 2) << 10 | (L & 3)) is (L * 257) & 0xFC03: one IMAD, one LOP3 (which also ORs
-//     in the thread's column);
-//   * two explicit register sets: the twelve floats of item i+1 are in flight while item i is converted;
-//   * 32-bit item offsets against one base pointer per array (IMAD.WIDE), no L2 policy descriptors.
+//   * the private-counter address ((L >> 2) << 10 | (L & 3)) is (L * 257) & 0xFC03: one PRMT, one LOP3 (which also ORs
+//     in the thread's column); the counter is bumped by ONE red.shared.add.u32.
 // ---------------------------------------------------------------------------------------------
 // hides a value's provenance from ptxas (otherwise `bits*4 + (base - K)` is re-associated into two adds per use)
 __device__ __forceinline__ uint32_t opaque(uint32_t x)
@@ -516,229 +409,28 @@ struct RetinexIn {
     float eps;
 };
 
-template <bool kFused>
-__global__ void __launch_bounds__(kK1Threads, 3)
-k_hist_lab_vec2(const float* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
+// ---------------------------------------------------------------------------------------------
+// K1 fast path kernel: COLUMN-OWNER threads.  One CTA per (frame, tile, row strip).  The first
+// nact = (256 / (tw/4)) * (tw/4) threads of the CTA own one 4-pixel column each and walk down the strip
+// rpi = 256 / (tw/4) rows at a time (1080p and 4K: 240 threads, 4 resp. 2 rows): ONE 32-bit group offset advances by a
+// constant, every address is one IMAD.WIDE.U32 against a per-thread base, the L2 prefetch target is the same offset plus a
+// constant.  (Spare threads idle in the main loop and own a histogram bin in the epilogue; tiles wider than 1024 px are
+// walked in passes of 256 columns.)  An item-linear predecessor spent 57 of its 224 instructions per 4-pixel item on
+// row / column wrap bookkeeping for its three pointer sets.  The kernel is bound by its memory streams and the L1/shared
+// data pipe, not by issue (profiles/r3_clahe.md).
+//   kU8In : the frame is packed u8 RGB (HWC, upr_clahe_lab_u8): a 4-pixel group is 12 contiguous bytes, three 32-bit
+//           loads; the bytes index the gamma table directly (no quantisation).
+//   kFused: the CLAHE input is the Retinex recombination of the CNN outputs (models/model.py:405-413,442 followed by
+//           adaptive_params.py:195), evaluated in registers (recombine_px) from x, illu and e: 28 B/px read instead of a
+//           12 B/px `enhanced` frame written by one kernel and re-read by this one.  One raw register set (7 float4)
+//           requested one iteration ahead; two CTAs per SM (128 registers) instead of three.
+// ---------------------------------------------------------------------------------------------
+template <bool kU8In, bool kFused>
+__global__ void __launch_bounds__(kK1Threads, kFused ? 2 : 3)
+k_hist_lab_vec3(const void* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
                 uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g, const RetinexIn rx)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
-    float* s_gammaf = reinterpret_cast<float*>(smem + 256 * kK1Threads);           // 256 x f32
-    uint16_t* s_cbrt = reinterpret_cast<uint16_t*>(s_gammaf + UPR_TAB_GAMMA_LEN);  // 2048 x u16
-    __shared__ int s_tmp[8];
-    __shared__ int s_flag;
-
-    const int tid = threadIdx.x;
-    const int strip = blockIdx.x % g.nstrips;
-    const int tile = blockIdx.x / g.nstrips;
-    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-    const int f = blockIdx.y;
-    const int ntiles = g.tiles_x * g.tiles_y;
-
-    {
-        uint4* z = reinterpret_cast<uint4*>(s_cnt);
-#pragma unroll
-        for (int i = 0; i < 256 * kK1Threads / 16 / kK1Threads; ++i) z[tid + i * kK1Threads] = make_uint4(0, 0, 0, 0);
-        s_gammaf[tid] = float(d_gamma[tid]);
-        reinterpret_cast<uint4*>(s_cbrt)[tid] = reinterpret_cast<const uint4*>(d_cbrt)[tid];  // 256 x 16 B = 4 KB
-    }
-    __syncthreads();
-
-    const uint32_t zero = blockIdx.z;  // always 0: keeps the constants below in registers (see wide_addr)
-    K1Tables t;
-    t.gam = uint32_t(__cvta_generic_to_shared(s_gammaf));
-    t.gam_q = opaque(t.gam - 4u * 0x4B000000u);
-    t.cbr_q = opaque(uint32_t(__cvta_generic_to_shared(s_cbrt)) - 2u * 0x4B000000u);
-    t.four = opaque(4u + zero);
-    t.sixteen = opaque(16u + zero);
-
-    const int row0 = ty * g.th + strip * g.strip_rows;
-    const int row1 = min(row0 + g.strip_rows, (ty + 1) * g.th);
-    const int tw4 = g.tw >> 2;
-    const int nitems = max(row1 - row0, 0) * tw4;
-    const uint32_t w4 = uint32_t(g.w) >> 2;
-    const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;      // fast path: 3 * plane < 2^32
-    // item offsets count 4-pixel groups: a float4 of the input and a u32 word of the Lab planes share the same index
-    const float4* inT = reinterpret_cast<const float4*>(in) + size_t(f) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
-    uint32_t* labT = reinterpret_cast<uint32_t*>(lab) + size_t(f) * 3 * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
-
-    const int dr = kK1Threads / tw4, dc = kK1Threads - dr * tw4;
-    const uint32_t dstep = uint32_t(dr) * w4 + uint32_t(dc), dwrap = w4 - uint32_t(tw4);
-    int c = tid % tw4;
-    // running 64-bit pointers (R plane of the input, L plane of the Lab intermediate); the other two planes are one
-    // 64-bit add away.  (IMAD.WIDE with a register multiplier is split by ptxas into IMAD.WIDE + a 64-bit add: 3 per
-    // address instead of 2.)
-    const char* pin = reinterpret_cast<const char*>(inT + (uint32_t(tid / tw4) * w4 + uint32_t(c)));
-    char* plab = reinterpret_cast<char*>(labT + (uint32_t(tid / tw4) * w4 + uint32_t(c)));
-    const uint32_t tid4 = uint32_t(tid) * 4u;
-
-    auto load = [&](const char* p, float4& r, float4& gch, float4& b) {
-        r = ld_nc_f4(p);
-        gch = ld_nc_f4(wide_imm<16>(p, plane4));
-        b = ld_nc_f4(wide_imm<32>(p, plane4));
-    };
-    auto store = [&](char* p, uint32_t wl, uint32_t wa, uint32_t wb) {
-        st_global_u32(p, wl);
-        st_global_u32(wide_imm<4>(p, plane4), wa);
-        st_global_u32(wide_imm<8>(p, plane4), wb);
-    };
-    // item i -> item i + 256 of the (rows x tw4) strip: returns the step in 4-pixel groups
-    auto advance = [&](int& cc) -> uint32_t {
-        cc += dc;
-        uint32_t st = dstep;
-        if (cc >= tw4) { cc -= tw4; st += dwrap; }
-        return st;
-    };
-
-    // L2 prefetch runs kPfAhead items (of 256 threads x 4 px) ahead of the register loads: the input is a pure stream
-    // (every byte read once), and with only one item of register prefetch the loads were exposed to the full DRAM
-    // latency (experiment: the kernel without its global loads ran in 0.26 ms instead of 0.44 ms).  Plain per-thread
-    // prefetch.global.L2 measured faster than cp.async.bulk.prefetch.L2 per row segment (0.402 vs 0.414 ms).
-    constexpr int kPfAhead = 3;   // (was 6 until the sweep recorded at k_hist_lab_vec3: fused Retinex + CLAHE 1.30 -> 1.21 ms)
-    int cpf = c;
-    const char* ppf = pin;
-    int ipf = tid;
-    auto prefetch_next = [&]() {
-        ipf += kK1Threads;
-        cpf += dc;
-        uint32_t st = dstep;
-        if (cpf >= tw4) { cpf -= tw4; st += dwrap; }
-        ppf = wide_imm<16>(ppf, st);
-        if (ipf < nitems) {
-            prefetch_l2(ppf);
-            prefetch_l2(wide_imm<16>(ppf, plane4));
-            prefetch_l2(wide_imm<32>(ppf, plane4));
-        }
-    };
-    if constexpr (!kFused) {
-#pragma unroll 1
-        for (int k = 0; k < kPfAhead; ++k) prefetch_next();
-    }
-
-    if constexpr (kFused) {
-        // one raw register set (x, e: 3 planes each, illu: 1) requested one item ahead, L2 prefetch kPfAhead items ahead
-        const long long e_delta = reinterpret_cast<const char*>(rx.e) - reinterpret_cast<const char*>(in);
-        const float4* ilT = reinterpret_cast<const float4*>(rx.illu) + size_t(f) * plane4 + size_t(row0) * w4 + uint32_t(tx * tw4);
-        const char* pil = reinterpret_cast<const char*>(ilT + (uint32_t(tid / tw4) * w4 + uint32_t(tid % tw4)));
-        const char* pilf = pil;   // runs with ppf
-        // L2 prefetch of x, e, illu, kPfAhead items ahead
-        auto prefetch7 = [&]() {
-            ipf += kK1Threads;
-            cpf += dc;
-            uint32_t st = dstep;
-            if (cpf >= tw4) { cpf -= tw4; st += dwrap; }
-            ppf = wide_imm<16>(ppf, st);
-            pilf = wide_imm<16>(pilf, st);
-            if (ipf < nitems) {
-                prefetch_l2(ppf);
-                prefetch_l2(wide_imm<16>(ppf, plane4));
-                prefetch_l2(wide_imm<32>(ppf, plane4));
-                prefetch_l2(ppf + e_delta);
-                prefetch_l2(wide_imm<16>(ppf + e_delta, plane4));
-                prefetch_l2(wide_imm<32>(ppf + e_delta, plane4));
-                prefetch_l2(pilf);
-            }
-        };
-#pragma unroll 1
-        for (int k = 0; k < kPfAhead; ++k) prefetch7();
-        float4 X[3], E[3], IL;
-        auto load7 = [&](const char* px, const char* pi) {
-            X[0] = ld_nc_f4(px); X[1] = ld_nc_f4(wide_imm<16>(px, plane4)); X[2] = ld_nc_f4(wide_imm<32>(px, plane4));
-            const char* pe = px + e_delta;
-            E[0] = ld_nc_f4(pe); E[1] = ld_nc_f4(wide_imm<16>(pe, plane4)); E[2] = ld_nc_f4(wide_imm<32>(pe, plane4));
-            IL = ld_nc_f4(pi);
-        };
-        auto recombine4 = [&](const float4 xv, const float4 ev, const float d[4]) {
-            float4 o;
-            float r;
-            recombine_px(xv.x, d[0], ev.x, r, o.x);
-            recombine_px(xv.y, d[1], ev.y, r, o.y);
-            recombine_px(xv.z, d[2], ev.z, r, o.z);
-            recombine_px(xv.w, d[3], ev.w, r, o.w);
-            return o;
-        };
-        int i = tid;
-        if (i < nitems) load7(pin, pil);
-        while (i < nitems) {
-            const float d[4] = {__fadd_rn(IL.x, rx.eps), __fadd_rn(IL.y, rx.eps), __fadd_rn(IL.z, rx.eps), __fadd_rn(IL.w, rx.eps)};
-            const float4 er = recombine4(X[0], E[0], d), eg = recombine4(X[1], E[1], d), eb = recombine4(X[2], E[2], d);
-            const uint32_t st1 = advance(c);
-            i += kK1Threads;
-            pin = wide_imm<16>(pin, st1);
-            pil = wide_imm<16>(pil, st1);
-            if (i < nitems) load7(pin, pil);
-            prefetch7();
-            uint32_t wl, wa, wb;
-            k1_item(er, eg, eb, t, s_cnt, tid4, wl, wa, wb);
-            store(plab, wl, wa, wb);
-            plab = const_cast<char*>(wide_imm<4>(plab, st1));
-        }
-    } else {
-    float4 ar, ag, ab, br, bg, bb;
-    int i = tid;
-    if (i < nitems) load(pin, ar, ag, ab);
-    while (i < nitems) {
-        const uint32_t st1 = advance(c);
-        const int i2 = i + kK1Threads;
-        if (i2 < nitems) load(wide_imm<16>(pin, st1), br, bg, bb);
-        prefetch_next();
-        uint32_t wl, wa, wb;
-        k1_item(ar, ag, ab, t, s_cnt, tid4, wl, wa, wb);
-        store(plab, wl, wa, wb);
-        if (i2 >= nitems) break;
-        const uint32_t st2 = advance(c);
-        pin = wide_imm<16>(pin, st1 + st2);
-        i = i2 + kK1Threads;
-        if (i < nitems) load(pin, ar, ag, ab);
-        prefetch_next();
-        k1_item(br, bg, bb, t, s_cnt, tid4, wl, wa, wb);
-        store(const_cast<char*>(wide_imm<4>(plab, st1)), wl, wa, wb);
-        plab = const_cast<char*>(wide_imm<4>(plab, st1 + st2));
-    }
-    }
-    __syncthreads();
-
-    // thread `tid` sums bin `tid`: byte (tid&3) of the 256 words of row (tid>>2).  The four threads of a
-    // row read the same 16-byte chunks (broadcast); chunk order is rotated by the row so that the eight
-    // rows of a warp hit disjoint banks.
-    unsigned total_u = 0;
-    {
-        const uint4* row = reinterpret_cast<const uint4*>(s_cnt + (tid >> 2) * (kK1Threads * 4));
-        const unsigned sel = 1u << (8 * (tid & 3));
-#pragma unroll 8
-        for (int k = 0; k < kK1Threads / 4; ++k) {
-            const uint4 v = row[(k + (tid >> 2)) & (kK1Threads / 4 - 1)];
-            total_u = __dp4a(v.x, sel, total_u);
-            total_u = __dp4a(v.y, sel, total_u);
-            total_u = __dp4a(v.z, sel, total_u);
-            total_u = __dp4a(v.w, sel, total_u);
-        }
-    }
-    int total = int(total_u);
-    const size_t t_idx = size_t(f) * ntiles + tile;
-    if (!publish_hist(total, hist_g + t_idx * 256, tickets + t_idx, g.nstrips, &s_flag)) return;
-    tile_lut_256(total, g.clip, g.lut_scale, lut_g + t_idx * 256, s_tmp);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1 fast path, third generation: COLUMN-OWNER threads.  The SASS of the second generation spends 57 of its 224
-// instructions per 4-pixel item on bookkeeping: a thread's items are 256 apart in the (rows x tw/4) strip, so the three
-// pointer sets (loads, L2 prefetches, Lab stores) each carry a row/column wrap, and every address is a 64-bit LEA pair.
-// Here the first nact = (256 / (tw/4)) * (tw/4) threads of the CTA own one 4-pixel column each and walk down the strip
-// rpi = nact / (tw/4) rows at a time (1080p: 240 threads, 4 rows): ONE 32-bit group offset advances by a constant, every
-// address is one IMAD.WIDE.U32 against a per-thread base, the prefetch target is the same offset plus a constant.  (The
-// spare threads of the last warp idle in the main loop and own a histogram bin in the epilogue.)  Together with the
-// gamma-address bias passed as a parameter and the PRMT counter index this is 585 instead of 668 SASS instructions per
-// loop trip (two items), 263 M instead of 293 M executed warp instructions per 64 x 1080p -- at the SAME 0.402 ms: the
-// kernel is bound by its memory streams, not by issue (profiles/r3_clahe.md).  Same arithmetic (k1_item): bit-identical.
-// ---------------------------------------------------------------------------------------------
-// kU8In: the frame is packed u8 RGB (HWC, upr_clahe_lab_u8): a 4-pixel group is 12 contiguous bytes, three 32-bit loads;
-// the bytes index the gamma table directly (no quantisation), everything after that is shared with the f32 kernel.
-template <bool kU8In>
-__global__ void __launch_bounds__(kK1Threads, 3)
-k_hist_lab_vec3(const void* __restrict__ in, uint8_t* __restrict__ lab, int32_t* __restrict__ hist_g,
-                uint8_t* __restrict__ lut_g, unsigned* __restrict__ tickets, const ClaheGeom g)
-{
+    static_assert(!(kU8In && kFused), "the fused Retinex prologue reads f32 planes");
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* s_cnt = smem;                                                   // [64 bin groups][256 threads][4 bins] u8
     float* s_gammaf = reinterpret_cast<float*>(smem + 256 * kK1Threads);           // 256 x f32
@@ -771,10 +463,11 @@ k_hist_lab_vec3(const void* __restrict__ in, uint8_t* __restrict__ lab, int32_t*
     t.sixteen = opaque(16u + zero);
 
     const int tw4 = g.tw >> 2;
-    const int rpi = kK1Threads / tw4;              // rows per iteration (host guarantees tw4 <= 256)
-    const int lr = tid / tw4, lc = tid - lr * tw4;
+    const int cpp = min(tw4, kK1Threads);          // columns per pass (one pass unless the tile is wider than 1024 px)
+    const int rpi = kK1Threads / cpp;              // rows per iteration
+    const int lr = tid / cpp, lc0 = tid - lr * cpp;
     const int row0 = ty * g.th + strip * g.strip_rows;
-    const int row1 = (lr < rpi) ? min(row0 + g.strip_rows, (ty + 1) * g.th) : 0;   // spare threads: empty range
+    const int strip_end = min(row0 + g.strip_rows, (ty + 1) * g.th);
     const uint32_t w4 = uint32_t(g.w) >> 2;
     const uint32_t plane4 = (uint32_t(g.h) * uint32_t(g.w)) >> 2;      // fast path: 3 * plane < 2^32
     const uint32_t step = uint32_t(rpi) * w4;
@@ -784,45 +477,25 @@ k_hist_lab_vec3(const void* __restrict__ in, uint8_t* __restrict__ lab, int32_t*
     const uint32_t pfo = uint32_t(kPf) * step;
     const uint32_t tid4 = uint32_t(tid) * 4u;
 
+#pragma unroll 1
+    for (int xc = 0; xc < tw4; xc += cpp) {
+    const int lc = xc + lc0;
+    const int row1 = (lr < rpi && lc < tw4) ? strip_end : 0;   // spare threads: empty range
     // per-THREAD plane bases (frame, tile column, this thread's 4-pixel column): a base that lives in vector registers
     // lets ptxas address base[o] with one IMAD.WIDE.U32 (block-uniform bases end up in uniform registers and cost a
     // shift, a multiply-high and two 64-bit adds per access).  Row offsets count 4-pixel groups: a float4 of the input
     // and a u32 word of the Lab planes share the same index.
     // (opaque_ptr: otherwise the front end re-associates base + (K + o) back onto the kernel parameter)
-    const float4* inR = opaque_ptr(reinterpret_cast<const float4*>(in) + (size_t(f) * 3 * plane4 + uint32_t(tx * tw4 + lc)));
+    const uint32_t col = uint32_t(tx * tw4 + lc);
+    const float4* inR = opaque_ptr(reinterpret_cast<const float4*>(in) + (size_t(f) * 3 * plane4 + col));
     const float4* inG = opaque_ptr(inR + plane4);
     const float4* inB = opaque_ptr(inG + plane4);
     struct Px4 { uint32_t w[3]; };   // one 4-pixel group of a packed u8 frame
-    const Px4* in8 = opaque_ptr(reinterpret_cast<const Px4*>(in) + (size_t(f) * plane4 + uint32_t(tx * tw4 + lc)));
-    uint32_t* labL = opaque_ptr(reinterpret_cast<uint32_t*>(lab) + (size_t(f) * 3 * plane4 + uint32_t(tx * tw4 + lc)));
+    const Px4* in8 = opaque_ptr(reinterpret_cast<const Px4*>(in) + (size_t(f) * plane4 + col));
+    uint32_t* labL = opaque_ptr(reinterpret_cast<uint32_t*>(lab) + (size_t(f) * 3 * plane4 + col));
     uint32_t* labA = opaque_ptr(labL + plane4);
     uint32_t* labB = opaque_ptr(labA + plane4);
 
-    // (u8 frames: the three words of a group travel in the .x lanes of the three float4 registers)
-    auto load = [&](uint32_t o, float4& r, float4& gch, float4& b) {
-        if constexpr (kU8In) {
-            r.x = __uint_as_float(ld_nc_u32p(&in8[o].w[0]));
-            gch.x = __uint_as_float(ld_nc_u32p(&in8[o].w[1]));
-            b.x = __uint_as_float(ld_nc_u32p(&in8[o].w[2]));
-        } else {
-            r = ld_nc_f4(inR + o);
-            gch = ld_nc_f4(inG + o);
-            b = ld_nc_f4(inB + o);
-        }
-    };
-    auto prefetch = [&](uint32_t o) {
-        if constexpr (kU8In) {
-            prefetch_l2(in8 + o);
-        } else {
-            prefetch_l2(inR + o);
-            prefetch_l2(inG + o);
-            prefetch_l2(inB + o);
-        }
-    };
-    auto item = [&](const float4& r, const float4& gch, const float4& b, uint32_t& wl, uint32_t& wa, uint32_t& wb) {
-        if constexpr (kU8In) k1_item_u8(__float_as_uint(r.x), __float_as_uint(gch.x), __float_as_uint(b.x), t, s_cnt, tid4, wl, wa, wb);
-        else k1_item(r, gch, b, t, s_cnt, tid4, wl, wa, wb);
-    };
     auto store = [&](uint32_t o, uint32_t wl, uint32_t wa, uint32_t wb) {
         st_global_u32(labL + o, wl);
         st_global_u32(labA + o, wa);
@@ -833,32 +506,106 @@ k_hist_lab_vec3(const void* __restrict__ in, uint8_t* __restrict__ lab, int32_t*
     uint32_t o = uint32_t(row) * w4;
     const int row_ld = row1 - rpi;                  // row < row_ld: there is a next iteration to load
     const int row_pf = row1 - kPf * rpi;            // row < row_pf: there is an iteration kPf ahead to prefetch
-    float4 ar, ag, ab, br, bg, bb;
-    if (row < row1) {
-        load(o, ar, ag, ab);
+
+    if constexpr (kFused) {
+        const float4* eR = opaque_ptr(reinterpret_cast<const float4*>(rx.e) + (size_t(f) * 3 * plane4 + col));
+        const float4* eG = opaque_ptr(eR + plane4);
+        const float4* eB = opaque_ptr(eG + plane4);
+        const float4* ilp = opaque_ptr(reinterpret_cast<const float4*>(rx.illu) + (size_t(f) * plane4 + col));
+        float4 X0, X1, X2, E0, E1, E2, IL;
+        auto load7 = [&](uint32_t oo) {
+            X0 = ld_nc_f4(inR + oo); X1 = ld_nc_f4(inG + oo); X2 = ld_nc_f4(inB + oo);
+            E0 = ld_nc_f4(eR + oo); E1 = ld_nc_f4(eG + oo); E2 = ld_nc_f4(eB + oo);
+            IL = ld_nc_f4(ilp + oo);
+        };
+        auto prefetch7 = [&](uint32_t oo) {
+            prefetch_l2(inR + oo); prefetch_l2(inG + oo); prefetch_l2(inB + oo);
+            prefetch_l2(eR + oo); prefetch_l2(eG + oo); prefetch_l2(eB + oo);
+            prefetch_l2(ilp + oo);
+        };
+        auto recombine4 = [&](const float4 xv, const float4 ev, const float d[4]) {
+            float4 r;
+            float refl;
+            recombine_px(xv.x, d[0], ev.x, refl, r.x);
+            recombine_px(xv.y, d[1], ev.y, refl, r.y);
+            recombine_px(xv.z, d[2], ev.z, refl, r.z);
+            recombine_px(xv.w, d[3], ev.w, refl, r.w);
+            return r;
+        };
+        if (row < row1) {
+            load7(o);
 #pragma unroll 1
-        for (int k = 1; k < kPf; ++k)
-            if (row + k * rpi < row1) prefetch(o + uint32_t(k) * step);
+            for (int k = 1; k < kPf; ++k)
+                if (row + k * rpi < row1) prefetch7(o + uint32_t(k) * step);
+        }
+        while (row < row1) {
+            const float d[4] = {__fadd_rn(IL.x, rx.eps), __fadd_rn(IL.y, rx.eps), __fadd_rn(IL.z, rx.eps), __fadd_rn(IL.w, rx.eps)};
+            const float4 er = recombine4(X0, E0, d), eg = recombine4(X1, E1, d), eb = recombine4(X2, E2, d);
+            if (row < row_ld) load7(o + step);
+            if (row < row_pf) prefetch7(o + pfo);
+            uint32_t wl, wa, wb;
+            k1_item(er, eg, eb, t, s_cnt, tid4, wl, wa, wb);
+            store(o, wl, wa, wb);
+            row += rpi;
+            o += step;
+        }
+    } else {
+        // (u8 frames: the three words of a group travel in the .x lanes of the three float4 registers)
+        auto load = [&](uint32_t oo, float4& r, float4& gch, float4& b) {
+            if constexpr (kU8In) {
+                r.x = __uint_as_float(ld_nc_u32p(&in8[oo].w[0]));
+                gch.x = __uint_as_float(ld_nc_u32p(&in8[oo].w[1]));
+                b.x = __uint_as_float(ld_nc_u32p(&in8[oo].w[2]));
+            } else {
+                r = ld_nc_f4(inR + oo);
+                gch = ld_nc_f4(inG + oo);
+                b = ld_nc_f4(inB + oo);
+            }
+        };
+        auto prefetch = [&](uint32_t oo) {
+            if constexpr (kU8In) {
+                prefetch_l2(in8 + oo);
+            } else {
+                prefetch_l2(inR + oo);
+                prefetch_l2(inG + oo);
+                prefetch_l2(inB + oo);
+            }
+        };
+        auto item = [&](const float4& r, const float4& gch, const float4& b, uint32_t& wl, uint32_t& wa, uint32_t& wb) {
+            if constexpr (kU8In) k1_item_u8(__float_as_uint(r.x), __float_as_uint(gch.x), __float_as_uint(b.x), t, s_cnt, tid4, wl, wa, wb);
+            else k1_item(r, gch, b, t, s_cnt, tid4, wl, wa, wb);
+        };
+        // two register sets: the twelve floats of iteration i+1 are in flight while iteration i is converted
+        float4 ar, ag, ab, br, bg, bb;
+        if (row < row1) {
+            load(o, ar, ag, ab);
+#pragma unroll 1
+            for (int k = 1; k < kPf; ++k)
+                if (row + k * rpi < row1) prefetch(o + uint32_t(k) * step);
+        }
+        while (row < row1) {
+            uint32_t wl, wa, wb;
+            if (row < row_ld) load(o + step, br, bg, bb);
+            if (row < row_pf) prefetch(o + pfo);
+            item(ar, ag, ab, wl, wa, wb);
+            store(o, wl, wa, wb);
+            row += rpi;
+            o += step;
+            if (row >= row1) break;
+            if (row < row_ld) load(o + step, ar, ag, ab);
+            if (row < row_pf) prefetch(o + pfo);
+            item(br, bg, bb, wl, wa, wb);
+            store(o, wl, wa, wb);
+            row += rpi;
+            o += step;
+        }
     }
-    while (row < row1) {
-        uint32_t wl, wa, wb;
-        if (row < row_ld) load(o + step, br, bg, bb);
-        if (row < row_pf) prefetch(o + pfo);
-        item(ar, ag, ab, wl, wa, wb);
-        store(o, wl, wa, wb);
-        row += rpi;
-        o += step;
-        if (row >= row1) break;
-        if (row < row_ld) load(o + step, ar, ag, ab);
-        if (row < row_pf) prefetch(o + pfo);
-        item(br, bg, bb, wl, wa, wb);
-        store(o, wl, wa, wb);
-        row += rpi;
-        o += step;
     }
     __syncthreads();
 
-    // thread `tid` sums bin `tid` (see k_hist_lab_vec2)
+    // thread `tid` sums bin `tid`: byte (tid&3) of the 256 words of row (tid>>2).  The four threads of a
+    // row read the same 16-byte chunks (broadcast); chunk order is rotated by the row so that the eight
+    // rows of a warp hit disjoint banks.
     unsigned total_u = 0;
     {
         const uint4* rowp = reinterpret_cast<const uint4*>(s_cnt + (tid >> 2) * (kK1Threads * 4));
@@ -950,93 +697,10 @@ k_hist_lab_generic(const void* __restrict__ in, uint8_t* __restrict__ lab, int32
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 fast path
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kK3Threads)
-k_map_vec(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, float* __restrict__ out, const MapGeom g)
-{
-    __shared__ uint32_t s_quad[256];
-    __shared__ uint32_t s_yf[256];
-    __shared__ __align__(16) float s_outf[4096];
-
-    const int tid = threadIdx.x;
-    const int strip = blockIdx.x % g.nstrips;
-    const int cell = blockIdx.x / g.nstrips;
-    const int cy = cell / (g.tiles_x + 1), cx = cell - cy * (g.tiles_x + 1);
-    const int f = blockIdx.y;
-
-    const int x0 = g.bx[cx], x1 = g.bx[cx + 1];
-    const int rows_cell = g.by[cy + 1] - g.by[cy];
-    const int srows = (rows_cell + g.nstrips - 1) / g.nstrips;
-    const int y0 = g.by[cy] + strip * srows;
-    const int y1 = min(y0 + srows, g.by[cy + 1]);
-    if (x0 >= x1 || y0 >= y1) return;
-
-    {
-        const int ty1 = max(cy - 1, 0), ty2 = min(cy, g.tiles_y - 1);
-        const int tx1 = max(cx - 1, 0), tx2 = min(cx, g.tiles_x - 1);
-        const uint8_t* lf = lut_g + size_t(f) * g.tiles_x * g.tiles_y * 256 + tid;
-        s_quad[tid] = uint32_t(lf[(ty1 * g.tiles_x + tx1) * 256]) | (uint32_t(lf[(ty1 * g.tiles_x + tx2) * 256]) << 8) |
-                      (uint32_t(lf[(ty2 * g.tiles_x + tx1) * 256]) << 16) | (uint32_t(lf[(ty2 * g.tiles_x + tx2) * 256]) << 24);
-        s_yf[tid] = d_labyf[tid];
-#pragma unroll
-        for (int i = 0; i < 4096 / 4 / kK3Threads; ++i)
-            reinterpret_cast<uint4*>(s_outf)[tid + i * kK3Threads] = reinterpret_cast<const uint4*>(d_outf_bits)[tid + i * kK3Threads];
-    }
-    __syncthreads();
-
-    const size_t plane = size_t(g.h) * g.w;
-    const uint8_t* labL = lab + size_t(f) * 3 * plane;
-    float* outR = out + size_t(f) * 3 * plane;
-    const float txbase = float(cx - 1), tybase = float(cy - 1);
-    const int cw4 = (x1 - x0) >> 2;
-    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
-
-    for (int xc = 0; xc < cw4; xc += kK3Threads) {
-        const int cwc = min(kK3Threads, cw4 - xc);
-        const int rpi = kK3Threads / cwc;  // rows per iteration
-        const int lr = tid / cwc, lc = tid - lr * cwc;
-        if (lr >= rpi) continue;
-        const int x = x0 + (xc + lc) * 4;
-        float xa[4], xa1[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float txf = __fadd_rn(__fmul_rn(float(x + k), g.inv_tw), -0.5f);
-            xa[k] = __fsub_rn(txf, txbase);
-            xa1[k] = __fsub_rn(1.0f, xa[k]);
-        }
-        for (int y = y0 + lr; y < y1; y += rpi) {
-            const float tyf = __fadd_rn(__fmul_rn(float(y), g.inv_th), -0.5f);
-            const float ya = __fsub_rn(tyf, tybase);
-            const float ya1 = __fsub_rn(1.0f, ya);
-            const size_t off = size_t(y) * g.w + x;
-            const uint32_t wl = ld_hint_u32(labL + off, pol_keep);
-            const uint32_t wa = ld_hint_u32(labL + plane + off, pol_keep);
-            const uint32_t wb = ld_hint_u32(labL + 2 * plane + off, pol_keep);
-            float o[3][4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t q = s_quad[(wl >> (8 * k)) & 0xffu];
-                const float top = __fadd_rn(__fmul_rn(byte_to_float(q, 0), xa1[k]), __fmul_rn(byte_to_float(q, 1), xa[k]));
-                const float bot = __fadd_rn(__fmul_rn(byte_to_float(q, 2), xa1[k]), __fmul_rn(byte_to_float(q, 3), xa[k]));
-                const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-                // rint via the 1.5*2^23 trick (round-half-even, same as cvRound); 0 <= res < 255.5
-                const int Lc = __float_as_int(__fadd_rn(res, 12582912.0f)) & 0xff;
-                lab_to_rgb_f32(Lc, int((wa >> (8 * k)) & 0xffu), int((wb >> (8 * k)) & 0xffu), s_yf, s_outf, o[0][k], o[1][k], o[2][k]);
-            }
-            st_stream_f4(outR + off, make_float4(o[0][0], o[0][1], o[0][2], o[0][3]), pol_stream);
-            st_stream_f4(outR + plane + off, make_float4(o[1][0], o[1][1], o[1][2], o[1][3]), pol_stream);
-            st_stream_f4(outR + 2 * plane + off, make_float4(o[2][0], o[2][1], o[2][2], o[2][3]), pol_stream);
-        }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// K3 fast path, fifth generation.  Experiments on the third one (profiles/r2_*): with loads AND stores suppressed the
+// K3 fast path.  Experiments on an earlier one-CTA-per-item version (profiles/r2_*): with loads AND stores suppressed the
 // kernel still took 0.40 of 0.44 ms -- it is bound by instruction issue (94 executed instructions per pixel incl.
 // prologues and idle lanes), not by HBM or by shared-memory bank conflicts (constant frames are as slow as noise).
-// Hence a shorter instruction stream:
+// Hence a short instruction stream:
 //   * abToXZ: the cubic branch is 4 instructions; the linear branch (i <= 3390: C truncating division, 7 instructions
 //     plus a select) becomes a PREDICATED 16-bit table load (23 KB table; only dark pixels take it, so the gather is
 //     sparse);
@@ -1046,7 +710,7 @@ k_map_vec(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, fl
 //   * persistent CTAs (2 per SM) pull (frame, cell, strip) items from an atomic counter: the 41 KB of tables are staged
 //     once per CTA instead of once per item, no tail wave; the quad table of the next item is built while the current
 //     one is mapped (one barrier per item).
-// Arithmetic identical to k_map_vec (Appendix A.2/A.3): bit-identical output.
+// Arithmetic: Appendix A.2 / A.3 (the generic kernel k_map_generic states it in plain C).
 // ---------------------------------------------------------------------------------------------
 constexpr int kK5MaxThreads = 512;
 constexpr int kXzLinMin = -8145;
@@ -1352,15 +1016,10 @@ static bool valid_shape(int n, int h, int w, int tiles_x, int tiles_y)
            size_t(h) * w <= (size_t(1) << 30);
 }
 
-// development switch (A/B timing on the GPU box, profiles/r2_clahe.md, r3_clahe.md): UPR_CLAHE_VARIANT bit 0 =
-// first-generation map kernel (k_map_vec), bit 1 = first-generation histogram kernel (k_hist_lab_vec), bit 2 = second-
-// generation histogram kernel (k_hist_lab_vec2) instead of the column-owner one, bit 3 = map kernel without the
-// replicated {A, y} table.  Same results either way.
-static int variant()
-{
-    const char* e = std::getenv("UPR_CLAHE_VARIANT");   // read per call so that tests can A/B within one process
-    return e ? std::atoi(e) : 0;
-}
+// cudaFuncAttributeMaxDynamicSharedMemorySize bookkeeping, one word per kernel instantiation, one bit per device ordinal.
+// Written without a lock on purpose: concurrent callers can only both see "not set yet" and both issue the (idempotent)
+// cudaFuncSetAttribute call; the words are atomics so that the race is a defined one.
+static std::atomic<unsigned long long> g_smem_mask[5];
 
 // raw tile coordinate of OpenCV's interpolation: floor(p * inv - 0.5f), fp32, separately rounded
 static inline int raw_tile(int p, float inv)
@@ -1381,7 +1040,7 @@ static int clahe_run(const void* in_v, void* out_v, int n, int h, int w, double 
     if (!valid_shape(n, h, w, tiles_x, tiles_y)) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
     if (!in_v || !out_v || !ws) return UPR_E_NULL;
-    if (rx && (in_u8 || out_u8)) return UPR_E_PARAM;
+    if (rx && in_u8) return UPR_E_PARAM;
     const float* in = static_cast<const float*>(in_v);      // valid when !in_u8
     float* out = static_cast<float*>(out_v);                // valid when !out_u8
     const size_t in_es = in_u8 ? 1 : sizeof(float), out_es = out_u8 ? 1 : sizeof(float);
@@ -1413,11 +1072,8 @@ static int clahe_run(const void* in_v, void* out_v, int n, int h, int w, double 
     // interpolation cell boundaries from the exact fp32 recipe (monotone in p)
     MapGeom m{};
     // (a one-row strip of a tile must fit the byte counters: <= 63 four-pixel items per thread, i.e. tiles <= 64512 px wide)
-    // the column-owner histogram kernel wants (almost) every thread to own a column: 240 of 256 at 1080p and 4K; it is
-    // the only vector kernel for packed u8 frames
-    const bool col_owner = g.tw / 4 <= kK1Threads && g.tw >= 4 && (kK1Threads / (g.tw / 4)) * (g.tw / 4) * 8 >= kK1Threads * 7;
     bool fast = !padded && tiles_x <= kMaxTiles && tiles_y <= kMaxTiles && (g.tw % 4 == 0) && g.tw / 4 <= 63 * kK1Threads &&
-                (in_u8 ? ((reinterpret_cast<uintptr_t>(in_v) & 3u) == 0 && col_owner) : aligned16(in_v)) &&
+                (in_u8 ? (reinterpret_cast<uintptr_t>(in_v) & 3u) == 0 : aligned16(in_v)) &&
                 (out_u8 ? (reinterpret_cast<uintptr_t>(out_v) & 3u) == 0 : aligned16(out_v)) &&
                 size_t(h) * w * 3 < (size_t(1) << 32) && (!rx || (aligned16(rx->illu) && aligned16(rx->e)));
     if (fast) {
@@ -1452,8 +1108,9 @@ static int clahe_run(const void* in_v, void* out_v, int n, int h, int w, double 
         if (fast) {
             // K1: byte counters allow <= 255 pixels per thread between flushes -> <= 63 items/thread
             const int tw4 = g.tw / 4;
-            // (column-owner kernel: 63 iterations of kK1Threads / tw4 rows; the item-linear kernels allow slightly more)
-            const int max_rows = tw4 <= kK1Threads ? 63 * (kK1Threads / tw4) : std::max(1, (63 * kK1Threads) / tw4);
+            // (63 iterations of kK1Threads / tw4 rows; tiles wider than 1024 px: 63 / passes rows, one row per iteration)
+            const int passes = (tw4 + kK1Threads - 1) / kK1Threads;
+            const int max_rows = tw4 <= kK1Threads ? 63 * (kK1Threads / tw4) : std::max(1, 63 / passes);
             int nstrips = (g.th + max_rows - 1) / max_rows;
             const int want = (3 * kNumSMsB200 + nf * ntiles - 1) / (nf * ntiles);  // fill the machine for tiny batches
             nstrips = std::min(std::max(nstrips, want), g.th);
@@ -1472,58 +1129,36 @@ static int clahe_run(const void* in_v, void* out_v, int n, int h, int w, double 
                 }
             }
             const size_t smem1 = size_t(256) * kK1Threads + UPR_TAB_GAMMA_LEN * 4 + UPR_TAB_CBRT_LEN * 2;
-            static unsigned long long m1 = 0, m2 = 0, m3 = 0, m4 = 0;
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec, smem1, m1));
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<false>, smem1, m2));
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec2<true>, smem1, m3));
-            static unsigned long long m4u = 0;
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3<false>, smem1, m4));
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3<true>, smem1, m4u));
             if (stage_mask & 1) {
+                const dim3 grid1(ntiles * g.nstrips, nf);
+                const RetinexIn rxf = rx ? RetinexIn{rx->illu + size_t(f0) * h * w, rx->e + fplane, rx->eps} : RetinexIn{nullptr, nullptr, 0.0f};
                 if (in_u8) {
-                    k_hist_lab_vec3<true><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
-                        static_cast<const uint8_t*>(in_v) + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g);
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3<true, false>, smem1, g_smem_mask[0]));
+                    k_hist_lab_vec3<true, false><<<grid1, kK1Threads, smem1, stream>>>(
+                        static_cast<const uint8_t*>(in_v) + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
                 } else if (rx) {
-                    const RetinexIn rxf{rx->illu + size_t(f0) * h * w, rx->e + fplane, rx->eps};
-                    k_hist_lab_vec2<true><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3<false, true>, smem1, g_smem_mask[1]));
+                    k_hist_lab_vec3<false, true><<<grid1, kK1Threads, smem1, stream>>>(
                         in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
-                } else if (variant() & 2) {
-                    k_hist_lab_vec<<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(in + fplane, lab + fplane, hist + ftile * 256,
-                                                                                                lut + ftile * 256, tickets + ftile, g);
-                } else if (col_owner && !(variant() & 4)) {
-                    k_hist_lab_vec3<false><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
-                        in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g);
                 } else {
-                    k_hist_lab_vec2<false><<<dim3(ntiles * g.nstrips, nf), kK1Threads, smem1, stream>>>(
-                        in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, RetinexIn{nullptr, nullptr, 0.0f});
+                    UPR_CUDA_TRY(ensure_dynamic_smem(k_hist_lab_vec3<false, false>, smem1, g_smem_mask[2]));
+                    k_hist_lab_vec3<false, false><<<grid1, kK1Threads, smem1, stream>>>(
+                        in + fplane, lab + fplane, hist + ftile * 256, lut + ftile * 256, tickets + ftile, g, rxf);
                 }
                 UPR_LAUNCH_CHECK();
             }
             const int ncells = (tiles_x + 1) * (tiles_y + 1);
             const int cell_rows = g.th;  // interior cells are one tile high
-            int ks = std::max(1, int((size_t(cell_rows) * g.tw + 32767) / 32768));
-            const int want3 = (8 * kNumSMsB200 + nf * ncells - 1) / (nf * ncells);
-            ks = std::min(std::max(ks, want3), std::max(cell_rows / 4, 1));
-            m.nstrips = ks;
             if (stage_mask & 2) {
-                if ((variant() & 1) && !out_u8) {
-                    k_map_vec<<<dim3(ncells * ks, nf), kK3Threads, 0, stream>>>(lab + fplane, lut + ftile * 256, out + fplane, m);
-                } else {
+                {
                     // thread count: the largest multiple of the interior cell width (in 4-px columns) <= 512
                     const int cw4 = g.tw / 4;
                     int nthr = cw4 <= kK5MaxThreads ? (kK5MaxThreads / cw4) * cw4 : kK5MaxThreads;
                     if (nthr < 256) nthr = kK5MaxThreads;
-                    const bool ayrep = (variant() & 8) == 0;   // bit 3: plain {A, y} table (A/B timing)
-                    const size_t smem5r = size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 * 16 + 2 * 256 * 4;
-                    const size_t smem5 = ayrep ? smem5r : size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4;
-                    static unsigned long long m5 = 0, m5r = 0, m5u = 0, m5ru = 0;
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<false, false>, size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4, m5));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<true, false>, smem5r, m5r));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<false, true>, size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 + 2 * 256 * 4, m5u));
-                    UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<true, true>, smem5r, m5ru));
+                    const size_t smem5 = size_t(kXzLinBytes) + 4096 * 4 + 512 * 4 * 16 + 2 * 256 * 4;
                     // items = (frame, cell, strip): ~4 items per resident CTA on small batches, strips of >= 16 rows (every item
                     // costs a barrier and a quad-table build: with 16 items per CTA and 8-row strips a 3-frame call took 99 us
-                    // instead of 78 us for the first-generation kernel)
+                    // instead of 78 us for a one-CTA-per-item kernel)
                     const int resident = 2 * kNumSMsB200;
                     int ks5 = std::max(1, int((size_t(4) * resident + size_t(nf) * ncells - 1) / (size_t(nf) * ncells)));
                     ks5 = std::min(ks5, std::max(cell_rows / 16, 1));
@@ -1533,9 +1168,13 @@ static int clahe_run(const void* in_v, void* out_v, int n, int h, int w, double 
                     if (!work_cleared) UPR_CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(unsigned), stream));
                     const dim3 grid5(unsigned(std::min<long long>(nitems, resident)));
                     void* outf = static_cast<char*>(out_v) + fplane * out_es;
-                    auto* kfn = out_u8 ? (ayrep ? k_map_vec5<true, true> : k_map_vec5<false, true>)
-                                       : (ayrep ? k_map_vec5<true, false> : k_map_vec5<false, false>);
-                    kfn<<<grid5, nthr, smem5, stream>>>(lab + fplane, lut + ftile * 256, outf, m, work, int(nitems));
+                    if (out_u8) {
+                        UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<true, true>, smem5, g_smem_mask[3]));
+                        k_map_vec5<true, true><<<grid5, nthr, smem5, stream>>>(lab + fplane, lut + ftile * 256, outf, m, work, int(nitems));
+                    } else {
+                        UPR_CUDA_TRY(ensure_dynamic_smem(k_map_vec5<true, false>, smem5, g_smem_mask[4]));
+                        k_map_vec5<true, false><<<grid5, nthr, smem5, stream>>>(lab + fplane, lut + ftile * 256, outf, m, work, int(nitems));
+                    }
                 }
                 UPR_LAUNCH_CHECK();
             }
@@ -1594,6 +1233,23 @@ int upr_retinex_clahe_f32(const float* x, const float* illu, const float* e, flo
     if (rc) return rc;
     return upr::clahe_run(out_nchw, out_nchw, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
                           static_cast<cudaStream_t>(stream));
+}
+
+int upr_retinex_clahe_f32_u8(const float* x, const float* illu, const float* e, unsigned char* out_nhwc, float* enhanced_scratch,
+                             int n, int h, int w, float eps, double clip_limit, int tiles_x, int tiles_y, void* workspace,
+                             size_t workspace_bytes, upr_stream_t stream)
+{
+    if (!x || !illu || !e) return (n == 0 && upr::valid_shape(n, h, w, tiles_x, tiles_y)) ? UPR_OK : UPR_E_NULL;
+    const upr::RetinexIn rx{illu, e, eps};
+    int rc = upr::clahe_run(x, out_nhwc, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
+                            static_cast<cudaStream_t>(stream), 3, &rx, false, true);
+    if (rc != upr::kNeedUnfused) return rc;
+    // ragged shapes: recombination into the caller's scratch frame, then CLAHE f32 -> u8
+    if (!enhanced_scratch) return UPR_E_WORKSPACE;
+    rc = upr_retinex_recombine_f32(x, illu, e, nullptr, enhanced_scratch, n, h, w, eps, stream);
+    if (rc) return rc;
+    return upr::clahe_run(enhanced_scratch, out_nhwc, n, h, w, clip_limit, tiles_x, tiles_y, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream), 3, nullptr, false, true);
 }
 
 int upr_clahe_lab_u8(const unsigned char* in_nhwc, unsigned char* out_nhwc, int n, int h, int w, double clip_limit, int tiles_x,

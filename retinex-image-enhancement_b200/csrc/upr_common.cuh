@@ -1,6 +1,7 @@
 // upr_common.cuh -- shared device/host helpers for the sm_100a kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 
 #include "../../include/upretinex_b200.h"
@@ -30,6 +31,19 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs must set it
 // on each of them.  `mask` is one bit per device ordinal (benign race: the call is idempotent).
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, std::atomic<unsigned long long>& mask)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+// (plain-word overload for call sites that keep their own function-local static; same benign, idempotent race)
 template <typename Kernel>
 inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, unsigned long long& mask)
 {

@@ -509,11 +509,14 @@ struct MsLayout {
 
 static MsLayout ms_layout(int n, int h, int w)
 {
+    // tickets first, at an offset that does not depend on (n, h, w): the kernels leave them at zero, so a workspace that was
+    // zero-filled once can be reused for any later batch size or shape (with the tickets behind the n-dependent partial sums a
+    // call with another n found stale data where it expected clean tickets -- caught by the 2 x 1080p oracle test)
     MsLayout L;
     L.oh2 = int(h * 0.5); L.ow2 = int(w * 0.5); L.oh4 = int(h * 0.25); L.ow4 = int(w * 0.25);
-    L.off_partial = 0;
-    L.off_tickets = align_up(size_t(n) * kMsMaxParts * 3 * sizeof(double), 256);
-    L.off_half = align_up(L.off_tickets + size_t(n) * sizeof(unsigned), 256);
+    L.off_tickets = 0;
+    L.off_partial = align_up(size_t(65536) * sizeof(unsigned), 256);
+    L.off_half = align_up(L.off_partial + size_t(n) * kMsMaxParts * 3 * sizeof(double), 256);
     L.off_quar = align_up(L.off_half + size_t(n) * 3 * L.oh2 * L.ow2 * sizeof(float), 256);
     L.total = align_up(L.off_quar + size_t(n) * 3 * L.oh4 * L.ow4 * sizeof(float), 256);
     return L;

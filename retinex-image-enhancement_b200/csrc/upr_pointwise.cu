@@ -182,9 +182,74 @@ static int gain_launch(const float* enh, const float* gain, float* out, int n, i
     return UPR_OK;
 }
 
+// ---- save_image quantiser (enhancers/simple_enhance.py:65-100) -----------------------------------
+// [n][c][h][w] f32 -> [n][h][w][c] u8 with (clip(x, 0, 1) * 255).astype(uint8): fp32 product, truncation.  NaN clips to NaN and
+// casts to 0 on the host; fmaxf(NaN, 0) = 0 gives the same byte here.  c = 1 (illumination maps) or 3 (frames).  One thread
+// per 4 pixels: c 128-bit loads, 4c contiguous bytes stored.
+template <int C>
+__global__ void __launch_bounds__(kPwThreads)
+k_quantize_u8(const float* __restrict__ x, unsigned char* __restrict__ out, long long plane, long long items)
+{
+    const long long plane4 = plane / 4;
+    const long long stride = (long long)gridDim.x * kPwThreads;
+    for (long long it = (long long)blockIdx.x * kPwThreads + threadIdx.x; it < items; it += stride) {
+        const long long f = it / plane4, p = it - f * plane4;
+        unsigned q[C][4];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(x + (f * C + c) * plane) + p);
+            const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[c][k] = unsigned(__float2int_rz(__fmul_rn(fminf(fmaxf(a[k], 0.0f), 1.0f), 255.0f)));
+        }
+        unsigned char* o = out + (f * plane + p * 4) * C;
+        if (C == 1) {
+            *reinterpret_cast<unsigned*>(o) = q[0][0] | (q[0][1] << 8) | (q[0][2] << 16) | (q[0][3] << 24);
+        } else {
+            unsigned* o32 = reinterpret_cast<unsigned*>(o);   // 12 bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+            o32[0] = q[0][0] | (q[1][0] << 8) | (q[2][0] << 16) | (q[0][1] << 24);
+            o32[1] = q[1][1] | (q[2][1] << 8) | (q[0][2] << 16) | (q[1][2] << 24);
+            o32[2] = q[2][2] | (q[0][3] << 8) | (q[1][3] << 16) | (q[2][3] << 24);
+        }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kPwThreads)
+k_quantize_u8_scalar(const float* __restrict__ x, unsigned char* __restrict__ out, long long plane, long long items)
+{
+    const long long stride = (long long)gridDim.x * kPwThreads;
+    for (long long it = (long long)blockIdx.x * kPwThreads + threadIdx.x; it < items; it += stride) {
+        const long long f = it / plane, p = it - f * plane;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            out[it * C + c] = (unsigned char)__float2int_rz(__fmul_rn(fminf(fmaxf(x[(f * C + c) * plane + p], 0.0f), 1.0f), 255.0f));
+    }
+}
+
 }  // namespace upr
 
 extern "C" {
+
+int upr_quantize_u8_f32(const float* x_nchw, unsigned char* out_nhwc, int n, int c, int h, int w, upr_stream_t stream)
+{
+    if (n < 0 || h <= 0 || w <= 0 || (c != 1 && c != 3)) return UPR_E_SHAPE;
+    if (n == 0) return UPR_OK;
+    if (!x_nchw || !out_nhwc) return UPR_E_NULL;
+    auto s = static_cast<cudaStream_t>(stream);
+    const long long plane = (long long)h * w;
+    if (plane % 4 == 0 && upr::aligned16(x_nchw) && (reinterpret_cast<uintptr_t>(out_nhwc) & 3u) == 0) {
+        const long long items = (long long)n * (plane / 4);
+        if (c == 1) upr::k_quantize_u8<1><<<upr::pw_grid(items), upr::kPwThreads, 0, s>>>(x_nchw, out_nhwc, plane, items);
+        else upr::k_quantize_u8<3><<<upr::pw_grid(items), upr::kPwThreads, 0, s>>>(x_nchw, out_nhwc, plane, items);
+    } else {
+        const long long items = (long long)n * plane;
+        if (c == 1) upr::k_quantize_u8_scalar<1><<<upr::pw_grid(items), upr::kPwThreads, 0, s>>>(x_nchw, out_nhwc, plane, items);
+        else upr::k_quantize_u8_scalar<3><<<upr::pw_grid(items), upr::kPwThreads, 0, s>>>(x_nchw, out_nhwc, plane, items);
+    }
+    UPR_LAUNCH_CHECK();
+    return UPR_OK;
+}
 
 int upr_retinex_recombine_f32(const float* x, const float* illu, const float* e, float* refl, float* enh, int n, int h,
                               int w, float eps, upr_stream_t stream)

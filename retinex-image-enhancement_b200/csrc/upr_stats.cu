@@ -607,13 +607,18 @@ static int tex_parts(int n, long long items_per_image)
 struct TexLayout {
     size_t off_partial, off_tickets, off_mean, total;
 };
+// The ticket words come FIRST, at offsets that do not depend on the batch size: the kernels leave them at zero, and a
+// workspace that was zero-filled once may then be reused for ANY later batch size (a trainer's last, smaller batch).  With
+// the tickets behind the n-dependent partial sums, a call with a different n found stale partial sums where it expected
+// clean tickets and summed an incomplete set of partials.
+constexpr size_t kTicketRegionBytes = (size_t(65535) + 2) * sizeof(unsigned);   // n <= 65535 image tickets + 1 batch ticket
 static TexLayout tex_layout(int n)
 {
     TexLayout L;
-    L.off_partial = 0;
-    L.off_tickets = align_up(size_t(n) * 1024 * 2 * sizeof(double), 256);
-    L.off_mean = align_up(L.off_tickets + (size_t(n) + 1) * sizeof(unsigned), 256);
-    L.total = align_up(L.off_mean + size_t(n) * sizeof(double), 256);
+    L.off_tickets = 0;
+    L.off_mean = align_up(kTicketRegionBytes, 256);
+    L.off_partial = align_up(L.off_mean + size_t(n) * sizeof(double), 256);
+    L.total = align_up(L.off_partial + size_t(n) * 1024 * 2 * sizeof(double), 256);
     return L;
 }
 

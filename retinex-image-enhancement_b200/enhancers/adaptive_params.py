@@ -12,7 +12,11 @@ Documented deviations (none changes a numerical result):
   * ``apply_clahe_enhancement`` returns a contiguous tensor (the reference returns a permuted
     HWC view with the same values) and accepts ``keep_on_device=True`` to skip the D2H copy;
   * ``apply_adaptive_enhancement`` keeps everything on the device (the reference crosses PCIe
-    three times per image, adaptive_params.py:188/:136/:198).
+    three times per image, adaptive_params.py:188/:136/:198);
+  * the parameter dict the reference computes inside ``apply_adaptive_enhancement`` and never uses
+    (adaptive_params.py:185) is formed lazily: the histogram kernel is launched asynchronously on the
+    input, the 1 KB D2H copy and the rules run only if ``last_parameters()`` is called -- the enhance
+    call itself never synchronises with the host.
 """
 from __future__ import annotations
 
@@ -50,6 +54,7 @@ class AdaptiveParameterAdjuster:
             "brightness_boost": 1.0,
             "contrast_adjust": 1.0,
         }
+        self._pending_hist = None
 
     # -- a3 ------------------------------------------------------------------------------------
     def calculate_brightness_features(self, image_tensor):
@@ -79,6 +84,22 @@ class AdaptiveParameterAdjuster:
         params["color_balance"] = 1.2 if dark > 0.6 else (1.1 if dark > 0.3 else 1.0)
         return params
 
+    def note_input(self, image_tensor):
+        """What apply_adaptive_enhancement does with its input before the CNN (adaptive_params.py:185), without the host
+        round trip: the gray histogram is computed on the device, asynchronously; see ``last_parameters``."""
+        self._pending_hist = native.brightness_hist(image_tensor)
+
+    def last_parameters(self):
+        """The parameter dict(s) of the most recent apply_adaptive_enhancement input (this call copies 1 KB per image to the
+        host and therefore synchronises); None before the first call."""
+        if self._pending_hist is None:
+            return None
+        from . import _stats
+        import numpy as np
+        feats = _stats.features_from_histogram(self._pending_hist.cpu().numpy().astype(np.int64))
+        rules = [self._rules(f) for f in feats]
+        return rules[0] if len(rules) == 1 else rules
+
     # -- a1 ------------------------------------------------------------------------------------
     def apply_clahe_enhancement(self, image_tensor, keep_on_device: bool = False):
         image_tensor = _as_batch(image_tensor)
@@ -91,10 +112,10 @@ class AdaptiveParameterAdjuster:
 
     # -- a2 ------------------------------------------------------------------------------------
     def apply_adaptive_enhancement(self, model, image_tensor, device):
-        # The reference computes the parameter dict here and never uses it (adaptive_params.py:185);
-        # the histogram kernel is cheap, so the call is kept for API/behaviour parity.
+        # The reference computes the parameter dict here and never uses it (adaptive_params.py:185): the histogram kernel is
+        # launched (asynchronously), the dict is available from last_parameters() on demand.
         image_tensor = _to_device(_as_batch(image_tensor), device)
-        self.adjust_parameters(image_tensor)
+        self.note_input(image_tensor)
         with torch.no_grad():
             if hasattr(model, "forward_maps") and not getattr(model, "training", False):
                 # recombination (models/model.py:405-413,442) fused into the CLAHE histogram kernel: the `enhanced` frame

@@ -5,26 +5,32 @@ Reference (file:line relative to the reference tree): load_image :23-62, save_im
 :103-132, enhance_single_image :135-199, enhance_batch_images :202-250.
 
 B200-first differences:
-  * everything between ``load_image`` and ``save_image`` stays on the device: one H2D of the input, one D2H of the
-    two results (the reference crosses PCIe three times per image, adaptive_params.py:188/:136/:198);
-  * ``enhance_batch_images`` groups same-sized images into batches (``batch_size``) so that the classical kernels
-    run over many frames per launch, honours ``enable_multi_scale`` / ``enable_content_aware`` (the reference
-    silently drops them at :240) and, when launched with one process per GPU (torchrun), shards the file list by
-    rank -- frames are independent, there is no collective;
-  * ``enhance_single_image`` accepts ``adjuster=`` (the reference's main.py:246 passes it and crashes on the
-    missing parameter).
-File decoding / PNG encoding are host-side I/O (PIL), outside the hot path.
+  * frames cross PCIe as uint8 in BOTH directions: the decoded file goes up as it is (3 B/px) and is de-quantised /
+    letterboxed on the device (upr_letterbox_u8_f32); what comes back is the frame ``save_image`` would store, quantised
+    on the device -- by the CLAHE map kernel itself on the default path (upr_retinex_clahe_f32_u8 / upr_clahe_lab_f32_u8),
+    by upr_quantize_u8_f32 otherwise -- plus the 1 B/px illumination map.  The reference moves 12 B/px three times per
+    image (adaptive_params.py:188/:136/:198);
+  * ``enhance_batch_images`` is a three-stage pipeline: a thread pool decodes files ahead of the GPU into
+    host arrays, same-shaped frames are packed into pinned double-buffered staging and run as ONE device batch on a side
+    stream, and PNG encoding runs on a second thread pool that waits on the batch's CUDA event -- decode, GPU work and
+    encode of neighbouring batches overlap.  It honours ``enable_multi_scale`` / ``enable_content_aware`` (the reference
+    silently drops them at :240) and, launched with one process per GPU (torchrun), shards the file list by rank and binds
+    each rank to cuda:LOCAL_RANK -- frames are independent, there is no collective;
+  * ``enhance_single_image`` accepts ``adjuster=`` (the reference's main.py:246 passes it and crashes on the missing
+    parameter).
+File decoding / PNG encoding themselves stay PIL (an nvJPEG decode would not be bit-identical to the reference's).
 """
 from __future__ import annotations
 
 import os
 import time
+from collections import deque
 
 import numpy as np
 import torch
 
 from ..models.model import UP_Retinex
-from ..utils.letterbox import letterbox_tensor
+from ..utils.letterbox import letterbox_geometry, letterbox_tensor
 from .adaptive_params import AdaptiveParameterAdjuster
 from .content_aware import ContentAwareEnhancer
 from .multi_scale import MultiScaleEnhancer
@@ -32,28 +38,61 @@ from .multi_scale import MultiScaleEnhancer
 VALID_EXTENSIONS = {".jpg", ".jpeg", ".png", ".bmp", ".tif", ".tiff"}
 
 
+def bind_rank_to_gpu() -> str:
+    """One process per GPU (torchrun): bind this process to cuda:LOCAL_RANK (and to the CPU cores next to that GPU, so that
+    pinned staging buffers are first-touched on its NUMA node) and return the device string the drivers should use.  Without
+    LOCAL_RANK / WORLD_SIZE in the environment it is the current device."""
+    if not torch.cuda.is_available():
+        return "cpu"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or "LOCAL_RANK" in os.environ:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        count = torch.cuda.device_count()
+        if local >= count:
+            raise RuntimeError(f"LOCAL_RANK={local} but only {count} CUDA device(s) are visible: launch one process per GPU")
+        torch.cuda.set_device(local)
+        from .. import native
+        native.bind_to_gpu_numa_node(local)
+        return f"cuda:{local}"
+    return f"cuda:{torch.cuda.current_device()}"
+
+
+def resolve_device(device) -> str:
+    """'cuda' / None under torchrun -> this rank's own GPU; anything explicit ('cuda:3', 'cpu') is taken as given."""
+    if device is None or str(device) == "cuda":
+        return bind_rank_to_gpu() if torch.cuda.is_available() else (device or "cpu")
+    return str(device)
+
+
+def _decode_u8(image_path):
+    """File -> contiguous uint8 [H,W,3] array and the file's (W, H), decoded like the reference (PIL, RGB)."""
+    from PIL import Image
+    img = Image.open(image_path).convert("RGB")
+    return np.ascontiguousarray(np.asarray(img, dtype=np.uint8)), img.size
+
+
+def _geometry(h, w, max_size):
+    """(resized hw, (top, left), output hw) of the reference's letterbox call (enhancers/simple_enhance.py:43-58)."""
+    if max_size is None:
+        return (h, w), (0, 0), (h, w)
+    (rh, rw), (top, bottom, left, right), _, _ = letterbox_geometry(h, w, max_size, auto=True, scaleup=False)
+    return (rh, rw), (top, left), (rh + top + bottom, rw + left + right)
+
+
 def load_image(image_path, max_size=None, device=None):
     """-> ([1,3,H,W] f32 tensor in [0,1], (W, H) of the file).  Host tensor like the reference's by default.  With a CUDA
     ``device`` (what the drivers below pass) the decoded uint8 frame is uploaded as is -- 3 instead of 12 bytes per pixel
     over PCIe -- and de-quantised / letterboxed on the device (upr_letterbox_u8_f32; same values, bit for bit)."""
-    from PIL import Image
-    img = Image.open(image_path).convert("RGB")
-    original_size = img.size
+    arr, original_size = _decode_u8(image_path)
     if device is not None and torch.device(device).type == "cuda":
         from .. import native
-        from ..utils.letterbox import letterbox_geometry
-        u8 = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).unsqueeze(0)
-        h, w = u8.shape[1], u8.shape[2]
-        if max_size is None:
-            (rh, rw), (top, bottom, left, right) = (h, w), (0, 0, 0, 0)
-        else:
-            (rh, rw), (top, bottom, left, right), _, _ = letterbox_geometry(h, w, max_size, auto=True, scaleup=False)
+        u8 = torch.from_numpy(arr).unsqueeze(0)
+        (rh, rw), (top, left), out_hw = _geometry(u8.shape[1], u8.shape[2], max_size)
         dev = torch.device(device)
         with torch.cuda.device(dev):
-            t = native.letterbox(u8.pin_memory().to(dev, non_blocking=True), (rh, rw), top, left,
-                                 (rh + top + bottom, rw + left + right))
+            t = native.letterbox(u8.pin_memory().to(dev, non_blocking=True), (rh, rw), top, left, out_hw)
         return t, original_size
-    t = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).to(torch.float32) / 255.0
+    t = torch.from_numpy(arr).permute(2, 0, 1).to(torch.float32) / 255.0
     if max_size is not None:
         t, _, _ = letterbox_tensor(t, new_shape=max_size, auto=True, scaleup=False)
     # max_size None: letterbox to the image's own shape is the identity on a k/255 grid (see utils/letterbox.py)
@@ -62,18 +101,21 @@ def load_image(image_path, max_size=None, device=None):
 
 def _to_u8_hwc(tensor):
     """[1,C,H,W] / [C,H,W] f32 -> [H,W,3] uint8 array: (clip(x,0,1)*255).astype(uint8) as in the reference's save_image
-    (enhancers/simple_enhance.py:65-80).  A CUDA tensor is clipped, quantised and interleaved on the device, so only 3 bytes
-    per pixel cross PCIe (the same truncating cast; uint8 arrays pass through)."""
+    (enhancers/simple_enhance.py:65-80).  A CUDA tensor is clipped, quantised and interleaved by upr_quantize_u8_f32, so only
+    1 or 3 bytes per pixel cross PCIe (the same truncating cast; uint8 arrays pass through, single-channel ones tripled)."""
     if isinstance(tensor, np.ndarray):
-        return tensor
+        a = tensor
+        if a.ndim == 3 and a.shape[2] == 1:
+            a = np.repeat(a, 3, axis=2)
+        return a
     if tensor.dim() == 4:
         tensor = tensor.squeeze(0)
     t = tensor.detach().to(torch.float32)
     if t.is_cuda:
-        q = (t.clamp(0, 1) * 255).to(torch.uint8)
-        if q.shape[0] == 1:
-            q = q.expand(3, -1, -1)
-        return q.permute(1, 2, 0).contiguous().cpu().numpy()
+        from .. import native
+        with torch.cuda.device(t.device):
+            q = native.quantize_u8(t.unsqueeze(0).contiguous())[0].cpu().numpy()
+        return np.repeat(q, 3, axis=2) if q.shape[2] == 1 else q
     a = (np.clip(t.numpy(), 0, 1) * 255).astype(np.uint8)
     if a.shape[0] == 1:
         return np.stack([a[0]] * 3, axis=2)
@@ -101,10 +143,33 @@ def _enhance_tensor(model, img_low, device, enable_multi_scale, enable_content_a
     return (adjuster or AdaptiveParameterAdjuster()).apply_adaptive_enhancement(model, img_low, device)
 
 
+def enhance_frames_u8(model, low, enable_multi_scale=False, enable_content_aware=False, adjuster=None,
+                      out_enh=None, out_illu=None):
+    """The same dispatch with the STORED frames as the result: low [N,3,H,W] f32 CUDA -> (enhanced [N,H,W,3] u8,
+    illumination [N,H,W,1] u8), both on the device, exactly the bytes ``save_image`` would write for the f32 results of
+    ``_enhance_tensor``.  On the default (CLAHE) path the map kernel emits the u8 frame itself."""
+    from .. import native
+    with torch.no_grad():
+        if not (enable_content_aware or enable_multi_scale):
+            adj = adjuster or AdaptiveParameterAdjuster()
+            adj.note_input(low)
+            if hasattr(model, "forward_maps") and not getattr(model, "training", False):
+                illu, e_map = model.forward_maps(low)
+                enh8 = native.retinex_clahe_u8(low.contiguous(), illu.contiguous(), e_map.contiguous(), adj.CLIP_LIMIT, adj.TILE_GRID,
+                                               out=out_enh)
+            else:
+                enhanced, _refl, illu = model(low)
+                enh8 = native.clahe_lab_f32_u8(enhanced.contiguous(), adj.CLIP_LIMIT, adj.TILE_GRID, out=out_enh)
+        else:
+            enhanced, illu = _enhance_tensor(model, low, low.device, enable_multi_scale, enable_content_aware)
+            enh8 = native.quantize_u8(enhanced.contiguous(), out=out_enh)
+        illu8 = native.quantize_u8(illu.contiguous(), out=out_illu)
+    return enh8, illu8
+
+
 def _write_outputs(img_low, img_enhanced, illu_map, image_path, output_dir, pool=None):
     """The reference's three files per image (enhancers/simple_enhance.py:177-195).  Quantisation happens here (on the
-    device for CUDA tensors); with ``pool`` (a ThreadPoolExecutor) the PNG encoding runs on host threads while the GPU
-    works on the next batch."""
+    device for CUDA tensors); with ``pool`` (a ThreadPoolExecutor) the PNG encoding runs on host threads."""
     os.makedirs(output_dir, exist_ok=True)
     stem = os.path.splitext(os.path.basename(image_path))[0]
     low, enh, illu = _to_u8_hwc(img_low), _to_u8_hwc(img_enhanced), _to_u8_hwc(illu_map)
@@ -123,6 +188,7 @@ def _write_outputs(img_low, img_enhanced, illu_map, image_path, output_dir, pool
 def enhance_single_image(model, image_path, output_dir, device, max_size=None, enable_multi_scale=False,
                          enable_content_aware=False, adjuster=None):
     print(f"正在处理: {os.path.basename(image_path)}")
+    device = resolve_device(device)
     img_low, _original_size = load_image(image_path, max_size, device=device)
     start = time.time()
     img_enhanced, illu_map = _enhance_tensor(model, img_low, device, enable_multi_scale, enable_content_aware, adjuster)
@@ -147,8 +213,36 @@ def shard_for_rank(items, rank=None, world=None):
     return items[lo:hi]
 
 
+class _Staging:
+    """Two pinned (input u8, enhanced u8, illumination u8[, letterboxed input u8]) buffer sets per frame shape: while the
+    writers still read set k, the GPU fills set k^1.  A set is reused only after the PNG tasks that read it have finished."""
+
+    def __init__(self, batch_size):
+        self.batch_size = batch_size
+        self.sets = {}
+
+    def acquire(self, in_hw, out_hw, want_low):
+        key = (in_hw, out_hw, want_low)
+        ring = self.sets.setdefault(key, {"next": 0, "slots": [None, None]})
+        k = ring["next"]
+        ring["next"] = k ^ 1
+        slot = ring["slots"][k]
+        if slot is None:
+            b = self.batch_size
+            pin = lambda *shape: torch.empty(shape, dtype=torch.uint8, pin_memory=True)  # noqa: E731
+            slot = {"in": pin(b, in_hw[0], in_hw[1], 3), "enh": pin(b, out_hw[0], out_hw[1], 3), "illu": pin(b, out_hw[0], out_hw[1], 1),
+                    "low": pin(b, out_hw[0], out_hw[1], 3) if want_low else None, "readers": []}
+            ring["slots"][k] = slot
+        for fut in slot["readers"]:
+            fut.result()
+        slot["readers"] = []
+        return slot
+
+
 def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_multi_scale=False,
-                         enable_content_aware=False, batch_size=16, model=None):
+                         enable_content_aware=False, batch_size=16, model=None, decode_workers=None, encode_workers=None):
+    from concurrent.futures import ThreadPoolExecutor
+    device = resolve_device(device)
     print("正在加载模型...")
     if model is None:
         model = UP_Retinex().to(device).eval()
@@ -159,30 +253,104 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
     mine = shard_for_rank(files)
     print(f"找到 {len(files)} 个图像文件 (本进程处理 {len(mine)} 个)")
     t0 = time.time()
-    pending = []   # consecutive same-shape images form one device batch
-    from concurrent.futures import ThreadPoolExecutor
-    writers = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
-    futures = []
+    os.makedirs(output_dir, exist_ok=True)
+    on_gpu = torch.device(device).type == "cuda"
+    cores = os.cpu_count() or 1
+    decoders = ThreadPoolExecutor(max_workers=decode_workers or min(8, cores))
+    writers = ThreadPoolExecutor(max_workers=encode_workers or min(8, cores))
+    futures, last_write_of_stem = [], {}
 
-    def flush():
-        if not pending:
+    def submit_write(stem, task):
+        """PNG tasks of inputs that share a stem (a.jpg and a.png) target the same three files: chain them so that they are
+        written one after the other, in list order, like the reference's sequential loop (the last one wins)."""
+        prev = last_write_of_stem.get(stem)
+
+        def run():
+            if prev is not None:
+                prev.result()
+            task()
+        fut = writers.submit(run)
+        last_write_of_stem[stem] = fut
+        futures.append(fut)
+        return fut
+
+    def png_task(path, low8, enh8, illu8, event):
+        stem = os.path.splitext(os.path.basename(path))[0]
+
+        def task():
+            if event is not None:
+                event.synchronize()          # the batch's D2H copies have landed in the pinned buffers
+            save_image(enh8, os.path.join(output_dir, f"{stem}_enhanced.png"))
+            save_image(illu8, os.path.join(output_dir, f"{stem}_illumination.png"))
+            create_comparison(low8, enh8, os.path.join(output_dir, f"{stem}_comparison.png"))
+        return stem, task
+
+    staging = _Staging(batch_size)
+    stream = torch.cuda.Stream(device=device) if on_gpu else None
+
+    def run_batch(batch):
+        """batch: list of (path, u8 HWC array) of one shape."""
+        if not on_gpu:        # host tensors: the reference's own behaviour, one by one (the hot-path ops will refuse them)
+            for path, arr in batch:
+                low = torch.from_numpy(arr).permute(2, 0, 1).to(torch.float32).div(255.0).unsqueeze(0)
+                if max_size is not None:
+                    low = letterbox_tensor(low[0], new_shape=max_size, auto=True, scaleup=False)[0].unsqueeze(0)
+                enhanced, illu = _enhance_tensor(model, low, device, enable_multi_scale, enable_content_aware)
+                futures.append(_write_outputs(low, enhanced, illu, path, output_dir, pool=writers))
             return
-        batch = torch.cat([p[1] for p in pending], dim=0)
-        enhanced, illu = _enhance_tensor(model, batch, device, enable_multi_scale, enable_content_aware)
-        for i, (path, low) in enumerate(pending):
-            futures.append(_write_outputs(low, enhanced[i:i + 1], illu[i:i + 1], path, output_dir, pool=writers))
-        pending.clear()
+        from .. import native
+        b = len(batch)
+        h, w = batch[0][1].shape[:2]
+        (rh, rw), (top, left), out_hw = _geometry(h, w, max_size)
+        identity = out_hw == (h, w) and (rh, rw) == (h, w)
+        slot = staging.acquire((h, w), out_hw, not identity)
+        for i, (_p, arr) in enumerate(batch):
+            slot["in"][i].copy_(torch.from_numpy(arr))
+        dev = torch.device(device)
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
+            d_in = slot["in"][:b].to(dev, non_blocking=True)
+            low = native.letterbox(d_in, (rh, rw), top, left, out_hw)
+            enh8, illu8 = enhance_frames_u8(model, low, enable_multi_scale, enable_content_aware)
+            slot["enh"][:b].copy_(enh8, non_blocking=True)
+            slot["illu"][:b].copy_(illu8, non_blocking=True)
+            if not identity:
+                slot["low"][:b].copy_(native.quantize_u8(low), non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(stream)
+        for i, (path, arr) in enumerate(batch):
+            low8 = arr if identity else slot["low"][i].numpy()      # un-letterboxed: the decoded bytes ARE the stored input
+            stem, task = png_task(path, low8, slot["enh"][i].numpy(), slot["illu"][i].numpy(), event)
+            slot["readers"].append(submit_write(stem, task))
 
     try:
-        for path in mine:
-            low, _ = load_image(path, max_size, device=device)
-            if pending and (pending[0][1].shape != low.shape or len(pending) >= batch_size):
-                flush()
-            pending.append((path, low))
-        flush()
+        window = deque()
+        ahead = max(2 * batch_size, 4)
+        it = iter(mine)
+        pending = []            # consecutive same-shape frames form one device batch
+
+        def top_up():
+            while len(window) < ahead:
+                path = next(it, None)
+                if path is None:
+                    return
+                window.append((path, decoders.submit(_decode_u8, path)))
+
+        top_up()
+        while window:
+            path, fut = window.popleft()
+            arr, _size = fut.result()
+            top_up()
+            if pending and (pending[0][1].shape != arr.shape or len(pending) >= batch_size):
+                run_batch(pending)
+                pending = []
+            pending.append((path, arr))
+        if pending:
+            run_batch(pending)
         for fut in futures:
-            fut.result()
+            if fut is not None:
+                fut.result()
     finally:
+        decoders.shutdown(wait=True)
         writers.shutdown(wait=True)
     total = time.time() - t0
     print("=" * 50)

@@ -193,27 +193,36 @@ class _EnhLossesFn(torch.autograd.Function):
 class EnhancedImageLosses:
     """The three modules ``TotalLoss`` calls on the enhanced image (losses/loss.py:672, :674, :675) share one evaluation: the
     first of ``exposure`` / ``color`` / ``spatial`` that sees a new ``img_enhanced`` runs the fused kernels, the other two
-    read the same result (keyed on the tensor objects and the version counter of ``img_enhanced``)."""
+    read the same result.  The cache is keyed on the two tensor objects, their version counters AND whether autograd records
+    the evaluation (a value computed under ``torch.no_grad()`` must not be handed to a later grad-enabled call on the same
+    tensor); it is dropped as soon as all three terms have been served, so that it never pins the previous iteration's tensors
+    and autograd graph."""
 
     def __init__(self, patch_size: int = 16, base_target_exposure: float = 0.6):
         self.patch_size, self.base_target_exposure = patch_size, base_target_exposure
-        self._enh, self._low, self._versions, self._val = None, None, None, None
+        self.clear()
 
-    def evaluate(self, img_enhanced, img_low=None):
+    def evaluate(self, img_enhanced, img_low=None, index=None):
         # the cache keeps the two tensor OBJECTS alive and compares by identity + version counter (an id() alone could be
         # re-used by the next iteration's tensor once this one is freed)
         same_enh = self._enh is img_enhanced
         if img_low is None:
             img_low = self._low if (same_enh and self._low is not None) else img_enhanced
-        hit = same_enh and self._low is img_low and self._versions == (img_enhanced._version, img_low._version)
+        key = (img_enhanced._version, img_low._version, bool(torch.is_grad_enabled() and img_enhanced.requires_grad))
+        hit = same_enh and self._low is img_low and self._versions == key
         if not hit:
             self._val = _EnhLossesFn.apply(img_enhanced, img_low, float(self.base_target_exposure), int(self.patch_size))
-            self._enh, self._low, self._versions = img_enhanced, img_low, (img_enhanced._version, img_low._version)
-        return self._val
+            self._enh, self._low, self._versions, self._served = img_enhanced, img_low, key, set()
+        val = self._val
+        if index is not None:
+            self._served.add(index)
+            if len(self._served) == 3:
+                self.clear()
+        return val
 
     def clear(self):
         """Drop the cached evaluation (and the references to its tensors and autograd graph)."""
-        self._enh, self._low, self._versions, self._val = None, None, None, None
+        self._enh, self._low, self._versions, self._val, self._served = None, None, None, None, set()
 
     class _Term(torch.nn.Module):
         def __init__(self, owner, index, takes_low):
@@ -221,7 +230,7 @@ class EnhancedImageLosses:
             self._owner, self._index, self._takes_low = [owner], index, takes_low   # list: keep the owner out of nn.Module's registry
 
         def forward(self, img_enhanced, img_low=None):
-            return self._owner[0].evaluate(img_enhanced, img_low)[self._index]
+            return self._owner[0].evaluate(img_enhanced, img_low, self._index)[self._index]
 
     def exposure(self):
         """Drop-in for AdaptiveExposureLoss: forward(img_enhanced, img_low)."""

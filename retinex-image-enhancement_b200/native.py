@@ -45,6 +45,8 @@ def _declare(lib):
     lib.upr_clahe_lab_f32_u8.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, vp, sz, vp]
     lib.upr_retinex_clahe_f32.restype = i32
     lib.upr_retinex_clahe_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, C.c_float, f64, i32, i32, vp, sz, vp]
+    lib.upr_retinex_clahe_f32_u8.restype = i32
+    lib.upr_retinex_clahe_f32_u8.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, C.c_float, f64, i32, i32, vp, sz, vp]
     lib.upr_clahe_lab_stages_f32.restype = i32
     lib.upr_clahe_lab_stages_f32.argtypes = [vp, vp, i32, i32, i32, f64, i32, i32, vp, sz, i32, vp]
     lib.upr_clahe_debug_dump.restype = i32
@@ -77,6 +79,8 @@ def _declare(lib):
     lib.upr_attention_apply_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.upr_content_aware_apply_f32.restype = i32
     lib.upr_content_aware_apply_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+    lib.upr_quantize_u8_f32.restype = i32
+    lib.upr_quantize_u8_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.upr_retinex_recombine_f32.restype = i32
     lib.upr_retinex_recombine_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
     lib.upr_retinex_decompose_f32.restype = i32
@@ -432,6 +436,33 @@ def retinex_clahe(x: torch.Tensor, illu: torch.Tensor, e: torch.Tensor, clip_lim
     return out
 
 
+def retinex_clahe_u8(x: torch.Tensor, illu: torch.Tensor, e: torch.Tensor, clip_limit: float = 2.0,
+                     tiles: Tuple[int, int] = (8, 8), eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """retinex_clahe() emitting the packed u8 RGB frame [N,H,W,3] that save_image would store (upr_retinex_clahe_f32_u8)."""
+    x = _require_cuda_f32(x, "x"); illu = _require_cuda_f32(illu, "illu"); e = _require_cuda_f32(e, "e")
+    n, c, h, w = x.shape
+    if c != 3 or e.shape != x.shape or illu.numel() != n * h * w:
+        raise ValueError("expected x,e [N,3,H,W] and illu [N,1,H,W]")
+    tx, ty = int(tiles[0]), int(tiles[1])
+    if out is None:
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=x.device)
+    elif tuple(out.shape) != (n, h, w, 3) or not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous uint8 CUDA tensor [N,H,W,3]")
+    L = lib()
+    with torch.cuda.device(x.device):
+        nbytes = L.upr_clahe_workspace_bytes(n, h, w, tx, ty)
+        if nbytes == 0:
+            raise UprError(-2, "upr_clahe_workspace_bytes")
+        ws = workspace(nbytes, x.device)
+        args = (n, h, w, float(eps), float(clip_limit), tx, ty, ws.data_ptr(), ws.numel(), _stream())
+        rc = L.upr_retinex_clahe_f32_u8(x.data_ptr(), illu.data_ptr(), e.data_ptr(), out.data_ptr(), None, *args)
+        if rc == -3:   # ragged shape: the recombination needs a scratch frame
+            scratch = torch.empty_like(x)
+            rc = L.upr_retinex_clahe_f32_u8(x.data_ptr(), illu.data_ptr(), e.data_ptr(), out.data_ptr(), scratch.data_ptr(), *args)
+        check(rc, "upr_retinex_clahe_f32_u8")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # a6/a7: saliency / attention
 # ------------------------------------------------------------------------------------------------
@@ -504,6 +535,21 @@ def retinex_recombine(x: torch.Tensor, illu: torch.Tensor, e: torch.Tensor, want
                                               refl.data_ptr() if refl is not None else None, enh.data_ptr(), n, h, w,
                                               float(eps), _stream()), "upr_retinex_recombine_f32")
     return refl, enh
+
+
+def quantize_u8(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """save_image's (clip(x, 0, 1) * 255).astype(uint8) on the device: [N,C,H,W] f32 (C = 1 or 3) -> [N,H,W,C] u8."""
+    x = _require_cuda_f32(x, "x")
+    n, c, h, w = x.shape
+    if c not in (1, 3):
+        raise ValueError("expected 1 or 3 channels")
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.uint8, device=x.device)
+    elif tuple(out.shape) != (n, h, w, c) or not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous uint8 CUDA tensor [N,H,W,C]")
+    with torch.cuda.device(x.device):
+        check(lib().upr_quantize_u8_f32(x.data_ptr(), out.data_ptr(), n, c, h, w, _stream()), "upr_quantize_u8_f32")
+    return out
 
 
 def retinex_decompose(x: torch.Tensor, illu: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:

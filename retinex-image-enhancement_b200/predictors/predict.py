@@ -59,25 +59,44 @@ def predict_batch(model, input_dir, output_dir, device, max_size=None, save_comp
 
 
 def load_checkpoint(model, checkpoint_path, device):
-    """trainers/train.py:165-186 format: {'epoch', 'model_state_dict', 'optimizer_state_dict'}."""
+    """Checkpoints of the reference trainer (trainers/train.py:134-162): {'epoch', 'model_state_dict', 'optimizer_state_dict'};
+    a bare state_dict is accepted too.  The module tree of models/model.py mirrors the reference's, so its keys load strictly;
+    a checkpoint trained with other ``use_preact`` / ``use_aspp`` flags than the model was built with is reported as such."""
+    if not os.path.exists(checkpoint_path):
+        raise FileNotFoundError(f"Checkpoint not found: {checkpoint_path}")
     ckpt = torch.load(checkpoint_path, map_location=device)
-    model.load_state_dict(ckpt["model_state_dict"] if "model_state_dict" in ckpt else ckpt)
+    state = ckpt["model_state_dict"] if isinstance(ckpt, dict) and "model_state_dict" in ckpt else ckpt
+    try:
+        model.load_state_dict(state)
+    except RuntimeError as e:
+        has_aspp = any(".bottleneck.1.aspp_branches." in k for k in state)
+        has_preact = any(k.endswith("enc1.bn1.weight") and state[k].shape[0] == 32 for k in state)
+        raise RuntimeError(f"checkpoint {checkpoint_path} does not match the model's architecture flags: it looks like "
+                           f"use_preact={has_preact}, use_aspp={has_aspp} (pass --use_preact / --use_aspp accordingly). "
+                           f"Original error: {e}") from e
+    if isinstance(ckpt, dict) and "epoch" in ckpt:
+        print(f"Loaded checkpoint from epoch {ckpt['epoch']}")
     return model
 
 
 def main(argv=None):
     p = argparse.ArgumentParser(description="UP-Retinex Inference")
-    p.add_argument("--checkpoint", type=str, default=None)
+    p.add_argument("--checkpoint", type=str, required=True)
     p.add_argument("--input", type=str, required=True)
     p.add_argument("--output", type=str, default="./results")
     p.add_argument("--max_size", type=int, default=None)
     p.add_argument("--no_comparison", action="store_true")
     p.add_argument("--device", type=str, default=None)
     args = p.parse_args(argv)
+    from ..enhancers.simple_enhance import bind_rank_to_gpu
     device = args.device or ("cuda" if torch.cuda.is_available() else "cpu")
-    model = UP_Retinex().to(device).eval()
-    if args.checkpoint:
-        load_checkpoint(model, args.checkpoint, device)
+    if device == "cuda" and torch.cuda.is_available():
+        device = bind_rank_to_gpu()
+    model = UP_Retinex()
+    load_checkpoint(model, args.checkpoint, "cpu")       # predict.py:282-288: a missing checkpoint is an error
+    model = model.to(device).eval()
+    if not os.path.exists(args.input):
+        raise ValueError(f"Invalid input path: {args.input}")
     if os.path.isdir(args.input):
         predict_batch(model, args.input, args.output, device, args.max_size, not args.no_comparison)
     else:

@@ -135,30 +135,11 @@ def test_full_size_properties(native):
     assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
 
 
-# ---- kernel generations ----------------------------------------------------------------------------------
-def test_kernel_generations_bit_identical(native, monkeypatch):
-    """UPR_CLAHE_VARIANT selects earlier kernel generations (3: k_hist_lab_vec + k_map_vec, 4: k_hist_lab_vec2); the
-    production pair (k_hist_lab_vec3 + k_map_vec5) must give the same Lab planes, histograms, LUTs and output, bit for bit,
-    on the named shapes, on a batch, and on inputs that leave [0,1] (slow quantisation path of the newer histogram kernels)."""
-    rng = np.random.default_rng(7)
-    cases = [O.kat_input(3, 1080, 1920, "uniform"), O.kat_input(6, 2160, 3840, "dark"),
-             np.concatenate([O.kat_input(20 + i, 400, 600, k) for i, k in enumerate(["uniform", "dark", "ramp", "const"])]),
-             (rng.random((2, 3, 240, 320), dtype=np.float32) * 3.0 - 1.0).astype(np.float32)]
-    cases[3][0, 0, 5, 7] = np.nan
-    cases[3][1, 2, 9, 3] = np.inf
-    for x in cases:
-        res = {}
-        for v in ("0", "3", "4"):
-            monkeypatch.setenv("UPR_CLAHE_VARIANT", v)
-            res[v] = run_clahe(native, x)
-        for v in ("3", "4"):
-            for a, b in zip(res["0"], res[v]):
-                assert np.array_equal(a, b)
-
-
+# ---- strip / pass geometry of the column-owner histogram kernel --------------------------------------------------
 def test_tiles_wider_than_the_byte_counters_allow(native):
     """One row of a 65536-px tile is 64 four-pixel items per thread (> 63 = 252 px, the budget of the private byte counters
-    between flushes): such shapes must leave the vector path.  Strip geometry at the budget (tile 64512 px wide) stays on it."""
+    between flushes): such shapes must leave the vector path.  Strip geometry at the budget (tile 64512 px wide: 63 passes of
+    256 columns, one-row strips) stays on it."""
     for w in (8 * 65536, 2 * 64512):
         tiles = (8, 1) if w == 8 * 65536 else (2, 1)
         x = O.kat_input(400, 4, w, "const")        # worst case: every pixel of a thread lands in one bin
@@ -192,6 +173,43 @@ def test_retinex_clahe_fused_equals_composition(native, n, h, w, tiles):
     if h * w <= 400 * 600:
         _, e_ref = O.retinex_recombine(x[:1], illu[:1], e[:1])
         assert np.array_equal(got[:1].cpu().numpy(), O.clahe_lab(e_ref, 2.0, tiles))
+
+
+@pytest.mark.parametrize("n,h,w,tiles", [(1, 64, 4096, (2, 2)), (2, 48, 2400, (2, 4)), (1, 32, 1200, (1, 1)), (3, 40, 152, (2, 2)),
+                                          (1, 2160, 3840, (2, 2))])
+def test_column_passes_and_partial_occupancy(native, n, h, w, tiles):
+    """Tiles wider than 1024 px are walked in passes of 256 four-pixel columns (2048-px tiles: 2 passes; 1200: 2, the second
+    one partial); narrow tiles leave most threads of the CTA without a column (76-px tiles: 19 columns x 13 rows = 247 owners).
+    f32, packed u8 and fused-Retinex instantiations of the same kernel."""
+    rng = np.random.default_rng(n * h + w)
+    x = np.concatenate([O.kat_input(330 + i, h, w, ("uniform", "dark", "ramp")[i % 3]) for i in range(n)])
+    compare(native, x, 2.0, tiles)
+    x8 = torch.from_numpy(np.ascontiguousarray((x * 255).astype(np.uint8).transpose(0, 2, 3, 1))).cuda()
+    out8 = native.clahe_lab_u8(x8, 2.0, tiles).cpu().numpy()
+    for i in range(n):
+        ref = O.clahe_lab(x8[i].cpu().numpy().transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255.0), 2.0, tiles)
+        assert np.array_equal(out8[i].transpose(2, 0, 1).astype(np.float32) / np.float32(255.0), ref[0])
+    e = rng.random((n, 3, h, w), dtype=np.float32)
+    illu = (rng.random((n, 1, h, w), dtype=np.float32) * 0.9 + 0.05).astype(np.float32)
+    xd, ed, id_ = (torch.from_numpy(a).cuda() for a in (x, e, illu))
+    got = native.retinex_clahe(xd, id_, ed, 2.0, tiles).cpu().numpy()
+    _, e_ref = O.retinex_recombine(x, illu, e)
+    for i in range(n):
+        assert np.array_equal(got[i:i + 1], O.clahe_lab(e_ref[i:i + 1], 2.0, tiles))
+
+
+def test_retinex_clahe_u8_output(native):
+    """upr_retinex_clahe_f32_u8 == upr_retinex_clahe_f32 followed by save_image's truncating cast (vector path; ragged shapes
+    through the caller's scratch frame)."""
+    rng = np.random.default_rng(77)
+    for n, h, w in ((2, 1080, 1920), (3, 400, 600), (1, 403, 601)):
+        x = np.concatenate([O.kat_input(840 + i, h, w, ("dark", "uniform")[i % 2]) for i in range(n)])
+        e = rng.random((n, 3, h, w), dtype=np.float32)
+        illu = (rng.random((n, 1, h, w), dtype=np.float32) * 0.9 + 0.05).astype(np.float32)
+        xd, ed, id_ = (torch.from_numpy(a).cuda() for a in (x, e, illu))
+        ref = native.retinex_clahe(xd, id_, ed)
+        want = (ref.clamp(0, 1) * 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        assert torch.equal(native.retinex_clahe_u8(xd, id_, ed), want)
 
 
 def test_second_device_same_process(native):

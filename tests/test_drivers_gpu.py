@@ -88,6 +88,89 @@ def test_predict_and_cli(cuda, tmp_path):
     assert os.path.exists(tmp_path / "cli" / "p_enhanced.png")           # single-file mode works (reference: TypeError)
     cli.simple_enhance_main(["--input", str(tmp_path / "p.png"), "--output", str(tmp_path / "cli2"), "--content_aware"])
     assert os.path.exists(tmp_path / "cli2" / "p_illumination.png")
+    # predict mode refuses to run without a checkpoint file (main.py:152-157) instead of writing the output of random weights
+    rc = cli.main(["--mode", "predict", "--input_path", str(tmp_path / "p.png"), "--output_dir", str(tmp_path / "nockpt"),
+                   "--checkpoint", str(tmp_path / "missing.pth")])
+    assert rc == 1 and not os.path.exists(tmp_path / "nockpt" / "p_enhanced.png")
+    # ... and loads the trainer's checkpoint format (trainers/train.py:134-162) into the same module tree
+    from retinex_image_enhancement_b200.models.model import UP_Retinex
+    torch.manual_seed(9)
+    trained = UP_Retinex(use_preact=False, use_aspp=False)
+    torch.save({"epoch": 7, "model_state_dict": trained.state_dict(), "optimizer_state_dict": {}}, tmp_path / "best_model.pth")
+    rc = cli.main(["--mode", "predict", "--input_path", str(tmp_path / "p.png"), "--output_dir", str(tmp_path / "ckpt"),
+                   "--checkpoint", str(tmp_path / "best_model.pth")])
+    assert rc == 0 and os.path.exists(tmp_path / "ckpt" / "p_enhanced.png")
+    x = torch.from_numpy((_read_png(tmp_path / "p.png").astype(np.float32) / np.float32(255.0)).transpose(2, 0, 1)[None]).cuda()
+    with torch.no_grad():
+        want = trained.cuda().eval()(x)[0]
+    assert np.array_equal(_read_png(tmp_path / "ckpt" / "p_enhanced.png"),
+                          (want.clamp(0, 1) * 255).to(torch.uint8)[0].permute(1, 2, 0).cpu().numpy())
+    with pytest.raises(RuntimeError, match="use_preact"):                 # architecture flags that do not match the checkpoint
+        cli.main(["--mode", "predict", "--input_path", str(tmp_path / "p.png"), "--output_dir", str(tmp_path / "ckpt2"),
+                  "--checkpoint", str(tmp_path / "best_model.pth"), "--use_preact"])
+
+
+def test_batch_driver_pipeline(cuda, tmp_path):
+    """enhance_batch_images: decode prefetch -> pinned staging -> one device batch per shape group -> u8 results -> PNG pool.
+    Inputs that share a stem are written one after the other (the last one in list order wins, like the reference's loop);
+    --max_size letterboxes on the device; the fused Retinex + CLAHE + u8 kernel serves models with forward_maps()."""
+    from retinex_image_enhancement_b200.enhancers.simple_enhance import (enhance_batch_images, enhance_frames_u8,
+                                                                         enhance_single_image, load_image)
+    from retinex_image_enhancement_b200.models.model import UP_Retinex
+    from PIL import Image
+    src = tmp_path / "in"
+    src.mkdir()
+    for i in range(7):
+        _write_png(str(src / f"f{i}.png"), 128, 192, 40 + i)
+    dup = np.random.default_rng(50).integers(0, 200, (128, 192, 3), dtype=np.uint8)
+    Image.fromarray(dup).save(src / "f3.bmp")                 # same stem as f3.png; sorted order: f3.bmp, f3.png -> the png wins
+    _write_png(str(src / "wide.png"), 160, 640, 60)
+    torch.manual_seed(3)
+    model = UP_Retinex(use_preact=False, use_aspp=False).to(cuda).eval()
+    enhance_batch_images(str(src), str(tmp_path / "out"), cuda, model=model, batch_size=3)
+    for name in [f"f{i}" for i in range(7)] + ["wide"]:
+        low, _ = load_image(str(src / f"{name}.png"), device=cuda)
+        enh8, illu8 = enhance_frames_u8(model, low)
+        assert np.array_equal(_read_png(tmp_path / "out" / f"{name}_enhanced.png"), enh8[0].cpu().numpy()), name
+        assert np.array_equal(_read_png(tmp_path / "out" / f"{name}_illumination.png")[:, :, :1], illu8[0].cpu().numpy()), name
+        cmp_img = _read_png(tmp_path / "out" / f"{name}_comparison.png")
+        assert np.array_equal(cmp_img[:, : cmp_img.shape[1] // 2], _read_png(src / f"{name}.png"))
+    # the batch driver's bytes are the single-image driver's bytes
+    enhance_single_image(model, str(src / "f5.png"), str(tmp_path / "single"), cuda)
+    assert np.array_equal(_read_png(tmp_path / "single" / "f5_enhanced.png"), _read_png(tmp_path / "out" / "f5_enhanced.png"))
+    # --max_size: letterbox (down-scale + 114 border to a multiple of 32) on the device, same bytes as the single-image path
+    enhance_batch_images(str(src), str(tmp_path / "lb"), cuda, max_size=96, model=model, batch_size=4)
+    enhance_single_image(model, str(src / "wide.png"), str(tmp_path / "lb1"), cuda, max_size=96)
+    assert np.array_equal(_read_png(tmp_path / "lb" / "wide_enhanced.png"), _read_png(tmp_path / "lb1" / "wide_enhanced.png"))
+    assert np.array_equal(_read_png(tmp_path / "lb" / "wide_comparison.png"), _read_png(tmp_path / "lb1" / "wide_comparison.png"))
+
+
+def test_adaptive_parameters_are_lazy(cuda):
+    from retinex_image_enhancement_b200.enhancers.adaptive_params import AdaptiveParameterAdjuster
+    adj = AdaptiveParameterAdjuster()
+    assert adj.last_parameters() is None
+    x = torch.from_numpy(O.kat_input(2, 400, 600, "dark"))
+    adj.apply_adaptive_enhancement(StubModel(), x, cuda)
+    assert adj.last_parameters() == O.adjust_parameters(x.numpy()) == adj.adjust_parameters(x)
+
+
+def test_ranks_bind_to_their_own_gpu(cuda, monkeypatch):
+    from retinex_image_enhancement_b200.enhancers import simple_enhance as S
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    assert S.resolve_device("cuda") == f"cuda:{torch.cuda.current_device()}" and S.resolve_device("cuda:0") == "cuda:0"
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("LOCAL_RANK", str(torch.cuda.device_count()))
+    with pytest.raises(RuntimeError, match="LOCAL_RANK"):
+        S.bind_rank_to_gpu()
+    if torch.cuda.device_count() >= 2:
+        before = torch.cuda.current_device()
+        monkeypatch.setenv("LOCAL_RANK", "1")
+        try:
+            assert S.resolve_device("cuda") == "cuda:1" and torch.cuda.current_device() == 1
+            assert torch.zeros(1, device=S.resolve_device(None)).device.index == 1
+        finally:
+            torch.cuda.set_device(before)
 
 
 def test_model_inference_uses_fused_recombine(cuda):

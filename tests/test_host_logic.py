@@ -63,6 +63,64 @@ def test_cli_flags_of_the_reference_are_accepted():
     assert a.mode == "enhance" and a.multi_scale and a.content_aware and a.max_size == 512 and unknown == ["--batch_size", "8"]
 
 
+def test_rank_to_gpu_binding_logic(monkeypatch):
+    """cli._device / resolve_device under torchrun: rank r of a node works on cuda:LOCAL_RANK (CPU container: torch.cuda is
+    faked; the real two-GPU check is tests/test_drivers_gpu.py::test_ranks_bind_to_their_own_gpu)."""
+    from retinex_image_enhancement_b200 import cli, native
+    from retinex_image_enhancement_b200.enhancers import simple_enhance as S
+    calls = []
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "device_count", lambda: 8)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: calls.append(d))
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(native, "bind_to_gpu_numa_node", lambda d: True)
+    for rank in (0, 5):
+        monkeypatch.setenv("WORLD_SIZE", "8")
+        monkeypatch.setenv("LOCAL_RANK", str(rank))
+        assert cli._device(None) == f"cuda:{rank}" and S.resolve_device("cuda") == f"cuda:{rank}"
+        assert calls[-1] == rank
+    assert S.resolve_device("cuda:3") == "cuda:3" and S.resolve_device("cpu") == "cpu"
+    monkeypatch.delenv("WORLD_SIZE")
+    monkeypatch.delenv("LOCAL_RANK")
+    assert S.resolve_device(None) == "cuda:0"
+
+
+def test_cli_defaults_are_the_references(tmp_path, capsys):
+    """main.py:29-44: --mode predict, --input_path ./data/test, --checkpoint ./checkpoints/best_model.pth; predict mode without
+    the checkpoint file prints the reference's message and does nothing (main.py:152-157)."""
+    from retinex_image_enhancement_b200 import cli
+    a = cli.build_main_parser().parse_args([])
+    assert (a.mode, a.input_path, a.checkpoint, a.output_dir) == ("predict", "./data/test", "./checkpoints/best_model.pth", "./results")
+    assert cli.main(["--checkpoint", str(tmp_path / "nope.pth"), "--output_dir", str(tmp_path / "o")]) == 1
+    assert "找不到模型检查点文件" in capsys.readouterr().out and not (tmp_path / "o").exists()
+    with pytest.raises(SystemExit):
+        cli.main(["--mode", "enhance", "--input_path", str(tmp_path / "missing_dir")])
+
+
+def test_enh_losses_cache_is_keyed_on_grad_mode_and_released(monkeypatch):
+    """EnhancedImageLosses: an evaluation made under no_grad is not handed to a grad-enabled call on the same tensor, and the
+    cache lets go of its tensors once the three terms have been served (kernels faked: CPU container)."""
+    from retinex_image_enhancement_b200.losses import loss as L
+    n_eval = []
+
+    class FakeFn:
+        @staticmethod
+        def apply(e, l, base, patch):
+            n_eval.append(torch.is_grad_enabled())
+            v = e.sum() * 0 + len(n_eval)
+            return v, v, v
+    monkeypatch.setattr(L, "_EnhLossesFn", FakeFn)
+    fused = L.EnhancedImageLosses()
+    t_exp, t_col, t_spa = fused.exposure(), fused.color(), fused.spatial()
+    e, low = torch.rand(1, 3, 8, 8, requires_grad=True), torch.rand(1, 3, 8, 8)
+    with torch.no_grad():
+        a = t_exp(e, low)
+    b = t_exp(e, low)                       # grad mode changed -> new evaluation
+    assert n_eval == [False, True] and a.item() == 1.0 and b.detach().item() == 2.0
+    assert t_col(e).detach().item() == 2.0 and t_spa(e, low).detach().item() == 2.0 and len(n_eval) == 2    # shared
+    assert fused._enh is None and fused._val is None          # all three served -> released
+
+
 def test_model_contract_training_path_on_cpu():
     from retinex_image_enhancement_b200.models.model import UP_Retinex, retinex_recombine
     m = UP_Retinex(use_preact=False, use_aspp=False)
@@ -158,3 +216,65 @@ def test_accelerate_reference_total_loss_patches_the_real_class(monkeypatch):
     assert type(total.exposure_loss).__name__ == type(total.color_loss).__name__ == type(total.spatial_loss).__name__ == "_Term"
     assert total.exposure_loss._owner[0] is total.color_loss._owner[0] is total.spatial_loss._owner[0]
     assert (total.exposure_loss._owner[0].patch_size, total.exposure_loss._owner[0].base_target_exposure) == (16, 0.6)
+
+
+def _reference_model_module(monkeypatch):
+    ref = os.environ.get("UPR_REFERENCE", "/root/reference")
+    if not os.path.isfile(os.path.join(ref, "models", "model.py")):
+        pytest.skip("reference tree not present")
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("upr_ref_model", os.path.join(ref, "models", "model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    monkeypatch.setitem(sys.modules, "upr_ref_model", mod)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("use_preact,use_aspp", [(False, False), (True, True)])
+def test_model_matches_reference_class(monkeypatch, use_preact, use_aspp):
+    """Build container only: this package's UP_Retinex has the reference's module tree -- a state_dict of the unmodified class
+    loads with strict=True (the trainer's checkpoint format, trainers/train.py:134-162) and the forward pass reproduces the
+    reference's three outputs bit for bit (stock torch ops on both sides: CPU, autograd enabled)."""
+    mod = _reference_model_module(monkeypatch)
+    from retinex_image_enhancement_b200.models.model import UP_Retinex, count_parameters
+    torch.manual_seed(5)
+    theirs = mod.UP_Retinex(use_preact=use_preact, use_aspp=use_aspp).eval()
+    for m in theirs.modules():                      # non-trivial batch-norm statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.uniform_(-0.2, 0.2); m.running_var.uniform_(0.5, 1.5)
+    ours = UP_Retinex(use_preact=use_preact, use_aspp=use_aspp).eval()
+    sd = theirs.state_dict()
+    assert list(ours.state_dict().keys()) == list(sd.keys())
+    assert all(ours.state_dict()[k].shape == v.shape for k, v in sd.items())
+    ours.load_state_dict({"epoch": 3, "model_state_dict": sd}["model_state_dict"], strict=True)
+    assert count_parameters(ours) == mod.count_parameters(theirs)
+    x = torch.rand(2, 3, 64, 96, requires_grad=True)
+    got, want = ours(x), theirs(x)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    illu, e = ours.forward_maps(x)
+    assert torch.equal(illu, want[2]) and e.shape == x.shape
+
+
+def test_accelerate_reference_model_on_the_real_class(monkeypatch):
+    """accelerate_reference_model gives the unmodified reference class forward_maps() (what the fused Retinex + CLAHE entry needs)
+    and leaves its autograd behaviour untouched; the recombination of forward_maps' outputs is the class's own `enhanced`."""
+    mod = _reference_model_module(monkeypatch)
+    from retinex_image_enhancement_b200.models.model import accelerate_reference_model
+    torch.manual_seed(6)
+    theirs = mod.UP_Retinex(use_preact=False, use_aspp=False).eval()
+    x = torch.rand(1, 3, 48, 64, requires_grad=True)
+    want = [t.detach().clone() for t in theirs(x)]
+    acc = accelerate_reference_model(theirs)
+    assert acc is theirs
+    got = acc(x)                                    # autograd on: stock ops, same numbers
+    for a, b in zip(got, want):
+        assert torch.equal(a.detach(), b)
+    illu, e = acc.forward_maps(x)
+    r = x / (illu + 1e-6)
+    assert torch.equal(illu.detach(), want[2]) and torch.equal((r * e + (1 - r) * e ** 2).detach(), want[0])
+    with torch.no_grad(), pytest.raises(RuntimeError):   # inference takes the kernel: CUDA tensors only
+        acc(x.detach())
+    with pytest.raises(TypeError):
+        accelerate_reference_model(torch.nn.Linear(2, 2))

@@ -251,42 +251,68 @@ def test_clahe_host_entry(native):
     assert native.lib().upr_host_pool_release() == 0
 
 
-# ---- streaming kernels vs the first-generation tile kernels ----------------------------------------------
+# ---- the BASELINE shapes (1080p, 4K) and awkward band / segment geometries against the oracle: full maps ---------------
+def _frames(n, h, w, base):
+    return np.concatenate([O.kat_input(base + i, h, w, ("uniform", "dark", "ramp")[i % 3]) for i in range(n)])
+
+
 @pytest.mark.parametrize("n,h,w", [(1, 2160, 3840), (2, 1080, 1920), (3, 400, 600), (1, 64, 120), (1, 8, 8), (2, 68, 244), (1, 128, 4096)])
-def test_multiscale_stream_vs_tile_kernel(native, monkeypatch, n, h, w):
-    """k_ms_stream (warp per band/segment) against k_ms_fused (tile kernel, UPR_MS_VARIANT=1) and, for small shapes, the oracle:
-    band edges (w not a multiple of 120), segment edges, one-sided differences on all four borders, batches."""
-    x = np.concatenate([O.kat_input(500 + i, h, w, ("uniform", "dark", "ramp")[i % 3]) for i in range(n)])
-    xd = dev(x)
-    monkeypatch.setenv("UPR_MS_VARIANT", "0")
-    m0, g0 = native.multiscale_stats(xd)
-    monkeypatch.setenv("UPR_MS_VARIANT", "1")
-    m1, g1 = native.multiscale_stats(xd)
-    np.testing.assert_allclose(m0.cpu().numpy(), m1.cpu().numpy(), rtol=2e-6)
-    np.testing.assert_allclose(g0.cpu().numpy(), g1.cpu().numpy(), rtol=2e-7)
-    if h * w <= 400 * 600:
-        for i in range(n):
-            m_ref, f_ref = O.multiscale_means(x[i:i + 1])
-            np.testing.assert_allclose(m0.cpu().numpy()[i], m_ref, rtol=2e-6)
-            assert abs(float(g0[i]) - f_ref) <= 2e-7
+def test_multiscale_full_shapes_vs_oracle(native, n, h, w):
+    """upr_multiscale_stats_f32 against the oracle at the BASELINE shapes and at band edges (w not a multiple of 120), segment
+    edges, one-sided differences on all four borders, batches.  Stated bound 1e-4 relative; achieved 2e-6."""
+    x = _frames(n, h, w, 500)
+    m, g = native.multiscale_stats(dev(x))
+    m, g = m.cpu().numpy(), g.cpu().numpy()
+    for i in range(n):
+        m_ref, f_ref = O.multiscale_means(x[i:i + 1])
+        np.testing.assert_allclose(m[i], m_ref, rtol=2e-6)
+        assert abs(float(g[i]) - f_ref) <= 2e-7 * f_ref + 6e-8
 
 
 @pytest.mark.parametrize("n,h,w", [(1, 2160, 3840), (2, 1080, 1920), (2, 70, 250), (1, 33, 481), (1, 3, 9), (1, 600, 17), (1, 20, 243)])
-def test_saliency_stream_vs_tile_kernel(native, monkeypatch, n, h, w):
-    """k_saliency_stream (fp32, vertical-then-horizontal) against k_saliency_blur (fp64 tile kernel, UPR_SAL_VARIANT=1):
-    band edges (w not a multiple of 240, lanes that straddle the right border), reflect-101 on narrow/short images,
-    row segments, batches.  Same bound as against the oracle."""
+def test_saliency_attention_full_shapes_vs_oracle(native, n, h, w):
+    """upr_saliency_f32 / upr_attention_f32 / upr_content_aware_apply_f32 against the oracle, FULL maps, at the BASELINE shapes
+    and at band edges (w not a multiple of the band width, lanes that straddle the right border), reflect-101 on narrow / short
+    images, row segments, batches.  The maps are normalised to [0,1]; stated bound 1e-4, achieved: saliency 1e-6
+    (2e-6 at 4K), attention 2e-6 (4e-6 at 4K) absolute -- the blur runs in fp32, the reference's in fp64."""
     x = np.concatenate([O.kat_input(600 + i, h, w, ("uniform", "dark")[i % 2]) for i in range(n)])
+    enh = np.random.default_rng(h + w).random((n, 3, h, w), dtype=np.float32) * np.float32(1.2)
     xd = dev(x)
-    monkeypatch.setenv("UPR_SAL_VARIANT", "0")
-    s0, a0 = native.saliency(xd).cpu().numpy(), native.attention(xd).cpu().numpy()
-    monkeypatch.setenv("UPR_SAL_VARIANT", "1")
-    s1, a1 = native.saliency(xd).cpu().numpy(), native.attention(xd).cpu().numpy()
-    np.testing.assert_allclose(s0, s1, rtol=0, atol=1e-6)
-    np.testing.assert_allclose(a0, a1, rtol=0, atol=2e-6)
-    if h * w <= 70 * 250:
+    sal, att = native.saliency(xd).cpu().numpy(), native.attention(xd).cpu().numpy()
+    out, att2 = native.content_aware_apply(xd, dev(enh), want_attention=True)
+    out, att2 = out.cpu().numpy(), att2.cpu().numpy()
+    big = h * w > 1080 * 1920
+    for i in range(n):
+        s_ref, a_ref = O.saliency(x[i:i + 1]), O.attention(x[i:i + 1])
+        np.testing.assert_allclose(sal[i:i + 1], s_ref, rtol=0, atol=2e-6 if big else 1e-6)
+        np.testing.assert_allclose(att[i:i + 1], a_ref, rtol=0, atol=4e-6 if big else 2e-6)
+        np.testing.assert_allclose(att2[i:i + 1], a_ref, rtol=0, atol=4e-6 if big else 2e-6)
+        np.testing.assert_allclose(out[i:i + 1], O.attention_apply(enh[i], a_ref), rtol=0, atol=2e-6)
+
+
+def test_zeroed_once_workspaces_survive_shape_and_batch_changes(native):
+    """The ticket words of the multi-scale and texture workspaces sit at offsets that do not depend on the batch size, so ONE
+    zero-filled workspace serves any sequence of shapes / batch sizes (a trainer's last, smaller batch; the generic path, which
+    parks half- and quarter-resolution images in the same buffer).  Round 1 kept the tickets behind the n-dependent partial sums
+    and summed an incomplete set of partials after such a change (3e-4 relative on 2 x 1080p)."""
+    big = _frames(1, 512, 768, 900)
+    native.multiscale_stats(dev(big), force_generic=True)         # dirties the half / quarter image area
+    native.multiscale_stats(dev(big))
+    for n, h, w in ((3, 256, 360), (2, 1080, 1920), (1, 256, 360), (5, 64, 120)):
+        x = _frames(n, h, w, 910 + n)
+        m = native.multiscale_stats(dev(x))[0].cpu().numpy()
         for i in range(n):
-            np.testing.assert_allclose(s0[i], O.saliency(x[i:i + 1])[0], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(m[i], O.multiscale_means(x[i:i + 1])[0], rtol=2e-6)
+    rng = np.random.default_rng(920)
+    for b in (8, 3, 11, 1, 8):
+        a = rng.random((b, 3, 96, 128), dtype=np.float32)
+        for method, ref in (("tv", O.texture_tv(a)), ("edge_density", O.texture_edge_density(a))):
+            got, stats = native.texture_complexity(dev(a), method, want_batch_stats=True)
+            if method == "tv":
+                np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=2e-6)
+            else:
+                assert np.abs(got.cpu().numpy() - ref).max() <= 4.0 / (96 * 128)
+            assert float(stats[1]) == b and abs(float(stats[0]) - float(got.double().sum())) <= 1e-5 * b
 
 
 def test_saliency_out_of_range_inputs(native):

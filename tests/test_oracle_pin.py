@@ -165,6 +165,32 @@ def test_golden_content(golden, small_cases):
             np.testing.assert_allclose(att[0, 0], small_cases[f"att_{rec['seed']}"], rtol=0, atol=2e-7)
 
 
+def test_golden_natural_images(natural):
+    """The oracle on crops of the reference's own photographs against what the unmodified reference computed on them."""
+    from conftest import natural_input
+    meta, arrays = natural
+    sub = meta["sub"]
+    for rec in meta["cases"]:
+        x = natural_input(arrays, rec["name"])
+        assert sha(x) == rec["sha_in"]
+        out = O.clahe_lab(x)
+        assert sha(out) == rec["clahe"]["sha_out"], rec["name"]
+        f = O.brightness_features(x)
+        for k, v in rec["bright"]["features"].items():
+            assert abs(f[k] - v) <= 1e-12, (rec["name"], k)
+        assert O.adjust_parameters(x) == rec["bright"]["params"]
+        m, fac = O.multiscale_means(x)
+        np.testing.assert_allclose(m, rec["multiscale"]["means"], rtol=2e-6)
+        assert abs(fac - rec["multiscale"]["factor"]) <= 2e-7
+        sal, att = O.saliency(x), O.attention(x)
+        np.testing.assert_allclose(sal[0, 0, ::sub, ::sub], arrays[f"{rec['name']}_sal_sub"], rtol=0, atol=2e-7)
+        np.testing.assert_allclose(att[0, 0, ::sub, ::sub], arrays[f"{rec['name']}_att_sub"], rtol=0, atol=4e-7)
+        assert int(sal.argmax()) == rec["content"]["sal_argmax"] and int(att.argmax()) == rec["content"]["att_argmax"]
+        assert abs(float(sal.astype(np.float64).mean()) - rec["content"]["sal_mean"]) <= 1e-7
+        assert abs(float(O.texture_tv(x)[0]) - rec["texture"]["tv"]) <= 2e-6 * rec["texture"]["tv"]
+        assert abs(float(O.texture_edge_density(x)[0]) - rec["texture"]["edge_density"]) <= 4.0 / (rec["h"] * rec["w"])
+
+
 def test_golden_retinex(small_cases):
     refl, enh = O.retinex_recombine(small_cases["retinex_x"], small_cases["retinex_illu"], small_cases["retinex_e"])
     assert np.array_equal(refl, small_cases["retinex_refl"])
