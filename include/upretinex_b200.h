@@ -165,6 +165,13 @@ UPR_API int upr_attention_apply_f32(const float* enh, const float* att_n1hw, flo
  * upr_attention_f32 followed by upr_attention_apply_f32. */
 UPR_API int upr_content_aware_apply_f32(const float* x_nchw, const float* enh_nchw, float* out_nchw, float* att_n1hw, int n,
                                         int h, int w, void* workspace, size_t workspace_bytes, upr_stream_t stream);
+/* BASELINE config 5, "content-aware + multi-scale": both gains of the reference's two enhancers applied to the CNN output in
+ * ONE epilogue -- out = clamp(clamp(enh * (1 + 0.2 att(x)), 0, 1) * gain[image], 0, 1), i.e. content_aware.py:119-120 followed
+ * by multi_scale.py:97-98 -- with gain_per_image from upr_multiscale_stats_f32 on the same input (device memory, no host
+ * visit).  Same workspace and attention output as upr_content_aware_apply_f32. */
+UPR_API int upr_content_multiscale_apply_f32(const float* x_nchw, const float* enh_nchw, const float* ms_gain_per_image,
+                                             float* out_nchw, float* att_n1hw, int n, int h, int w, void* workspace,
+                                             size_t workspace_bytes, upr_stream_t stream);
 
 /* The quantiser of save_image (enhancers/simple_enhance.py:65-100), on the device: [n][c][h][w] f32 -> [n][h][w][c] u8 with
  * (clip(x, 0, 1) * 255).astype(uint8) -- fp32 product, truncation; c = 1 (illumination maps) or 3 (frames).  What the batch

@@ -313,7 +313,6 @@ static int gauss_launch(const float* x, float* out, int planes, int h, int w, co
     CUtensorMap tmap;
     std::memset(&tmap, 0, sizeof tmap);
     bool tma = (w % 4 == 0) && aligned16(x) && w >= 2 * kGtMaxR + 2 && h >= 2 * kGtMaxR + 2 && encode_tiled_fn() != nullptr;
-    { const char* e = std::getenv("UPR_EXT_NO_TMA"); if (e && e[0] == '1') tma = false; }   // A/B switch (tests)
     if (tma) {
         const cuuint64_t gdim[3] = {cuuint64_t(w), cuuint64_t(h), cuuint64_t(planes)};
         const cuuint64_t gstride[2] = {cuuint64_t(w) * 4, cuuint64_t(w) * cuuint64_t(h) * 4};

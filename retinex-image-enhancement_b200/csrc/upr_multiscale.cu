@@ -7,17 +7,15 @@
 //   gain = 1 + 0.1 * sum_s w_s * mean(features_s),   w = (0.5, 0.3, 0.2)
 //
 // The reference launches ~25 eager ops and re-reads the image ~10x.  Two paths here:
-//   * fused (H % 4 == 0 and W % 4 == 0, the named 1080p/4K shapes): ONE read of x.  At exact 1/2 and 1/4
+//   * streaming (H % 4 == 0 and W % 4 == 0, the named 1080p/4K shapes): ONE read of x.  At exact 1/2 and 1/4
 //     scales torch's bilinear sample points fall on pixel-pair midpoints, so the 1/2 image is the 2x2 mean
-//     and the 1/4 image is the mean of the centre 2x2 of every 4x4 block -- both are built in shared memory
-//     from the full-resolution tile (+4 px halo) a CTA has already staged, and all 3 x 7 channel sums come
-//     out of that one tile.
+//     and the 1/4 image is the mean of the centre 2x2 of every 4x4 block -- both fall out of the rows a warp
+//     already holds in registers, and all 3 x 7 channel sums come out of that one pass (k_ms_stream).
 //   * generic (any size, and whenever the feature maps themselves are requested): a bilinear down-sample
 //     kernel followed by one feature kernel per scale.
 // Sums are fp64 per thread -> warp shuffle -> one partial per CTA -> the last CTA of the image adds the
 // partials in index order (deterministic) and writes the three means and the gain.
 #include <algorithm>
-#include <cstdlib>
 
 #include "upr_common.cuh"
 
@@ -165,133 +163,10 @@ __global__ void k_ms_finalize(const double* __restrict__ p0, const double* __res
 }
 
 // -----------------------------------------------------------------------------------------
-// fused path: tile = 64 x 32 full-resolution pixels (16 x 8 quarter-resolution pixels), halo 4
-// -----------------------------------------------------------------------------------------
-constexpr int kTW = 64, kTH = 32, kHalo = 4;
-constexpr int kFW = kTW + 2 * kHalo, kFH = kTH + 2 * kHalo;          // 72 x 40 full-res staging
-constexpr int kHW = kTW / 2 + 2, kHH = kTH / 2 + 2;                  // 34 x 18 half-res (+1 halo)
-constexpr int kQW = kTW / 4 + 2, kQH = kTH / 4 + 2;                  // 18 x 10 quarter-res (+1 halo)
-
-template <int kW, int kH>
-__device__ __forceinline__ double tile_feature_sum(const float* __restrict__ s, int halo, int tw, int th, int gx0, int gy0,
-                                                   int gw, int gh)
-{
-    // s: [3][kH][kW] with `halo` border; pixel (ty,tx) of the tile sits at s[c][ty+halo][tx+halo];
-    // (gx0, gy0) = image coordinate of tile pixel (0,0) at this scale; gw x gh = image size at this scale.
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < tw * th; i += kMsThreads) {
-        const int ty = i / tw, tx = i - ty * tw;
-        const int x = gx0 + tx, y = gy0 + ty;
-        if (x >= gw || y >= gh) continue;
-        float v[3], e[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* p = s + (c * kH + ty + halo) * kW + tx + halo;
-            v[c] = p[0];
-            e[c] = edge_mag<false>(grad1(p[-1], v[c], p[1], x, gw), grad1(p[-kW], v[c], p[kW], y, gh));
-        }
-        const float lum = luma601(v[0], v[1], v[2]);
-        acc += double(__fadd_rn(__fadd_rn(__fadd_rn(v[0], v[1]), __fadd_rn(v[2], lum)), __fadd_rn(__fadd_rn(e[0], e[1]), e[2])));
-    }
-    return acc;
-}
-
-__global__ void __launch_bounds__(kMsThreads)
-k_ms_fused(const float* __restrict__ x, int h, int w, int tiles_x, double* __restrict__ partial,
-           unsigned* __restrict__ tickets, float* __restrict__ means, float* __restrict__ gain)
-{
-    extern __shared__ __align__(16) float s_ms[];
-    float* s_full = s_ms;                          // [3][kFH][kFW]
-    float* s_half = s_full + 3 * kFH * kFW;        // [3][kHH][kHW]
-    float* s_quar = s_half + 3 * kHH * kHW;        // [3][kQH][kQW]
-    __shared__ double s_red[kMsThreads / 32];
-    __shared__ int s_flag;
-
-    const int tid = threadIdx.x;
-    const int f = blockIdx.y, parts = gridDim.x;
-    const int tyi = blockIdx.x / tiles_x, txi = blockIdx.x - tyi * tiles_x;
-    const int x0 = txi * kTW, y0 = tyi * kTH;
-    const long long plane = (long long)h * w;
-    const float* img = x + (long long)f * 3 * plane;
-    const uint64_t pol = policy_evict_first();
-
-    // stage the full-resolution tile + halo (coordinates clamped into the image: values that come from a
-    // clamp are never used, torch.gradient is one-sided at the borders)
-    constexpr int kFW4 = kFW / 4;
-    for (int i = tid; i < 3 * kFH * kFW4; i += kMsThreads) {
-        const int c = i / (kFH * kFW4), r = (i / kFW4) % kFH, q = i % kFW4;
-        const int gy = min(max(y0 - kHalo + r, 0), h - 1);
-        const int gx = x0 - kHalo + q * 4;
-        float4 v;
-        if (gx >= 0 && gx + 3 < w) {
-            v = ld_stream_f4(img + c * plane + (long long)gy * w + gx, pol);
-        } else {
-            const float* row = img + c * plane + (long long)gy * w;
-            v.x = __ldg(row + min(max(gx, 0), w - 1));
-            v.y = __ldg(row + min(max(gx + 1, 0), w - 1));
-            v.z = __ldg(row + min(max(gx + 2, 0), w - 1));
-            v.w = __ldg(row + min(max(gx + 3, 0), w - 1));
-        }
-        *reinterpret_cast<float4*>(s_full + (c * kFH + r) * kFW + q * 4) = v;
-    }
-    __syncthreads();
-    // half-resolution tile with 1 halo: half pixel (hy,hx) of the tile = full pixels (2hy..2hy+1, 2hx..2hx+1)
-    for (int i = tid; i < 3 * kHH * kHW; i += kMsThreads) {
-        const int c = i / (kHH * kHW), r = (i / kHW) % kHH, q = i % kHW;
-        const float* p = s_full + (c * kFH + (2 * (r - 1) + kHalo)) * kFW + 2 * (q - 1) + kHalo;
-        const float top = __fadd_rn(__fmul_rn(0.5f, p[0]), __fmul_rn(0.5f, p[1]));
-        const float bot = __fadd_rn(__fmul_rn(0.5f, p[kFW]), __fmul_rn(0.5f, p[kFW + 1]));
-        s_half[i] = __fadd_rn(__fmul_rn(0.5f, top), __fmul_rn(0.5f, bot));
-    }
-    // quarter-resolution tile with 1 halo: centre 2x2 of the 4x4 block
-    for (int i = tid; i < 3 * kQH * kQW; i += kMsThreads) {
-        const int c = i / (kQH * kQW), r = (i / kQW) % kQH, q = i % kQW;
-        const float* p = s_full + (c * kFH + (4 * (r - 1) + 1 + kHalo)) * kFW + 4 * (q - 1) + 1 + kHalo;
-        const float top = __fadd_rn(__fmul_rn(0.5f, p[0]), __fmul_rn(0.5f, p[1]));
-        const float bot = __fadd_rn(__fmul_rn(0.5f, p[kFW]), __fmul_rn(0.5f, p[kFW + 1]));
-        s_quar[i] = __fadd_rn(__fmul_rn(0.5f, top), __fmul_rn(0.5f, bot));
-    }
-    __syncthreads();
-
-    double a0 = tile_feature_sum<kFW, kFH>(s_full, kHalo, kTW, kTH, x0, y0, w, h);
-    double a1 = tile_feature_sum<kHW, kHH>(s_half, 1, kTW / 2, kTH / 2, x0 / 2, y0 / 2, w / 2, h / 2);
-    double a2 = tile_feature_sum<kQW, kQH>(s_quar, 1, kTW / 4, kTH / 4, x0 / 4, y0 / 4, w / 4, h / 4);
-    a0 = ms_block_sum(a0, s_red);
-    a1 = ms_block_sum(a1, s_red);
-    a2 = ms_block_sum(a2, s_red);
-    double* pp = partial + ((long long)f * parts + blockIdx.x) * 3;
-    if (tid == 0) { pp[0] = a0; pp[1] = a1; pp[2] = a2; }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned t = atomicAdd(tickets + f, 1u);
-        s_flag = (t == unsigned(parts - 1));
-        if (s_flag) tickets[f] = 0;
-    }
-    __syncthreads();
-    if (!s_flag) return;
-    __threadfence();
-    // last CTA of the image: ordered sum of the partials (256 threads stride over them, then a fixed tree)
-    double sums[3] = {0.0, 0.0, 0.0};
-    for (int k = tid; k < parts; k += kMsThreads) {
-        const double* q = partial + ((long long)f * parts + k) * 3;
-        sums[0] += __ldcg(q);
-        sums[1] += __ldcg(q + 1);
-        sums[2] += __ldcg(q + 2);
-    }
-    sums[0] = ms_block_sum(sums[0], s_red);
-    sums[1] = ms_block_sum(sums[1], s_red);
-    sums[2] = ms_block_sum(sums[2], s_red);
-    if (tid == 0) {
-        const double counts[3] = {double(h) * w, double(h / 2) * (w / 2), double(h / 4) * (w / 4)};
-        ms_finalize(sums, counts, means + 3 * f, gain + f, nullptr);
-    }
-}
-
-// -----------------------------------------------------------------------------------------
-// streaming path (replaces the tile kernel above for the named shapes): one warp per (frame, 120-column band, row
-// segment), no shared memory, no block barrier.  ncu on k_ms_fused: 288 executed instructions per pixel, 80 % issue
-// utilisation -- index arithmetic of three tile passes, 41 % halo re-staging, per-pixel luma and fp64 adds.  Here:
+// streaming path (H % 4 == 0, W % 4 == 0: the named shapes): one warp per (frame, 120-column band, row segment), no shared
+// memory, no block barrier.  (A shared-memory tile kernel that staged a 72 x 40 halo tile and derived the half / quarter
+// images from it ran 288 executed instructions per pixel at 80 % issue utilisation -- index arithmetic of three tile
+// passes, 41 % halo re-staging, per-pixel luma and fp64 adds -- 1.31 ms against 0.36 ms on 16 x 4K; profiles/r2_multiscale_full.md.)
 //   * a lane owns 4 full-resolution columns = 2 half-resolution columns = 1 quarter-resolution column and walks down
 //     the segment one quarter row (4 image rows) at a time; the rows needed for vertical differences are carried in
 //     registers, horizontal neighbours come from the adjacent lanes by shuffle (lanes 0 and 31 are halo);
@@ -547,35 +422,20 @@ static int ms_run(const float* x, int n, int h, int w, float* means, float* gain
     if (want_feat && !(f1 && f2 && f3)) return UPR_E_NULL;
     if (!want_feat && (!means || !gain)) return UPR_E_NULL;
 
-    const int tiles_x = (w + kTW - 1) / kTW, tiles_y = (h + kTH - 1) / kTH;
-    const bool fused = allow_fused && !want_feat && h % 4 == 0 && w % 4 == 0 && aligned16(x) &&
-                       (long long)tiles_x * tiles_y <= kMsMaxParts * 16LL;
-    if (fused) {
-        // development switch, read per call: UPR_MS_VARIANT=1 selects the first-generation tile kernel (A/B runs, tests)
-        const char* ev = std::getenv("UPR_MS_VARIANT");
-        const int variant = ev ? std::atoi(ev) : 0;
-        if (!(variant & 1) && h / 4 >= 2 && w / 4 >= 2) {
-            // streaming kernel: one warp per (band, row segment, frame); ~6 warps per resident slot, segments >= 64 rows
-            const int bands = (w + kMsBandCols - 1) / kMsBandCols;
-            const long long slots = 24LL * kNumSMsB200;
-            long long nseg = (6 * slots + (long long)n * bands - 1) / ((long long)n * bands);
-            nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
-            int seg_rows = int((h + nseg - 1) / nseg);
-            seg_rows = (seg_rows + 3) / 4 * 4;
-            const int segs = (h + seg_rows - 1) / seg_rows;
-            if ((long long)bands * segs <= kMsMaxParts) {
-                k_ms_stream<<<dim3(bands * segs, n), 32, 0, s>>>(x, h, w, bands, seg_rows, partial, tickets, means, gain);
-                UPR_LAUNCH_CHECK();
-                return UPR_OK;
-            }
-        }
-        const int parts = tiles_x * tiles_y;
-        // partial holds 3 doubles per CTA; the generic layout reserves kMsMaxParts*3 per image
-        if (parts <= kMsMaxParts) {
-            const size_t smem = size_t(3) * (kFH * kFW + kHH * kHW + kQH * kQW) * sizeof(float);
-            static unsigned long long mask = 0;
-            UPR_CUDA_TRY(ensure_dynamic_smem(k_ms_fused, smem, mask));
-            k_ms_fused<<<dim3(parts, n), kMsThreads, smem, s>>>(x, h, w, tiles_x, partial, tickets, means, gain);
+    const bool stream_ok = allow_fused && !want_feat && h % 4 == 0 && w % 4 == 0 && h / 4 >= 2 && w / 4 >= 2 && aligned16(x);
+    if (stream_ok) {
+        // one warp per (band, row segment, frame); ~6 warps per resident slot, segments >= 64 rows
+        const int bands = (w + kMsBandCols - 1) / kMsBandCols;
+        const long long slots = 24LL * kNumSMsB200;
+        long long nseg = (6 * slots + (long long)n * bands - 1) / ((long long)n * bands);
+        nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
+        int seg_rows = int((h + nseg - 1) / nseg);
+        seg_rows = (seg_rows + 3) / 4 * 4;
+        // (very wide frames: longer segments keep the per-frame partial count inside the workspace)
+        while ((long long)bands * ((h + seg_rows - 1) / seg_rows) > kMsMaxParts && seg_rows < h) seg_rows *= 2;
+        const int segs = (h + seg_rows - 1) / seg_rows;
+        if ((long long)bands * segs <= kMsMaxParts) {
+            k_ms_stream<<<dim3(bands * segs, n), 32, 0, s>>>(x, h, w, bands, seg_rows, partial, tickets, means, gain);
             UPR_LAUNCH_CHECK();
             return UPR_OK;
         }

@@ -8,16 +8,14 @@
 //   sal  = float32((blur - min) / (max - min + 1e-8))   per image
 //   att  = sal * (1 / (luma(x) + 0.1)); att = (att - min) / (max - min + 1e-8)   fp32, per image
 //
-// K5 k_saliency_blur: one CTA per 64x64 output tile.  The reflect-101 extension commutes with the (mirror
-//    symmetric) Laplacian and Gaussian, so the whole chain is evaluated on the reflected plane: gray
-//    (tile+8 halo, u8) -> |lap| (tile+7, u16) -> row pass (fp64, symmetric taps paired so the integer
-//    pair sums are exact) -> column pass (fp64) -> un-normalised blur stored as fp32, per-CTA fp64 min/max
-//    folded into per-image ordered-integer atomics (exact, order independent).
+// K5 k_saliency_stream: one warp per (frame, 256-column band, row segment).  The reflect-101 extension commutes with
+//    the (mirror symmetric) Laplacian and Gaussian, so the whole chain is evaluated on the reflected plane: gray (exact
+//    integers in fp32) -> |lap| -> fp16 ring of 16 rows -> vertical then horizontal 15-tap pass in fp32 -> un-normalised
+//    blur stored as fp32, per-warp min/max folded into per-image ordered-integer atomics (exact, order independent).
 // K6 k_attention_raw: sal normalise + luma division fused, fp32 min/max of the raw attention per image.
 // K7 k_normalize: (v - min) / (max - min + 1e-8) in place (used for both maps).
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 
 #include <cuda_fp16.h>
 
@@ -26,14 +24,6 @@
 namespace upr {
 
 constexpr int kSalThreads = 256;
-constexpr int kSalTile = 64;
-constexpr int kGW = kSalTile + 16;  // gray   80 x 80
-constexpr int kLW = kSalTile + 14;  // |lap|  78 x 78
-constexpr int kRH = kSalTile + 14;  // row pass: 78 rows x 64 cols fp64
-
-struct GaussTaps {
-    double t[8];  // t[d] = weight at distance d from the centre of the 15-tap kernel (kernel parameter -> constant bank)
-};
 
 __device__ __forceinline__ int reflect101_s(int p, int len)
 {
@@ -79,85 +69,11 @@ __global__ void k_sal_reset(SalMinMax* mm, int n)
     mm[i].pad0 = mm[i].pad1 = 0;
 }
 
-__global__ void __launch_bounds__(kSalThreads)
-k_saliency_blur(const float* __restrict__ x, int h, int w, int tiles_x, float* __restrict__ blur_out, SalMinMax* __restrict__ mm,
-                const GaussTaps taps)
-{
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    double* s_row = reinterpret_cast<double*>(s_raw);                                  // [kRH][kSalTile]
-    unsigned short* s_lap = reinterpret_cast<unsigned short*>(s_row + kRH * kSalTile);  // [kLW][kLW]
-    unsigned char* s_gray = reinterpret_cast<unsigned char*>(s_lap + kLW * kLW);        // [kGW][kGW]
-    __shared__ double s_mn[kSalThreads / 32], s_mx[kSalThreads / 32];
-
-    const int tid = threadIdx.x;
-    const int f = blockIdx.y;
-    const int tyi = blockIdx.x / tiles_x, txi = blockIdx.x - tyi * tiles_x;
-    const int x0 = txi * kSalTile, y0 = tyi * kSalTile;
-    const long long plane = (long long)h * w;
-    const float* img = x + (long long)f * 3 * plane;
-
-    // gray on the reflected plane: s_gray[r][c] = gray(reflect(y0-8+r), reflect(x0-8+c))
-    for (int i = tid; i < kGW * kGW; i += kSalThreads) {
-        const int r = i / kGW, c = i - r * kGW;
-        const int gy = reflect101_s(y0 - 8 + r, h), gx = reflect101_s(x0 - 8 + c, w);
-        const long long o = (long long)gy * w + gx;
-        const int qr = quantize_u8(__ldg(img + o)), qg = quantize_u8(__ldg(img + plane + o)),
-                  qb = quantize_u8(__ldg(img + 2 * plane + o));
-        s_gray[i] = (unsigned char)((qr * 9798 + qg * 19235 + qb * 3735 + 16384) >> 15);
-    }
-    __syncthreads();
-    // |laplacian| at plane coordinates (y0-7+r, x0-7+c)
-    for (int i = tid; i < kLW * kLW; i += kSalThreads) {
-        const int r = i / kLW, c = i - r * kLW;
-        const unsigned char* g = s_gray + (r + 1) * kGW + c + 1;
-        const int v = int(g[-kGW]) + int(g[kGW]) + int(g[-1]) + int(g[1]) - 4 * int(g[0]);
-        s_lap[i] = (unsigned short)abs(v);
-    }
-    __syncthreads();
-    // row pass: rows y0-7 .. y0+70, columns x0 .. x0+63
-    for (int i = tid; i < kRH * kSalTile; i += kSalThreads) {
-        const int r = i / kSalTile, c = i - r * kSalTile;
-        const unsigned short* p = s_lap + r * kLW + c + 7;
-        double acc = taps.t[0] * double(int(p[0]));
-#pragma unroll
-        for (int d = 1; d <= 7; ++d) acc = __fma_rn(taps.t[d], double(int(p[-d]) + int(p[d])), acc);
-        s_row[i] = acc;
-    }
-    __syncthreads();
-    // column pass + store + min/max
-    double mn = INFINITY, mx = -INFINITY;
-    for (int i = tid; i < kSalTile * kSalTile; i += kSalThreads) {
-        const int r = i / kSalTile, c = i - r * kSalTile;
-        const int gy = y0 + r, gx = x0 + c;
-        if (gy >= h || gx >= w) continue;
-        const double* p = s_row + (r + 7) * kSalTile + c;
-        double acc = taps.t[0] * p[0];
-#pragma unroll
-        for (int d = 1; d <= 7; ++d) acc = __fma_rn(taps.t[d], p[-d * kSalTile] + p[d * kSalTile], acc);
-        blur_out[(long long)f * plane + (long long)gy * w + gx] = float(acc);
-        mn = fmin(mn, acc);
-        mx = fmax(mx, acc);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    if ((tid & 31) == 0) { s_mn[tid >> 5] = mn; s_mx[tid >> 5] = mx; }
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int k = 1; k < kSalThreads / 32; ++k) { mn = fmin(mn, s_mn[k]); mx = fmax(mx, s_mx[k]); }
-        atomicMin(&mm[f].blur_min, dbl_key(mn));
-        atomicMax(&mm[f].blur_max, dbl_key(mx));
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// K5s k_saliency_stream: the same chain as k_saliency_blur as a row-streaming, one-warp-per-CTA kernel.
-//   The tile kernel above executes 271 SASS instructions per pixel (ncu, profiles/r2_c5.md): 56 % halo re-computation
-//   of the gray stage (80x80 per 64x64), scalar reflect-indexed loads, 15 shared loads per output and pass, an fp64
-//   FMA chain.  Here a warp owns a band of 256 columns (lane = 8 columns; lanes 0 and 31 are the +-8 halo, 240 columns
+// K5 k_saliency_stream: a row-streaming, one-warp-per-CTA kernel.
+//   (A 64x64 shared-memory tile kernel with an fp64 blur executed 271 SASS instructions per pixel -- 56 % halo
+//   re-computation of the gray stage (80x80 per 64x64), scalar reflect-indexed loads, 15 shared loads per output and
+//   pass, an fp64 FMA chain: 1.76 ms against 0.65 ms on 16 x 4K, profiles/r2_content_aware_full.md.)  A warp owns a band of 256 columns (lane = 8 columns; lanes 0 and 31 are the +-8 halo, 240 columns
 //   are written) and marches down a row segment:
 //     load row k (two 128-bit loads per plane and lane) -> quantise/gray on the FMA pipe (exact integer arithmetic in
 //     fp32, see upr_clahe.cu) -> |lap| of row k-1 (vertical neighbours from registers, the two horizontal ones by
@@ -166,7 +82,7 @@ k_saliency_blur(const float* __restrict__ x, int h, int w, int tiles_x, float* _
 //     pass of row k-8 (symmetric taps paired) -> one fp32 row exchanged through a per-warp buffer (__syncwarp only) ->
 //     HORIZONTAL pass -> un-normalised blur (fp32) + running min/max.
 //   Vertical-then-horizontal and fp32 accumulation differ from OpenCV's fp64 rows-then-columns by ~2e-7 relative --
-//   the same order as the fp32 store of the tile kernel, and far inside the stated 1e-4 bound.
+//   the same order as the fp32 rounding of the stored blur itself, and far inside the stated 1e-4 bound.
 //   Row segments overlap by 16 rows, bands by 16 columns (amplification ~1.07 x 1.06 instead of 1.56).
 // ---------------------------------------------------------------------------------------------
 constexpr int kSsLaneCols = 8;
@@ -463,12 +379,16 @@ k_att_normalize(float* __restrict__ att, long long plane, const SalMinMax* __res
 // once instead of being normalised in place (8 B/px) and then re-read per channel by the gain kernel.
 __device__ __forceinline__ float sal_clamp01_keep_nan(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 
-template <bool kWriteAtt, int VEC>
+// kGain: the multi-scale gain of the same input (multi_scale.py:97-98) is applied in the same epilogue, to the clamped
+// content-aware result: out = clamp(clamp(enh * (1 + 0.2 att), 0, 1) * gain[f], 0, 1) -- the "content-aware + multi-scale"
+// chain of BASELINE config 5 without a second pass over the frame.
+template <bool kWriteAtt, bool kGain, int VEC>
 __global__ void __launch_bounds__(kSalThreads)
 k_att_gain(const float* __restrict__ raw, const float* __restrict__ enh, float* __restrict__ out, float* __restrict__ att_out,
-           long long plane, const SalMinMax* __restrict__ mm)
+           long long plane, const SalMinMax* __restrict__ mm, const float* __restrict__ gain)
 {
     const int f = blockIdx.y;
+    const float ms_gain = kGain ? __ldg(gain + f) : 1.0f;
     const float mn = key_flt(mm[f].att_min), mx = key_flt(mm[f].att_max);
     const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-8f);
     const float* r = raw + (long long)f * plane;
@@ -503,30 +423,30 @@ k_att_gain(const float* __restrict__ raw, const float* __restrict__ enh, float* 
                 w.y = sal_clamp01_keep_nan(__fmul_rn(v.y, g[1]));
                 w.z = sal_clamp01_keep_nan(__fmul_rn(v.z, g[2]));
                 w.w = sal_clamp01_keep_nan(__fmul_rn(v.w, g[3]));
+                if (kGain) {
+                    w.x = sal_clamp01_keep_nan(__fmul_rn(w.x, ms_gain));
+                    w.y = sal_clamp01_keep_nan(__fmul_rn(w.y, ms_gain));
+                    w.z = sal_clamp01_keep_nan(__fmul_rn(w.z, ms_gain));
+                    w.w = sal_clamp01_keep_nan(__fmul_rn(w.w, ms_gain));
+                }
                 __stcs(reinterpret_cast<float4*>(o + c * plane) + i, w);
             } else {
-                o[c * plane + i] = sal_clamp01_keep_nan(__fmul_rn(e[c * plane + i], g[0]));
+                float w1 = sal_clamp01_keep_nan(__fmul_rn(e[c * plane + i], g[0]));
+                if (kGain) w1 = sal_clamp01_keep_nan(__fmul_rn(w1, ms_gain));
+                o[c * plane + i] = w1;
             }
         }
     }
 }
 
-static GaussTaps sal_taps()
+static GaussTapsF sal_taps_f()
 {
-    // cv2.getGaussianKernel(15, sigma=0.3*((15-1)*0.5-1)+0.8 = 2.6), fp64
+    // cv2.getGaussianKernel(15, sigma=0.3*((15-1)*0.5-1)+0.8 = 2.6) in fp64, rounded to fp32; t[d] = weight at distance d
     double k[15], sum = 0.0;
     const double sigma = 0.3 * ((15 - 1) * 0.5 - 1) + 0.8;
     for (int i = 0; i < 15; ++i) { const double d = i - 7; k[i] = std::exp(-0.5 * d * d / (sigma * sigma)); sum += k[i]; }
-    GaussTaps g;
-    for (int d = 0; d < 8; ++d) g.t[d] = k[7 + d] / sum;
-    return g;
-}
-
-static GaussTapsF sal_taps_f()
-{
-    const GaussTaps g = sal_taps();
     GaussTapsF r;
-    for (int d = 0; d < 8; ++d) r.t[d] = float(g.t[d]);
+    for (int d = 0; d < 8; ++d) r.t[d] = float(k[7 + d] / sum);
     return r;
 }
 
@@ -535,17 +455,10 @@ static size_t sal_ws_bytes(int n, int h, int w)
     return align_up(size_t(n) * sizeof(SalMinMax), 256) + align_up(size_t(n) * h * w * sizeof(float), 256);
 }
 
-// development switch: UPR_SAL_VARIANT=1 selects the first-generation tile kernel (fp64 blur) for A/B runs
-static int sal_variant()
-{
-    const char* e = std::getenv("UPR_SAL_VARIANT");   // read per call so that tests can A/B within one process
-    return e ? std::atoi(e) : 0;
-}
-
 // mode 0: saliency only -> out ; mode 1: attention -> out (saliency is an internal temporary);
 // mode 2: out = clamp(enh * (1 + 0.2 attention), 0, 1) with the attention map optional (att_out)
 static int sal_run(int mode, const float* x, int n, int h, int w, float* out, void* ws, size_t ws_bytes, cudaStream_t s,
-                   const float* enh = nullptr, float* att_out = nullptr)
+                   const float* enh = nullptr, float* att_out = nullptr, const float* ms_gain = nullptr)
 {
     if (n < 0 || n > 65535 || h <= 0 || w <= 0) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
@@ -556,14 +469,7 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
     const long long plane = (long long)h * w;
     k_sal_reset<<<(n + 127) / 128, 128, 0, s>>>(mm, n);
     UPR_LAUNCH_CHECK();
-    if (sal_variant() & 1) {
-        static const GaussTaps taps = sal_taps();
-        const int tiles_x = (w + kSalTile - 1) / kSalTile, tiles_y = (h + kSalTile - 1) / kSalTile;
-        const size_t smem = size_t(kRH) * kSalTile * sizeof(double) + size_t(kLW) * kLW * 2 + size_t(kGW) * kGW;
-        static unsigned long long mask = 0;
-        UPR_CUDA_TRY(ensure_dynamic_smem(k_saliency_blur, smem, mask));
-        k_saliency_blur<<<dim3(tiles_x * tiles_y, n), kSalThreads, smem, s>>>(x, h, w, tiles_x, blur, mm, taps);
-    } else {
+    {
         static const GaussTapsF taps = sal_taps_f();
         const int bands = (w + kSsBandCols - 1) / kSsBandCols;
         // one warp per (band, row segment, frame): aim at ~6 warps per resident slot (20 warps/SM) for balance, but keep
@@ -590,13 +496,17 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
         if (v4) k_sal_normalize<true, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, blur, plane, mm);
         else k_sal_normalize<true, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, blur, plane, mm);
         UPR_LAUNCH_CHECK();
-        if (att_out) {
-            if (v4) k_att_gain<true, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, enh, out, att_out, plane, mm);
-            else k_att_gain<true, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, enh, out, att_out, plane, mm);
-        } else {
-            if (v4) k_att_gain<false, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, enh, out, nullptr, plane, mm);
-            else k_att_gain<false, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, enh, out, nullptr, plane, mm);
-        }
+        const dim3 grid(parts, n);
+#define UPR_ATT_GAIN(A, G)                                                                                                     \
+    do {                                                                                                                       \
+        if (v4) k_att_gain<A, G, 4><<<grid, kSalThreads, 0, s>>>(blur, enh, out, att_out, plane, mm, ms_gain);                  \
+        else k_att_gain<A, G, 1><<<grid, kSalThreads, 0, s>>>(blur, enh, out, att_out, plane, mm, ms_gain);                     \
+    } while (0)
+        if (att_out && ms_gain) UPR_ATT_GAIN(true, true);
+        else if (att_out) UPR_ATT_GAIN(true, false);
+        else if (ms_gain) UPR_ATT_GAIN(false, true);
+        else UPR_ATT_GAIN(false, false);
+#undef UPR_ATT_GAIN
         UPR_LAUNCH_CHECK();
     } else {
         if (v4) k_sal_normalize<true, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, out, plane, mm);
@@ -636,6 +546,15 @@ int upr_content_aware_apply_f32(const float* x_nchw, const float* enh_nchw, floa
 {
     return upr::sal_run(2, x_nchw, n, h, w, out_nchw, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), enh_nchw,
                         att_n1hw);
+}
+
+int upr_content_multiscale_apply_f32(const float* x_nchw, const float* enh_nchw, const float* ms_gain_per_image, float* out_nchw,
+                                     float* att_n1hw, int n, int h, int w, void* workspace, size_t workspace_bytes,
+                                     upr_stream_t stream)
+{
+    if (!ms_gain_per_image && n > 0) return UPR_E_NULL;
+    return upr::sal_run(2, x_nchw, n, h, w, out_nchw, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), enh_nchw,
+                        att_n1hw, ms_gain_per_image);
 }
 
 }  // extern "C"

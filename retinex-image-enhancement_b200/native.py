@@ -81,6 +81,8 @@ def _declare(lib):
     lib.upr_content_aware_apply_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
     lib.upr_quantize_u8_f32.restype = i32
     lib.upr_quantize_u8_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.upr_content_multiscale_apply_f32.restype = i32
+    lib.upr_content_multiscale_apply_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
     lib.upr_retinex_recombine_f32.restype = i32
     lib.upr_retinex_recombine_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
     lib.upr_retinex_decompose_f32.restype = i32
@@ -519,6 +521,29 @@ def content_aware_apply(x: torch.Tensor, enh: torch.Tensor, out: Optional[torch.
         check(L.upr_content_aware_apply_f32(x.data_ptr(), enh.data_ptr(), out.data_ptr(), att.data_ptr() if att is not None else None,
                                             n, h, w, ws.data_ptr(), ws.numel(), _stream()), "upr_content_aware_apply_f32")
     return (out, att) if want_attention else out
+
+
+def content_multiscale_apply(x: torch.Tensor, enh: torch.Tensor, out: Optional[torch.Tensor] = None, gain: Optional[torch.Tensor] = None):
+    """BASELINE config 5 chain in four launches: multi-scale statistics of x (gain stays on the device), saliency blur, raw
+    attention, and ONE epilogue  clamp(clamp(enh * (1 + 0.2 att), 0, 1) * gain, 0, 1)  (upr_content_multiscale_apply_f32).
+    Equal to content_aware_apply() followed by scale_clamp().  Returns (out, gain [N])."""
+    x = _require_cuda_f32(x, "x")
+    enh = _require_cuda_f32(enh, "enh")
+    n, c, h, w = x.shape
+    if c != 3 or enh.shape != x.shape:
+        raise ValueError("expected x, enh [N,3,H,W]")
+    if gain is None:
+        _means, gain = multiscale_stats(x)
+    gain = _require_cuda_f32(gain, "gain").reshape(-1)
+    if gain.numel() != n:
+        raise ValueError("gain must have one entry per image")
+    out = torch.empty_like(enh) if out is None else out
+    L = lib()
+    with torch.cuda.device(x.device):
+        ws = workspace(L.upr_saliency_workspace_bytes(n, h, w), x.device)
+        check(L.upr_content_multiscale_apply_f32(x.data_ptr(), enh.data_ptr(), gain.data_ptr(), out.data_ptr(), None, n, h, w,
+                                                 ws.data_ptr(), ws.numel(), _stream()), "upr_content_multiscale_apply_f32")
+    return out, gain
 
 
 def retinex_recombine(x: torch.Tensor, illu: torch.Tensor, e: torch.Tensor, want_reflectance: bool = True,

@@ -102,21 +102,55 @@ int main()
     printf("resident CTAs per SM: %d\n", per_sm);
     const double px = double(frames) * 2160 * 3840;
     printf("%7s %6s %6s %5s | %8s %12s %14s\n", "ctas/sm", "reuse", "groups", "hint", "ms", "GB/s@48B/px", "GB/s@64B/px");
-    for (int cps : {2, 4, 8}) for (int groups : {1, 2, 4}) for (int reuse : {0, 1}) for (int hint : {0, 1}) {
+    cudaStream_t st; CK(cudaStreamCreate(&st));
+    for (int persist : {0, 1}) for (int cps : {4, 6}) for (int groups : {1, 2}) for (int reuse : {0, 1}) for (int hint : {0}) {
         if (cps > per_sm) continue;
+        if (persist && !reuse) continue;
+        if (persist) {
+            // pin the T slots (33 MB per group) in the persisting L2 carve-out
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(79) << 20));
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = T;
+            av.accessPolicyWindow.num_bytes = size_t(groups) * plane4 * 16;
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
         int grid = 148 * cps; grid -= grid % groups;
         float best = 1e9f;
         for (int rep = 0; rep < 3; ++rep) {
             CK(cudaMemset(bars, 0, 1024));
-            CK(cudaEventRecord(e0));
+            CK(cudaDeviceSynchronize());
+            CK(cudaEventRecord(e0, st));
             int fr = frames, r = reuse, g = groups, h = hint; size_t p4 = plane4;
             void* args[] = {&X, &E, &O, &T, &p4, &fr, &r, &g, &h, &bars, &sink};
-            CK(cudaLaunchCooperativeKernel((void*)pipeline, dim3(grid), dim3(256), args, 0, 0));
-            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+            CK(cudaLaunchCooperativeKernel((void*)pipeline, dim3(grid), dim3(256), args, 0, st));
+            CK(cudaEventRecord(e1, st)); CK(cudaEventSynchronize(e1));
             float t; CK(cudaEventElapsedTime(&t, e0, e1));
             if (t < best) best = t;
         }
-        printf("%7d %6d %6d %5d | %8.3f %12.0f %14.0f\n", cps, reuse, groups, hint, best, 48.0 * px / best / 1e6, 64.0 * px / best / 1e6);
+        printf("%7d %6d %6d %5d | %8.3f %12.0f %14.0f  persist=%d\n", cps, reuse, groups, hint, best, 48.0 * px / best / 1e6, 64.0 * px / best / 1e6, persist);
+        if (persist) {
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.num_bytes = 0;
+            CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+            CK(cudaCtxResetPersistingL2Cache());
+        }
+    }
+    // barrier cost alone: same kernel on a tiny plane (48 group barriers, no data)
+    {
+        CK(cudaMemset(bars, 0, 1024));
+        int grid = 148 * 4, fr = frames, r = 1, g = 1, h = 0; size_t p4 = 1024;
+        void* args[] = {&X, &E, &O, &T, &p4, &fr, &r, &g, &h, &bars, &sink};
+        CK(cudaLaunchCooperativeKernel((void*)pipeline, dim3(grid), dim3(256), args, 0, st));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemset(bars, 0, 1024));
+        CK(cudaEventRecord(e0, st));
+        CK(cudaLaunchCooperativeKernel((void*)pipeline, dim3(grid), dim3(256), args, 0, st));
+        CK(cudaEventRecord(e1, st)); CK(cudaEventSynchronize(e1));
+        float t; CK(cudaEventElapsedTime(&t, e0, e1));
+        printf("48 barriers on an empty pipeline (592 CTAs): %.3f ms\n", t);
     }
     return 0;
 }

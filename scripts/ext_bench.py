@@ -8,10 +8,6 @@ px = x.numel()
 res = {}
 for name, fn in (("blur5", lambda: E.gaussian_blur(x, 5)), ("blur15", lambda: E.gaussian_blur(x, 15)), ("blur31", lambda: E.gaussian_blur(x, 31, 5.0)),
                  ("msr_7_15_31", lambda: E.multi_scale_retinex(x, (7, 15, 31))), ("pyr_down", lambda: E.pyr_down(x)), ("gamma", lambda: E.gamma_correct(x, 0.45))):
-    for tma in ("0", "1"):
-        if tma == "1" and not name.startswith(("blur", "msr")):
-            continue
-        os.environ["UPR_EXT_NO_TMA"] = tma
-        med, _ = time_op(fn, 10)
-        res[name + ("" if tma == "0" else "_no_tma")] = {"ms": round(med, 4), "GBs_8B_per_elem": round(8 * px / med / 1e6, 1)}
+    med, _ = time_op(fn, 10)
+    res[name] = {"ms": round(med, 4), "GBs_8B_per_elem": round(8 * px / med / 1e6, 1)}
 print(json.dumps(res))

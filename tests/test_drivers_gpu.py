@@ -19,6 +19,19 @@ def cuda():
     return "cuda"
 
 
+class MapsStub(torch.nn.Module):
+    """A model with forward_maps(): pointwise, hence bit-identical whatever the batch composition (cuDNN convolutions are not)."""
+
+    def forward_maps(self, x):
+        return x.mean(dim=1, keepdim=True) * 0.5 + 0.25, torch.sqrt(x)
+
+    def forward(self, x):
+        from retinex_image_enhancement_b200.models.model import retinex_recombine
+        illu, e = self.forward_maps(x)
+        reflectance, enhanced = retinex_recombine(x.contiguous(), illu.contiguous(), e.contiguous())
+        return enhanced, reflectance, illu
+
+
 class StubModel(torch.nn.Module):
     """enhanced = sqrt(x) (a fixed brightening), illu = mean over channels."""
 
@@ -125,8 +138,7 @@ def test_batch_driver_pipeline(cuda, tmp_path):
     dup = np.random.default_rng(50).integers(0, 200, (128, 192, 3), dtype=np.uint8)
     Image.fromarray(dup).save(src / "f3.bmp")                 # same stem as f3.png; sorted order: f3.bmp, f3.png -> the png wins
     _write_png(str(src / "wide.png"), 160, 640, 60)
-    torch.manual_seed(3)
-    model = UP_Retinex(use_preact=False, use_aspp=False).to(cuda).eval()
+    model = MapsStub().to(cuda).eval()
     enhance_batch_images(str(src), str(tmp_path / "out"), cuda, model=model, batch_size=3)
     for name in [f"f{i}" for i in range(7)] + ["wide"]:
         low, _ = load_image(str(src / f"{name}.png"), device=cuda)
@@ -143,6 +155,16 @@ def test_batch_driver_pipeline(cuda, tmp_path):
     enhance_single_image(model, str(src / "wide.png"), str(tmp_path / "lb1"), cuda, max_size=96)
     assert np.array_equal(_read_png(tmp_path / "lb" / "wide_enhanced.png"), _read_png(tmp_path / "lb1" / "wide_enhanced.png"))
     assert np.array_equal(_read_png(tmp_path / "lb" / "wide_comparison.png"), _read_png(tmp_path / "lb1" / "wide_comparison.png"))
+    # the real CNN (reference module tree, random weights) through the same pipeline, and the other two enhancers
+    torch.manual_seed(3)
+    cnn = UP_Retinex(use_preact=False, use_aspp=False).to(cuda).eval()
+    enhance_batch_images(str(src), str(tmp_path / "cnn"), cuda, model=cnn, batch_size=4)
+    enhance_batch_images(str(src), str(tmp_path / "ca"), cuda, model=model, batch_size=4, enable_content_aware=True)
+    enhance_batch_images(str(src), str(tmp_path / "ms"), cuda, model=model, batch_size=4, enable_multi_scale=True)
+    for d in ("cnn", "ca", "ms"):
+        assert _read_png(tmp_path / d / "wide_enhanced.png").shape == (160, 640, 3) and os.path.exists(tmp_path / d / "f6_comparison.png")
+    enhance_single_image(model, str(src / "f2.png"), str(tmp_path / "ca1"), cuda, enable_content_aware=True)
+    assert np.array_equal(_read_png(tmp_path / "ca1" / "f2_enhanced.png"), _read_png(tmp_path / "ca" / "f2_enhanced.png"))
 
 
 def test_adaptive_parameters_are_lazy(cuda):

@@ -336,6 +336,23 @@ def test_content_aware_apply_fused(native):
         assert torch.equal(native.content_aware_apply(dev(xs), dev(enh)), ref)
 
 
+def test_content_multiscale_chain(native):
+    """BASELINE config 5: content-aware then multi-scale on the same CNN output, one shared epilogue -- bit-identical to the two
+    enhancers' own epilogues back to back, and equal to the oracle's composition within the attention tolerance."""
+    for n, h, w in ((2, 400, 600), (1, 1080, 1920), (2, 33, 51)):
+        xs = np.concatenate([O.kat_input(720 + i, h, w, ("uniform", "dark")[i % 2]) for i in range(n)])
+        enh = np.random.default_rng(721).random((n, 3, h, w), dtype=np.float32) * np.float32(1.3)
+        xd, ed = dev(xs), dev(enh)
+        _m, gain = native.multiscale_stats(xd, force_generic=(h % 4 != 0))
+        ref = native.scale_clamp(native.content_aware_apply(xd, ed), gain)
+        out, gain2 = native.content_multiscale_apply(xd, ed)
+        assert torch.equal(out, ref) and torch.equal(gain, gain2)
+        for i in range(n):
+            f_ref = O.multiscale_means(xs[i:i + 1])[1]
+            want = O.scale_clamp(O.attention_apply(enh[i], O.attention(xs[i:i + 1])), np.float32(f_ref))
+            np.testing.assert_allclose(out[i:i + 1].cpu().numpy(), want, rtol=0, atol=2e-6)
+
+
 def test_fused_peer_allreduce_two_gpus():
     """upr_texture_weight_peer_f32 under torchrun on two GPUs: bit-equal to statistics kernel + NCCL all-reduce + weight kernel on
     every rank, every step (unequal local batches included; beyond two ranks NCCL's summation order differs from the kernel's

@@ -203,8 +203,12 @@ def test_enhanced_losses_autograd_and_total_loss_views(native):
     fused = EnhancedImageLosses()
     exposure, color, spatial = fused.exposure(), fused.color(), fused.spatial()
     a = enh.clone().requires_grad_(True)
-    le, lc, ls = exposure(a, low), color(a), spatial(a, low)          # the order TotalLoss.forward uses (loss.py:672-675)
-    assert fused._val is not None and le is fused._val[0] and lc is fused._val[1] and ls is fused._val[2]   # one evaluation
+    le, lc = exposure(a, low), color(a)                              # the order TotalLoss.forward uses (loss.py:672-675)
+    val = fused._val
+    assert val is not None and le is val[0] and lc is val[1]
+    ls = spatial(a, low)
+    assert ls is val[2]                                               # one evaluation served all three terms ...
+    assert fused._val is None and fused._enh is None                  # ... and was then released (no pinned graph / tensors)
     (10.0 * le + 5.0 * lc + 1.0 * ls).backward()
     b = enh.clone().requires_grad_(True)
     se, sc, ss = stock(b)
@@ -213,14 +217,16 @@ def test_enhanced_losses_autograd_and_total_loss_views(native):
         assert abs(float(got) - float(want)) <= rtol * abs(float(want))
     assert (a.grad - b.grad).abs().max() <= 2e-5 * b.grad.abs().max()
     # a new tensor or an in-place update triggers a new evaluation; ColorLoss alone after that pairs with the same input image
-    first = fused._val
     a2 = enh.clone().requires_grad_(True)
     exposure(a2, low)
     second = fused._val
-    assert second is not first and color(a2) is second[1]
+    assert second is not val and color(a2) is second[1]
     with torch.no_grad():
         low.mul_(0.5)
     assert spatial(a2, low) is not second[2]
+    with torch.no_grad():                                             # an evaluation without autograd is never reused with it
+        e_ng = exposure(a2, low)
+    assert exposure(a2, low) is not e_ng and exposure(a2, low).requires_grad
     fused.clear()
     assert fused._val is None and fused._enh is None
     with pytest.raises(ValueError):
