@@ -167,6 +167,53 @@ def enhance_frames_u8(model, low, enable_multi_scale=False, enable_content_aware
     return enh8, illu8
 
 
+_stream_rings = {}
+
+
+def _stream_ring(dev, count=3):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), count)
+    ring = _stream_rings.get(key)
+    if ring is None:
+        ring = [torch.cuda.Stream(device=dev) for _ in range(count)]
+        _stream_rings[key] = ring
+    return ring
+
+
+def enhance_frames_host_u8(model, frames_u8, out_enh, out_illu, device, max_size=None, enable_multi_scale=False,
+                           enable_content_aware=False, out_low=None, chunk=8):
+    """The device side of the batch driver, end to end at the uint8 boundary: HOST frames as decoded ([N,H,W,3] u8, pinned for
+    full PCIe speed) -> HOST frames as ``save_image`` would store them (``out_enh`` [N,H',W',3] u8, ``out_illu`` [N,H',W',1] u8;
+    ``out_low`` [N,H',W',3] receives the letterboxed input when ``max_size`` changes it).  The batch is cut into chunks of
+    ``chunk`` frames that rotate over three CUDA streams: the upload of chunk k+1 and the download of chunk k-1 overlap the
+    kernels of chunk k; 3 B/px go up, 4 B/px come back.  Returns the CUDA events of the chunks, in order: ``event.synchronize()``
+    before reading the corresponding frames of the output buffers (the PNG writers of enhance_batch_images do exactly that)."""
+    from .. import native
+    dev = torch.device(resolve_device(device))
+    n, h, w = frames_u8.shape[0], frames_u8.shape[1], frames_u8.shape[2]
+    (rh, rw), (top, left), out_hw = _geometry(h, w, max_size)
+    ring = _stream_ring(dev)
+    launch = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(launch)
+    events = []
+    with torch.cuda.device(dev):
+        for k, f0 in enumerate(range(0, n, chunk)):
+            f1 = min(f0 + chunk, n)
+            st = ring[k % len(ring)]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                low = native.letterbox(frames_u8[f0:f1].to(dev, non_blocking=True), (rh, rw), top, left, out_hw)
+                enh8, illu8 = enhance_frames_u8(model, low, enable_multi_scale, enable_content_aware)
+                out_enh[f0:f1].copy_(enh8, non_blocking=True)
+                out_illu[f0:f1].copy_(illu8, non_blocking=True)
+                if out_low is not None:
+                    out_low[f0:f1].copy_(native.quantize_u8(low), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            events.append(ev)
+    return events
+
+
 def _write_outputs(img_low, img_enhanced, illu_map, image_path, output_dir, pool=None):
     """The reference's three files per image (enhancers/simple_enhance.py:177-195).  Quantisation happens here (on the
     device for CUDA tensors); with ``pool`` (a ThreadPoolExecutor) the PNG encoding runs on host threads."""
@@ -286,7 +333,6 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
         return stem, task
 
     staging = _Staging(batch_size)
-    stream = torch.cuda.Stream(device=device) if on_gpu else None
 
     def run_batch(batch):
         """batch: list of (path, u8 HWC array) of one shape."""
@@ -298,7 +344,6 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
                 enhanced, illu = _enhance_tensor(model, low, device, enable_multi_scale, enable_content_aware)
                 futures.append(_write_outputs(low, enhanced, illu, path, output_dir, pool=writers))
             return
-        from .. import native
         b = len(batch)
         h, w = batch[0][1].shape[:2]
         (rh, rw), (top, left), out_hw = _geometry(h, w, max_size)
@@ -306,17 +351,9 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
         slot = staging.acquire((h, w), out_hw, not identity)
         for i, (_p, arr) in enumerate(batch):
             slot["in"][i].copy_(torch.from_numpy(arr))
-        dev = torch.device(device)
-        with torch.cuda.device(dev), torch.cuda.stream(stream):
-            d_in = slot["in"][:b].to(dev, non_blocking=True)
-            low = native.letterbox(d_in, (rh, rw), top, left, out_hw)
-            enh8, illu8 = enhance_frames_u8(model, low, enable_multi_scale, enable_content_aware)
-            slot["enh"][:b].copy_(enh8, non_blocking=True)
-            slot["illu"][:b].copy_(illu8, non_blocking=True)
-            if not identity:
-                slot["low"][:b].copy_(native.quantize_u8(low), non_blocking=True)
-            event = torch.cuda.Event()
-            event.record(stream)
+        event = enhance_frames_host_u8(model, slot["in"][:b], slot["enh"][:b], slot["illu"][:b], device, max_size,
+                                       enable_multi_scale, enable_content_aware, out_low=None if identity else slot["low"][:b],
+                                       chunk=b)[-1]
         for i, (path, arr) in enumerate(batch):
             low8 = arr if identity else slot["low"][i].numpy()      # un-letterboxed: the decoded bytes ARE the stored input
             stem, task = png_task(path, low8, slot["enh"][i].numpy(), slot["illu"][i].numpy(), event)
