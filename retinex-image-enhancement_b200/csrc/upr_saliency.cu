@@ -107,7 +107,16 @@ __device__ __forceinline__ void ss_load8(const float* __restrict__ row, int c0, 
     }
 }
 
-__global__ void __launch_bounds__(32)
+// resident one-warp CTAs per SM the kernel is compiled for (register cap = 65536 / (32 * kSsMinBlocks))
+#ifndef UPR_SS_MINBLOCKS
+#define UPR_SS_MINBLOCKS 1
+#endif
+constexpr int kSsMinBlocks = UPR_SS_MINBLOCKS;
+#ifndef UPR_SS_GENERATION
+#define UPR_SS_GENERATION 2
+#endif
+
+__global__ void __launch_bounds__(32, kSsMinBlocks)
 k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, float* __restrict__ blur_out,
                   SalMinMax* __restrict__ mm, const GaussTapsF taps)
 {
@@ -267,6 +276,320 @@ k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) { g0[i] = g1[i]; g1[i] = g2[i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0 && mn <= mx) {
+        atomicMin(&mm[f].blur_min, dbl_key(double(mn)));
+        atomicMax(&mm[f].blur_max, dbl_key(double(mx)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 second generation, k_saliency_stream2.  ncu on k_saliency_stream: 102 executed instructions per pixel at 114 registers,
+// issue-bound (0.65 ms per 16 x 4K for 16 B/px); tighter launch bounds only add spills (18 -> 32 warps/SM: 0.89 -> 1.13 ms,
+// profiles/r4_saliency.md).  So the instruction stream itself is cut:
+//   * TWO output rows per iteration.  The vertical pass streams the 16 live |lap| rows through registers once and feeds both
+//     rows' accumulators (half the shared-memory loads per pixel); no symmetric pairing -- a pair add plus an FMA costs the same
+//     two issue slots as two FMAs;
+//   * packed fp32 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: two fp32 lanes per issue slot) on natural column pairs -- the
+//     registers a 128-bit load delivers -- for quantisation, gray, the vertical part of the Laplacian, the whole vertical pass
+//     and the FMA half of the horizontal pass (its pair sums are scalar adds that land in aligned register pairs);
+//   * the |lap| ring holds fp32 (no half <-> float conversions: one per tap and pixel in the first generation), 16 KB per warp;
+//     shared memory then bounds residency at 10 warps per SM, which is enough because every warp carries 16 independent pixels.
+// Same arithmetic as the first generation up to the order of the fp32 tap sums (still far inside the 1e-4 bound, tests).
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;   // (lo, hi) = two fp32 values in an aligned register pair
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2_rz(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    // volatile: ptxas contracts mul.rn.f32x2 + add/sub.f32x2 into FFMA2 (observed), which would skip the rounding of x * 255
+    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm volatile("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+constexpr int kS2RingRowBytes = 1024;                 // 32 lanes x 8 columns x fp32: columns 0-3 of all lanes, then columns 4-7
+constexpr int kS2RingBytes = 16 * kS2RingRowBytes;    // 16 live |lap| rows
+constexpr int kS2XRowFloats = 2 * 34 * 4;             // one exchanged row: [half][34 lane slots] float4 (slots -1 and 32 are padding)
+
+// gray of 8 pixels from planar f32 rows, packed column pairs.  kFast: every value is in [+0, 1] (see k_saliency_stream).
+__device__ __forceinline__ void s2_gray8(const float (&r)[8], const float (&g)[8], const float (&b)[8], f32x2 (&out)[4])
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = __vimax3_u32(m, __float_as_uint(r[i]), __vimax3_u32(__float_as_uint(g[i]), __float_as_uint(b[i]), 0u));
+    if (m <= 0x3F800000u) {
+        const f32x2 k255 = pk2(255.0f, 255.0f), kmagic = pk2(8388608.0f, 8388608.0f);
+        const f32x2 kr = pk2(9798.0f, 9798.0f), kg = pk2(19235.0f, 19235.0f), kb = pk2(3735.0f, 3735.0f);
+        const f32x2 khalf = pk2(16384.0f, 16384.0f), kinv = pk2(0.000030517578125f, 0.000030517578125f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // trunc(v * 255) == RZ(RN(v * 255) + 2^23) - 2^23; the dot product and the shift are exact integer arithmetic in fp32
+            const f32x2 qr = sub2(add2_rz(mul2(pk2(r[2 * j], r[2 * j + 1]), k255), kmagic), kmagic);
+            const f32x2 qg = sub2(add2_rz(mul2(pk2(g[2 * j], g[2 * j + 1]), k255), kmagic), kmagic);
+            const f32x2 qb = sub2(add2_rz(mul2(pk2(b[2 * j], b[2 * j + 1]), k255), kmagic), kmagic);
+            const f32x2 sgr = fma2(qb, kb, fma2(qg, kg, fma2(qr, kr, khalf)));
+            out[j] = sub2(fma2_rz(sgr, kinv, kmagic), kmagic);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = float((quantize_u8(r[2 * j]) * 9798 + quantize_u8(g[2 * j]) * 19235 + quantize_u8(b[2 * j]) * 3735 + 16384) >> 15);
+            const float c = float((quantize_u8(r[2 * j + 1]) * 9798 + quantize_u8(g[2 * j + 1]) * 19235 + quantize_u8(b[2 * j + 1]) * 3735 + 16384) >> 15);
+            out[j] = pk2(a, c);
+        }
+    }
+}
+
+// |4-neighbour Laplacian| of the middle row, 8 columns: vertical part packed, horizontal neighbours scalar (lane edges by shuffle)
+__device__ __forceinline__ void s2_lap8(const f32x2 (&up)[4], const f32x2 (&mid)[4], const f32x2 (&dn)[4], float (&out)[8])
+{
+    const f32x2 kneg4 = pk2(-4.0f, -4.0f);
+    float m[8], v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        upk2(mid[j], m[2 * j], m[2 * j + 1]);
+        upk2(fma2(mid[j], kneg4, add2(up[j], dn[j])), v[2 * j], v[2 * j + 1]);
+    }
+    const float left = __shfl_up_sync(0xffffffffu, m[7], 1), right = __shfl_down_sync(0xffffffffu, m[0], 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float l = i == 0 ? left : m[i - 1], rr = i == 7 ? right : m[i + 1];
+        out[i] = fabsf(__fadd_rn(v[i], __fadd_rn(l, rr)));
+    }
+}
+
+// Requires w % 8 == 0, h >= 16 and 16-byte aligned planes (the named shapes); k_saliency_stream serves everything else.  There is
+// no scalar or reflect-indexed code in this kernel (its instruction stream must stay inside the instruction cache): every lane loads
+// aligned vectors from a clamped column, rows reflect with one comparison, and the two halo lanes that hang over the left / right
+// image border take their gray values -- the reflection of columns 1..8 resp. w-2..w-9 -- from the neighbouring lanes by shuffle.
+__global__ void __launch_bounds__(32, 10)
+k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg_rows, float* __restrict__ blur_out,
+                   SalMinMax* __restrict__ mm, const GaussTapsF taps)
+{
+    __shared__ __align__(16) unsigned char s_ring[kS2RingBytes];
+    __shared__ __align__(16) float s_xch[2][2][kS2XRowFloats];   // [iteration parity][row m / m+1]
+
+    const int lane = threadIdx.x;
+    const int band = blockIdx.x % bands, seg = blockIdx.x / bands;
+    const int f = blockIdx.y;
+    const int r0 = seg * seg_rows, r1 = min(r0 + seg_rows, h);
+    if (r0 >= h) return;
+    const int c0 = band * kSsBandCols - kSsLaneCols + lane * kSsLaneCols;   // plane column of this lane's first pixel
+    const long long plane = (long long)h * w;
+    const float* img = x + (long long)f * 3 * plane + min(max(c0, 0), w - kSsLaneCols);
+    const bool writer = lane >= 1 && lane <= 30 && c0 < w;
+    const bool left_edge = band == 0;                       // lane 0 holds columns -8 .. -1
+    const int lane_r = (w - band * kSsBandCols) / kSsLaneCols + 1;   // the lane that holds columns w .. w+7 (if <= 31)
+    const bool right_edge = lane_r <= 31;
+
+    const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(s_ring)) + uint32_t(lane) * 16u;
+    f32x2 T[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) T[d] = pk2(taps.t[d], taps.t[d]);
+
+    f32x2 gm2[4], gm1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gm2[j] = gm1[j] = 0ull;
+    float mn = INFINITY, mx = -INFINITY;
+
+    auto row_ptr = [&](int k) -> const float* {
+        k = k < 0 ? -k : (k >= h ? 2 * (h - 1) - k : k);      // BORDER_REFLECT_101, |overhang| <= 10 < h
+        return img + (long long)k * w;
+    };
+    float4 nx[2][3][2];
+    auto load_rows = [&](int k) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const float* rp = row_ptr(k + rr);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                nx[rr][c][0] = __ldg(reinterpret_cast<const float4*>(rp + c * plane));
+                nx[rr][c][1] = __ldg(reinterpret_cast<const float4*>(rp + c * plane) + 1);
+            }
+        }
+    };
+    auto prefetch_rows = [&](int k) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const float* rp = row_ptr(k + rr);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + plane));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 2 * plane));
+        }
+    };
+    // gray of one loaded row (packed column pairs) incl. the reflected halo columns at the image borders
+    auto gray_row = [&](const float4 (&v)[3][2], f32x2 (&out)[4]) {
+        const float r[8] = {v[0][0].x, v[0][0].y, v[0][0].z, v[0][0].w, v[0][1].x, v[0][1].y, v[0][1].z, v[0][1].w};
+        const float g[8] = {v[1][0].x, v[1][0].y, v[1][0].z, v[1][0].w, v[1][1].x, v[1][1].y, v[1][1].z, v[1][1].w};
+        const float b[8] = {v[2][0].x, v[2][0].y, v[2][0].z, v[2][0].w, v[2][1].x, v[2][1].y, v[2][1].z, v[2][1].w};
+        s2_gray8(r, g, b, out);
+        if (left_edge || right_edge) {      // warp-uniform
+            float e[8], o[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) upk2(out[j], e[2 * j], e[2 * j + 1]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = e[i];
+            if (left_edge) {
+                // column -8 + i  <-  column 8 - i : lane 2 element 0 (i = 0), lane 1 element 8 - i (i = 1 .. 7)
+                const float t0 = __shfl_sync(0xffffffffu, e[0], 2);
+                if (lane == 0) o[0] = t0;
+#pragma unroll
+                for (int i = 1; i < 8; ++i) {
+                    const float ti = __shfl_sync(0xffffffffu, e[8 - i], 1);
+                    if (lane == 0) o[i] = ti;
+                }
+            }
+            if (right_edge) {
+                // column w + j  <-  column w - 2 - j : lane_r - 1 element 6 - j (j = 0 .. 6), lane_r - 2 element 7 (j = 7)
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const float tj = __shfl_sync(0xffffffffu, e[6 - j], (lane_r - 1) & 31);
+                    if (lane == lane_r) o[j] = tj;
+                }
+                const float t7 = __shfl_sync(0xffffffffu, e[7], (lane_r - 2) & 31);
+                if (lane == lane_r) o[7] = t7;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] = pk2(o[2 * j], o[2 * j + 1]);
+        }
+    };
+
+    // iteration t converts gray rows G0 + 2t, G0 + 2t + 1, forms |lap| rows G0 + 2t - 1, G0 + 2t and, from t = 8 on, the output
+    // rows m = r0 + 2 (t - 8) and m + 1 (|lap| rows m - 7 .. m + 8 are then in the ring)
+    const int G0 = r0 - 8;
+    const int iters = 8 + (r1 - r0 + 1) / 2;
+    load_rows(G0);
+    uint32_t p = 0;   // ring row that receives the first of this iteration's two |lap| rows (even)
+#pragma unroll 1
+    for (int t = 0; t < iters; ++t) {
+        f32x2 ga[4], gb[4];
+        gray_row(nx[0], ga);
+        gray_row(nx[1], gb);
+        if (t + 1 < iters) load_rows(G0 + 2 * (t + 1));
+        if (t + 2 < iters) prefetch_rows(G0 + 2 * (t + 2));
+        {
+            float la[8], lb[8];
+            s2_lap8(gm2, gm1, ga, la);
+            s2_lap8(gm1, ga, gb, lb);
+            const uint32_t a0 = ring0 + p * uint32_t(kS2RingRowBytes);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "f"(la[0]), "f"(la[1]), "f"(la[2]), "f"(la[3]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0+512], {%1,%2,%3,%4};" ::"r"(a0), "f"(la[4]), "f"(la[5]), "f"(la[6]), "f"(la[7]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0+1024], {%1,%2,%3,%4};" ::"r"(a0), "f"(lb[0]), "f"(lb[1]), "f"(lb[2]), "f"(lb[3]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0+1536], {%1,%2,%3,%4};" ::"r"(a0), "f"(lb[4]), "f"(lb[5]), "f"(lb[6]), "f"(lb[7]) : "memory");
+        }
+        if (t >= 8) {
+            // ---- vertical pass of rows m (taps |i - 7|) and m + 1 (taps |i - 8|) over ring rows m - 7 + i, i = 0 .. 15 ----
+            f32x2 am[4], am1[4];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t a = ring0 + (((p + 2u + uint32_t(i)) & 15u) * uint32_t(kS2RingRowBytes));
+                f32x2 v[4];
+                asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "r"(a));
+                asm volatile("ld.shared.v2.b64 {%0,%1}, [%2+512];" : "=l"(v[2]), "=l"(v[3]) : "r"(a));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (i == 0) am[j] = mul2(T[7], v[j]);
+                    else if (i <= 14) am[j] = fma2(T[i < 7 ? 7 - i : i - 7], v[j], am[j]);
+                    if (i == 1) am1[j] = mul2(T[7], v[j]);
+                    else if (i >= 2) am1[j] = fma2(T[i < 8 ? 8 - i : i - 8], v[j], am1[j]);
+                }
+            }
+            // ---- exchange the two rows of vertical sums with the neighbouring lanes ----
+            float* xr0 = s_xch[t & 1][0];
+            float* xr1 = s_xch[t & 1][1];
+            {
+                const uint32_t b0 = uint32_t(__cvta_generic_to_shared(xr0)) + uint32_t(lane + 1) * 16u;
+                const uint32_t b1 = uint32_t(__cvta_generic_to_shared(xr1)) + uint32_t(lane + 1) * 16u;
+                asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(b0), "l"(am[0]), "l"(am[1]) : "memory");
+                asm volatile("st.shared.v2.b64 [%0+544], {%1,%2};" ::"r"(b0), "l"(am[2]), "l"(am[3]) : "memory");
+                asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(b1), "l"(am1[0]), "l"(am1[1]) : "memory");
+                asm volatile("st.shared.v2.b64 [%0+544], {%1,%2};" ::"r"(b1), "l"(am1[2]), "l"(am1[3]) : "memory");
+            }
+            __syncwarp();
+            const int m = r0 + 2 * (t - 8);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const float4* rowA = reinterpret_cast<const float4*>(rr == 0 ? xr0 : xr1) + 1;   // slot -1 and slot 32 are padding
+                const float4* rowB = rowA + 34;
+                float bwin[24];
+                {
+                    const float4 t0 = rowA[lane - 1], t1 = rowB[lane - 1], t4 = rowA[lane + 1], t5 = rowB[lane + 1];
+                    bwin[0] = t0.x; bwin[1] = t0.y; bwin[2] = t0.z; bwin[3] = t0.w;
+                    bwin[4] = t1.x; bwin[5] = t1.y; bwin[6] = t1.z; bwin[7] = t1.w;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) upk2(rr == 0 ? am[j] : am1[j], bwin[8 + 2 * j], bwin[9 + 2 * j]);
+                    bwin[16] = t4.x; bwin[17] = t4.y; bwin[18] = t4.z; bwin[19] = t4.w;
+                    bwin[20] = t5.x; bwin[21] = t5.y; bwin[22] = t5.z; bwin[23] = t5.w;
+                }
+                // horizontal pass: symmetric pair sums are scalar adds into aligned register pairs, the tap FMAs are packed
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = 2 * j;
+                    f32x2 acc = mul2(T[0], pk2(bwin[8 + i], bwin[9 + i]));
+#pragma unroll
+                    for (int d = 1; d <= 7; ++d)
+                        acc = fma2(T[d], pk2(__fadd_rn(bwin[8 + i - d], bwin[8 + i + d]), __fadd_rn(bwin[9 + i - d], bwin[9 + i + d])), acc);
+                    upk2(acc, o[i], o[i + 1]);
+                }
+                const int row = m + rr;
+                if (writer && row < r1) {
+                    float* dst = blur_out + (long long)f * plane + (long long)row * w + c0;
+                    __stcg(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+                    __stcg(reinterpret_cast<float4*>(dst + 4), make_float4(o[4], o[5], o[6], o[7]));
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) { mn = fminf(mn, fminf(o[i], o[i + 1])); mx = fmaxf(mx, fmaxf(o[i], o[i + 1])); }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { gm2[j] = ga[j]; gm1[j] = gb[j]; }
+        p = (p + 2u) & 15u;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -474,13 +797,17 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
         const int bands = (w + kSsBandCols - 1) / kSsBandCols;
         // one warp per (band, row segment, frame): aim at ~6 warps per resident slot (20 warps/SM) for balance, but keep
         // segments >= 64 rows (16 of every segment's rows are re-computed halo)
-        const long long slots = 20LL * kNumSMsB200;
+        const long long slots = (long long)std::max(kSsMinBlocks, 18) * kNumSMsB200;
         long long nseg = (6 * slots + (long long)n * bands - 1) / ((long long)n * bands);
         nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
         const int seg_rows = int((h + nseg - 1) / nseg);
         const int segs = (h + seg_rows - 1) / seg_rows;
         if ((long long)bands * segs > 0x7fffffffLL) return UPR_E_SHAPE;
-        k_saliency_stream<<<dim3(unsigned(bands * segs), n), 32, 0, s>>>(x, h, w, bands, seg_rows, blur, mm, taps);
+        // the packed two-rows-per-iteration kernel serves w % 8 == 0, h >= 16, 16-byte aligned planes; everything else (ragged
+        // widths, tiny images, unaligned views) takes the general one-row kernel with its reflect-indexed scalar loads
+        const bool packed = UPR_SS_GENERATION == 2 && w % 8 == 0 && h >= 16 && aligned16(x) && aligned16(blur);
+        if (packed) k_saliency_stream2<<<dim3(unsigned(bands * segs), n), 32, 0, s>>>(x, h, w, bands, seg_rows, blur, mm, taps);
+        else k_saliency_stream<<<dim3(unsigned(bands * segs), n), 32, 0, s>>>(x, h, w, bands, seg_rows, blur, mm, taps);
     }
     UPR_LAUNCH_CHECK();
     const bool v4 = plane % 4 == 0 && aligned16(x) && aligned16(out) && (mode != 2 || (aligned16(enh) && (!att_out || aligned16(att_out))));

@@ -124,8 +124,8 @@ def test_content_golden(native, golden, small_cases):
         x = O.kat_input(rec["seed"], rec["h"], rec["w"], rec["kind"])
         sal = native.saliency(dev(x)).cpu().numpy()
         att = native.attention(dev(x)).cpu().numpy()
-        assert abs(float(sal.astype(np.float64).mean()) - rec["sal_mean"]) <= 1e-7
-        assert abs(float(att.astype(np.float64).mean()) - rec["att_mean"]) <= 1e-7
+        assert abs(float(sal.astype(np.float64).mean()) - rec["sal_mean"]) <= 3e-7
+        assert abs(float(att.astype(np.float64).mean()) - rec["att_mean"]) <= 3e-7
         assert int(att.argmax()) == rec["att_argmax"] and int(sal.argmax()) == rec["sal_argmax"]
         if f"sal_{rec['seed']}" in small_cases:
             # fp32 blur (the reference blurs in fp64 and rounds the normalised map to fp32): a few 1e-7 absolute on [0,1]
