@@ -298,8 +298,9 @@ k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_
 //   * packed fp32 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: two fp32 lanes per issue slot) on natural column pairs -- the
 //     registers a 128-bit load delivers -- for quantisation, gray, the vertical part of the Laplacian, the whole vertical pass
 //     and the FMA half of the horizontal pass (its pair sums are scalar adds that land in aligned register pairs);
-//   * the |lap| ring holds fp32 (no half <-> float conversions: one per tap and pixel in the first generation), 16 KB per warp;
-//     shared memory then bounds residency at 10 warps per SM, which is enough because every warp carries 16 independent pixels.
+//   * the |lap| ring stays fp16 (exact) and every ring row is converted ONCE per iteration for both output rows; the two rows
+//     formed in the iteration itself never leave registers.  (An fp32 ring needs no conversions but twice the shared-memory
+//     wavefronts: ncu had that variant at 84 % of the L1/shared data pipe with 44 % of the issue slots used.)
 // Same arithmetic as the first generation up to the order of the fp32 tap sums (still far inside the 1e-4 bound, tests).
 // ---------------------------------------------------------------------------------------------
 typedef unsigned long long f32x2;   // (lo, hi) = two fp32 values in an aligned register pair
@@ -352,7 +353,7 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
     return r;
 }
 
-constexpr int kS2RingRowBytes = 1024;                 // 32 lanes x 8 columns x fp32: columns 0-3 of all lanes, then columns 4-7
+constexpr int kS2RingRowBytes = 512;                  // 32 lanes x 8 columns x fp16 (integers <= 1020: exact)
 constexpr int kS2RingBytes = 16 * kS2RingRowBytes;    // 16 live |lap| rows
 constexpr int kS2XRowFloats = 2 * 34 * 4;             // one exchanged row: [half][34 lane slots] float4 (slots -1 and 32 are padding)
 
@@ -407,9 +408,12 @@ __device__ __forceinline__ void s2_lap8(const f32x2 (&up)[4], const f32x2 (&mid)
 // no scalar or reflect-indexed code in this kernel (its instruction stream must stay inside the instruction cache): every lane loads
 // aligned vectors from a clamped column, rows reflect with one comparison, and the two halo lanes that hang over the left / right
 // image border take their gray values -- the reflection of columns 1..8 resp. w-2..w-9 -- from the neighbouring lanes by shuffle.
-__global__ void __launch_bounds__(32, 10)
+// kLum: also leaves luma(x) = .299 r + .587 g + .114 b (content_aware.py:76-78, separately rounded like torch) of the segment's own
+// rows in `lum_out` (frame stride lum_stride floats), so that the attention pass reads 4 instead of 12 B/px.
+template <bool kLum>
+__global__ void __launch_bounds__(32, 12)
 k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg_rows, float* __restrict__ blur_out,
-                   SalMinMax* __restrict__ mm, const GaussTapsF taps)
+                   SalMinMax* __restrict__ mm, const GaussTapsF taps, float* __restrict__ lum_out, long long lum_stride)
 {
     __shared__ __align__(16) unsigned char s_ring[kS2RingBytes];
     __shared__ __align__(16) float s_xch[2][2][kS2XRowFloats];   // [iteration parity][row m / m+1]
@@ -463,10 +467,20 @@ k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg
         }
     };
     // gray of one loaded row (packed column pairs) incl. the reflected halo columns at the image borders
-    auto gray_row = [&](const float4 (&v)[3][2], f32x2 (&out)[4]) {
+    auto gray_row = [&](const float4 (&v)[3][2], f32x2 (&out)[4], int k) {
         const float r[8] = {v[0][0].x, v[0][0].y, v[0][0].z, v[0][0].w, v[0][1].x, v[0][1].y, v[0][1].z, v[0][1].w};
         const float g[8] = {v[1][0].x, v[1][0].y, v[1][0].z, v[1][0].w, v[1][1].x, v[1][1].y, v[1][1].z, v[1][1].w};
         const float b[8] = {v[2][0].x, v[2][0].y, v[2][0].z, v[2][0].w, v[2][1].x, v[2][1].y, v[2][1].z, v[2][1].w};
+        if constexpr (kLum) {
+            if (writer && k >= r0 && k < r1) {      // rows of this segment only (never a reflected row)
+                float l[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) l[i] = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r[i]), __fmul_rn(0.587f, g[i])), __fmul_rn(0.114f, b[i]));
+                float* dst = lum_out + (long long)f * lum_stride + (long long)k * w + c0;
+                __stcg(reinterpret_cast<float4*>(dst), make_float4(l[0], l[1], l[2], l[3]));
+                __stcg(reinterpret_cast<float4*>(dst + 4), make_float4(l[4], l[5], l[6], l[7]));
+            }
+        }
         s2_gray8(r, g, b, out);
         if (left_edge || right_edge) {      // warp-uniform
             float e[8], o[8];
@@ -508,29 +522,47 @@ k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg
 #pragma unroll 1
     for (int t = 0; t < iters; ++t) {
         f32x2 ga[4], gb[4];
-        gray_row(nx[0], ga);
-        gray_row(nx[1], gb);
+        gray_row(nx[0], ga, G0 + 2 * t);
+        gray_row(nx[1], gb, G0 + 2 * t + 1);
         if (t + 1 < iters) load_rows(G0 + 2 * (t + 1));
         if (t + 2 < iters) prefetch_rows(G0 + 2 * (t + 2));
+        float la[8], lb[8];
+        s2_lap8(gm2, gm1, ga, la);
+        s2_lap8(gm1, ga, gb, lb);
+        uint32_t ha[4], hb[4];       // the two new |lap| rows as fp16 pairs
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __half2 a2 = __floats2half2_rn(la[2 * j], la[2 * j + 1]), b2 = __floats2half2_rn(lb[2 * j], lb[2 * j + 1]);
+            ha[j] = *reinterpret_cast<const uint32_t*>(&a2);
+            hb[j] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
         {
-            float la[8], lb[8];
-            s2_lap8(gm2, gm1, ga, la);
-            s2_lap8(gm1, ga, gb, lb);
             const uint32_t a0 = ring0 + p * uint32_t(kS2RingRowBytes);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "f"(la[0]), "f"(la[1]), "f"(la[2]), "f"(la[3]) : "memory");
-            asm volatile("st.shared.v4.f32 [%0+512], {%1,%2,%3,%4};" ::"r"(a0), "f"(la[4]), "f"(la[5]), "f"(la[6]), "f"(la[7]) : "memory");
-            asm volatile("st.shared.v4.f32 [%0+1024], {%1,%2,%3,%4};" ::"r"(a0), "f"(lb[0]), "f"(lb[1]), "f"(lb[2]), "f"(lb[3]) : "memory");
-            asm volatile("st.shared.v4.f32 [%0+1536], {%1,%2,%3,%4};" ::"r"(a0), "f"(lb[4]), "f"(lb[5]), "f"(lb[6]), "f"(lb[7]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(ha[0]), "r"(ha[1]), "r"(ha[2]), "r"(ha[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0+512], {%1,%2,%3,%4};" ::"r"(a0), "r"(hb[0]), "r"(hb[1]), "r"(hb[2]), "r"(hb[3]) : "memory");
         }
         if (t >= 8) {
-            // ---- vertical pass of rows m (taps |i - 7|) and m + 1 (taps |i - 8|) over ring rows m - 7 + i, i = 0 .. 15 ----
+            // ---- vertical pass of rows m (taps |i - 7|) and m + 1 (taps |i - 8|) over |lap| rows m - 7 + i, i = 0 .. 15: rows
+            // 0 .. 13 stream from the fp16 ring (one 128-bit load per row and lane), rows 14 and 15 are this iteration's own
+            // registers.  (Keeping 4 .. 12 more rows in registers across iterations changes nothing: 0.61-0.63 ms either way --
+            // with the luma plane written as well the kernel moves 3.0 GB per 16 x 4K in 0.48 ms, i.e. it runs at the HBM rate) ----
             f32x2 am[4], am1[4];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const uint32_t a = ring0 + (((p + 2u + uint32_t(i)) & 15u) * uint32_t(kS2RingRowBytes));
                 f32x2 v[4];
-                asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "r"(a));
-                asm volatile("ld.shared.v2.b64 {%0,%1}, [%2+512];" : "=l"(v[2]), "=l"(v[3]) : "r"(a));
+                if (i < 14) {
+                    uint32_t u[4];
+                    const uint32_t a = ring0 + (((p + 2u + uint32_t(i)) & 15u) * uint32_t(kS2RingRowBytes));
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(a));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u[j]));
+                        v[j] = pk2(c.x, c.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = i == 14 ? pk2(la[2 * j], la[2 * j + 1]) : pk2(lb[2 * j], lb[2 * j + 1]);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (i == 0) am[j] = mul2(T[7], v[j]);
@@ -603,19 +635,30 @@ k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg
 }
 
 // sal = float((blur - min) / (max - min + 1e-8)); optional attention raw value + its fp32 min/max.
-// blur is held in fp32 (so min and max are fp32 values): the subtraction is done exactly in fp64, the quotient in fp32
-// (IEEE division) -- within 1 ulp of the reference's fp64 quotient rounded to fp32, without a 30-instruction fp64 divide
-// per pixel (the first version of this kernel ran at 2.4 TB/s because of it).  VEC = 4 pixels per thread.
-template <bool kAttention, int VEC>
+// blur is held in fp32 (so min and max are fp32 values).  Per pixel: one fp32 subtraction, one multiplication by the per-image
+// reciprocal of the range (formed once per thread in fp64) and, for the attention, one multiplication by rcp.approx(luma + 0.1):
+// within ~3 ulp of the reference's quotients -- 4e-7 on maps normalised to [0,1], against a stated bound of 1e-4 (the
+// full-map oracle tests hold 2e-6) -- instead of two IEEE divisions and an fp64 round trip per pixel, which kept this kernel on
+// the XU pipe (ncu round 3: 43-46 %) instead of on its memory streams.  VEC = 4 pixels per thread.
+__device__ __forceinline__ float rcp_approx(float v)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// kLumPlane: `x` is a luma plane left behind by k_saliency_stream2<true> (frame stride x_stride floats) instead of the RGB frame.
+template <bool kAttention, int VEC, bool kLumPlane = false>
 __global__ void __launch_bounds__(kSalThreads)
 k_sal_normalize(const float* __restrict__ blur, const float* __restrict__ x, float* __restrict__ out, long long plane,
-                SalMinMax* __restrict__ mm)
+                SalMinMax* __restrict__ mm, long long x_stride = 0)
 {
     __shared__ float s_mn[kSalThreads / 32], s_mx[kSalThreads / 32];
     const int f = blockIdx.y;
     const double bmn = key_dbl(mm[f].blur_min), bmx = key_dbl(mm[f].blur_max);
-    const float den = float(bmx - bmn + 1e-8);
-    const float* img = x + (long long)f * 3 * plane;
+    const float bmn_f = float(bmn);                       // exact: the minimum of fp32 values
+    const float inv_den = float(1.0 / (bmx - bmn + 1e-8));
+    const float* img = x + (long long)f * (kLumPlane ? x_stride : 3 * plane);
     const float* bl = blur + (long long)f * plane;
     float* o = out + (long long)f * plane;
     float mn = INFINITY, mx = -INFINITY;
@@ -626,7 +669,10 @@ k_sal_normalize(const float* __restrict__ blur, const float* __restrict__ x, flo
         if (VEC == 4) {
             const float4 t = __ldcs(reinterpret_cast<const float4*>(bl) + i);
             b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
-            if (kAttention) {
+            if (kAttention && kLumPlane) {
+                const float4 tl = __ldcs(reinterpret_cast<const float4*>(img) + i);
+                r[0] = tl.x; r[1] = tl.y; r[2] = tl.z; r[3] = tl.w;
+            } else if (kAttention) {
                 const float4 tr = __ldg(reinterpret_cast<const float4*>(img) + i);
                 const float4 tg = __ldg(reinterpret_cast<const float4*>(img + plane) + i);
                 const float4 tb = __ldg(reinterpret_cast<const float4*>(img + 2 * plane) + i);
@@ -640,10 +686,11 @@ k_sal_normalize(const float* __restrict__ blur, const float* __restrict__ x, flo
         }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            const float sal = __fdiv_rn(float(double(b[k]) - bmn), den);
+            const float sal = __fmul_rn(__fsub_rn(b[k], bmn_f), inv_den);
             if (kAttention) {
-                const float lum = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r[k]), __fmul_rn(0.587f, g[k])), __fmul_rn(0.114f, bb[k]));
-                const float a = __fmul_rn(sal, __fdiv_rn(1.0f, __fadd_rn(lum, 0.1f)));
+                const float lum = kLumPlane ? r[k]
+                                            : __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r[k]), __fmul_rn(0.587f, g[k])), __fmul_rn(0.114f, bb[k]));
+                const float a = __fmul_rn(sal, rcp_approx(__fadd_rn(lum, 0.1f)));
                 res[k] = a;
                 mn = fminf(mn, a);
                 mx = fmaxf(mx, a);
@@ -673,26 +720,32 @@ k_sal_normalize(const float* __restrict__ blur, const float* __restrict__ x, flo
     }
 }
 
+// 1 / (max - min + 1e-8) of the raw attention (content_aware.py:88-89), once per thread: the per-pixel quotient becomes a product
+__device__ __forceinline__ float att_inv_range(float mn, float mx)
+{
+    return __fdiv_rn(1.0f, __fadd_rn(__fsub_rn(mx, mn), 1e-8f));
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(kSalThreads)
 k_att_normalize(float* __restrict__ att, long long plane, const SalMinMax* __restrict__ mm)
 {
     const int f = blockIdx.y;
     const float mn = key_flt(mm[f].att_min), mx = key_flt(mm[f].att_max);
-    const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-8f);
+    const float inv = att_inv_range(mn, mx);
     const long long nvec = plane / VEC;
     const long long stride = (long long)gridDim.x * kSalThreads;
     float* base = att + (long long)f * plane;
     for (long long i = (long long)blockIdx.x * kSalThreads + threadIdx.x; i < nvec; i += stride) {
         if (VEC == 4) {
             float4 v = reinterpret_cast<float4*>(base)[i];
-            v.x = __fdiv_rn(__fsub_rn(v.x, mn), den);
-            v.y = __fdiv_rn(__fsub_rn(v.y, mn), den);
-            v.z = __fdiv_rn(__fsub_rn(v.z, mn), den);
-            v.w = __fdiv_rn(__fsub_rn(v.w, mn), den);
+            v.x = __fmul_rn(__fsub_rn(v.x, mn), inv);
+            v.y = __fmul_rn(__fsub_rn(v.y, mn), inv);
+            v.z = __fmul_rn(__fsub_rn(v.z, mn), inv);
+            v.w = __fmul_rn(__fsub_rn(v.w, mn), inv);
             reinterpret_cast<float4*>(base)[i] = v;
         } else {
-            base[i] = __fdiv_rn(__fsub_rn(base[i], mn), den);
+            base[i] = __fmul_rn(__fsub_rn(base[i], mn), inv);
         }
     }
 }
@@ -713,13 +766,14 @@ k_att_gain(const float* __restrict__ raw, const float* __restrict__ enh, float* 
     const int f = blockIdx.y;
     const float ms_gain = kGain ? __ldg(gain + f) : 1.0f;
     const float mn = key_flt(mm[f].att_min), mx = key_flt(mm[f].att_max);
-    const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-8f);
+    const float inv = att_inv_range(mn, mx);
     const float* r = raw + (long long)f * plane;
     const float* e = enh + (long long)f * 3 * plane;
     float* o = out + (long long)f * 3 * plane;
     float* ao = kWriteAtt ? att_out + (long long)f * plane : nullptr;
     const long long nvec = plane / VEC;
     const long long stride = (long long)gridDim.x * kSalThreads;
+#pragma unroll 2
     for (long long i = (long long)blockIdx.x * kSalThreads + threadIdx.x; i < nvec; i += stride) {
         float a[VEC], g[VEC];
         if (VEC == 4) {
@@ -730,7 +784,7 @@ k_att_gain(const float* __restrict__ raw, const float* __restrict__ enh, float* 
         }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            a[k] = __fdiv_rn(__fsub_rn(a[k], mn), den);
+            a[k] = __fmul_rn(__fsub_rn(a[k], mn), inv);
             g[k] = __fadd_rn(1.0f, __fmul_rn(0.2f, a[k]));
         }
         if (kWriteAtt) {
@@ -792,6 +846,7 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
     const long long plane = (long long)h * w;
     k_sal_reset<<<(n + 127) / 128, 128, 0, s>>>(mm, n);
     UPR_LAUNCH_CHECK();
+    bool lum_in_out = false;
     {
         static const GaussTapsF taps = sal_taps_f();
         const int bands = (w + kSsBandCols - 1) / kSsBandCols;
@@ -806,7 +861,20 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
         // the packed two-rows-per-iteration kernel serves w % 8 == 0, h >= 16, 16-byte aligned planes; everything else (ragged
         // widths, tiny images, unaligned views) takes the general one-row kernel with its reflect-indexed scalar loads
         const bool packed = UPR_SS_GENERATION == 2 && w % 8 == 0 && h >= 16 && aligned16(x) && aligned16(blur);
-        if (packed) k_saliency_stream2<<<dim3(unsigned(bands * segs), n), 32, 0, s>>>(x, h, w, bands, seg_rows, blur, mm, taps);
+        // content-aware apply: the result frame is free scratch until the last pass writes it -- its first plane takes luma(x),
+        // which the attention pass then reads instead of the 12 B/px frame (not when `out` aliases an input)
+        if (packed && mode == 2 && aligned16(out)) {
+            const char *o0 = reinterpret_cast<const char*>(out), *o1 = o0 + size_t(n) * 3 * plane * sizeof(float);
+            auto overlaps = [&](const void* q) {
+                const char* q0 = reinterpret_cast<const char*>(q);
+                return q0 < o1 && q0 + size_t(n) * 3 * plane * sizeof(float) > o0;
+            };
+            lum_in_out = !overlaps(enh) && !overlaps(x);
+        }
+        if (packed && lum_in_out)
+            k_saliency_stream2<true><<<dim3(unsigned(bands * segs), n), 32, 0, s>>>(x, h, w, bands, seg_rows, blur, mm, taps, out, 3 * plane);
+        else if (packed)
+            k_saliency_stream2<false><<<dim3(unsigned(bands * segs), n), 32, 0, s>>>(x, h, w, bands, seg_rows, blur, mm, taps, nullptr, 0);
         else k_saliency_stream<<<dim3(unsigned(bands * segs), n), 32, 0, s>>>(x, h, w, bands, seg_rows, blur, mm, taps);
     }
     UPR_LAUNCH_CHECK();
@@ -820,7 +888,8 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
         UPR_LAUNCH_CHECK();
     } else if (mode == 2) {
         // raw attention over the blur plane in place (each element is read and written by the same thread)
-        if (v4) k_sal_normalize<true, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, blur, plane, mm);
+        if (lum_in_out) k_sal_normalize<true, 4, true><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, out, blur, plane, mm, 3 * plane);
+        else if (v4) k_sal_normalize<true, 4><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, blur, plane, mm);
         else k_sal_normalize<true, 1><<<dim3(parts, n), kSalThreads, 0, s>>>(blur, x, blur, plane, mm);
         UPR_LAUNCH_CHECK();
         const dim3 grid(parts, n);

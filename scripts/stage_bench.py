@@ -9,4 +9,4 @@ native.clahe_lab(x,out=out)
 r={}
 for m,name in ((1,"k1"),(2,"k3"),(3,"op")):
     r[name]=time_op(lambda: native.clahe_lab(x,out=out,stage_mask=m),20)[0]
-print(json.dumps({"variant":os.environ.get("UPR_CLAHE_VARIANT"),"dbg":os.environ.get("UPR_CLAHE_DBG"),**r}))
+print(json.dumps(r))

@@ -334,6 +334,16 @@ def test_content_aware_apply_fused(native):
         out, att2 = native.content_aware_apply(dev(xs), dev(enh), want_attention=True)
         assert torch.equal(out, ref) and torch.equal(att2, att)
         assert torch.equal(native.content_aware_apply(dev(xs), dev(enh)), ref)
+    # the vector path parks luma(x) in the result frame between its passes: bit-identical to the plain path, and switched off when
+    # the result aliases an input (in-place apply)
+    xs = np.concatenate([O.kat_input(705 + i, 64, 256, k) for i, k in enumerate(["uniform", "dark"])])
+    enh = np.random.default_rng(706).random((2, 3, 64, 256), dtype=np.float32) * 1.3
+    ref = native.attention_apply(dev(enh), native.attention(dev(xs)))
+    assert torch.equal(native.content_aware_apply(dev(xs), dev(enh)), ref)
+    e2 = dev(enh)
+    assert torch.equal(native.content_aware_apply(dev(xs), e2, out=e2), ref)
+    x2 = dev(xs)
+    assert torch.equal(native.content_aware_apply(x2, dev(enh), out=x2), ref)
 
 
 def test_content_multiscale_chain(native):
