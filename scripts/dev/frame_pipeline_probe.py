@@ -48,6 +48,10 @@ def graph_of(per_frame, n, nstreams, group):
     return g
 
 
+GROUPS = tuple(int(v) for v in os.environ.get('FPC', '1,2,4').split(','))
+STREAMS = tuple(int(v) for v in os.environ.get('STREAMS', '1,2,3,4').split(','))
+
+
 def main():
     res = {}
     for name, (n, h, w) in {"4k": (16, 2160, 3840), "1080p": (64, 1080, 1920)}.items():
@@ -57,8 +61,8 @@ def main():
         base_ca = time_ms(lambda: native.content_aware_apply(x, enh, out=out))
         base_cl = time_ms(lambda: native.clahe_lab(x, out=out))
         r = {"content_aware_batch_ms": base_ca, "clahe_batch_ms": base_cl, "variants": []}
-        for group in (1, 2, 4):
-            for ns in (1, 2, 3, 4):
+        for group in GROUPS:
+            for ns in STREAMS:
                 if group * ns > n:
                     continue
                 try:

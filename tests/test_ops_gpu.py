@@ -346,6 +346,34 @@ def test_content_aware_apply_fused(native):
     assert torch.equal(native.content_aware_apply(x2, dev(enh), out=x2), ref)
 
 
+def test_chunked_two_stream_schedule(native):
+    """Batches of >= 2 chunks (~25 Mpx each) run their passes chunk by chunk on two library-owned side streams: same bits as frame
+    by frame calls, for every entry point, also when captured in a CUDA graph (the side streams fork from and join the caller's)."""
+    n, h, w = 7, 2160, 3840
+    g = torch.Generator(device="cuda").manual_seed(77)
+    x = torch.rand((n, 3, h, w), device="cuda", generator=g) * 0.7
+    enh = torch.rand((n, 3, h, w), device="cuda", generator=g) * 1.2
+    out = native.content_aware_apply(x, enh)
+    sal, att = native.saliency(x), native.attention(x)
+    chain, gain = native.content_multiscale_apply(x, enh)
+    for i in (0, 3, 6):
+        assert torch.equal(out[i:i + 1], native.content_aware_apply(x[i:i + 1], enh[i:i + 1]))
+        assert torch.equal(sal[i:i + 1], native.saliency(x[i:i + 1])) and torch.equal(att[i:i + 1], native.attention(x[i:i + 1]))
+        assert torch.equal(chain[i:i + 1], native.content_multiscale_apply(x[i:i + 1], enh[i:i + 1])[0])
+    np.testing.assert_allclose(att[6:7].cpu().numpy(), O.attention(x[6:7].cpu().numpy()), rtol=0, atol=4e-6)
+    torch.cuda.synchronize()
+    xs, es = x.clone(), enh.clone()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        got = native.content_aware_apply(xs, es)
+    xs.zero_(); es.zero_()
+    graph.replay()
+    xs.copy_(x); es.copy_(enh)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(got, out)
+
+
 def test_content_multiscale_chain(native):
     """BASELINE config 5: content-aware then multi-scale on the same CNN output, one shared epilogue -- bit-identical to the two
     enhancers' own epilogues back to back, and equal to the oracle's composition within the attention tolerance."""
