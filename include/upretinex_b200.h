@@ -238,6 +238,11 @@ UPR_API int upr_edge_smooth_loss_f32(const float* illu, const float* img_low, in
  * counter >= 1, the same on every rank, strictly increasing.  method: 0 = 'tv', 1 = 'edge_density'.  All ranks must
  * call it (collective); a peer that never arrives traps the kernel after ~1 s instead of hanging. */
 UPR_API size_t upr_peer_stats_buffer_bytes(void);
+/* Wall-clock bound on the wait for a peer inside upr_texture_weight_peer_f32 (default 600 000 ms).  A rank whose peer does not
+ * arrive in time returns NaN statistics / weight and records {sequence number of the failed call, rank it waited for} in its
+ * own buffer; upr_peer_status copies those two words to the host (synchronises `stream`; {0, 0} = no failure so far). */
+UPR_API int upr_peer_set_timeout_ms(double ms);
+UPR_API int upr_peer_status(const void* own_buffer_dev, unsigned* status2_host, upr_stream_t stream);
 UPR_API int upr_texture_weight_peer_f32(const float* x, int n, int c, int h, int w, int method, float* per_image,
                                         float* batch_stats2, void* workspace, size_t workspace_bytes,
                                         const unsigned long long* peer_buffers_dev, int rank, int world, unsigned seq,

@@ -405,7 +405,7 @@ __device__ __forceinline__ void s2_lap8(const f32x2 (&up)[4], const f32x2 (&mid)
     }
 }
 
-// Requires w % 8 == 0, h >= 16 and 16-byte aligned planes (the named shapes); k_saliency_stream serves everything else.  There is
+// Requires w % 8 == 0, w >= 16, h >= 16 and 16-byte aligned planes (the named shapes); k_saliency_stream serves everything else.  There is
 // no scalar or reflect-indexed code in this kernel (its instruction stream must stay inside the instruction cache): every lane loads
 // aligned vectors from a clamped column, rows reflect with one comparison, and the two halo lanes that hang over the left / right
 // image border take their gray values -- the reflection of columns 1..8 resp. w-2..w-9 -- from the neighbouring lanes by shuffle.
@@ -857,7 +857,8 @@ static int sal_launch(int mode, const float* x, int n, int h, int w, float* out,
         if ((long long)bands * segs > 0x7fffffffLL) return UPR_E_SHAPE;
         // the packed two-rows-per-iteration kernel serves w % 8 == 0, h >= 16, 16-byte aligned planes; everything else (ragged
         // widths, tiny images, unaligned views) takes the general one-row kernel with its reflect-indexed scalar loads
-        const bool packed = UPR_SS_GENERATION == 2 && w % 8 == 0 && h >= 16 && aligned16(x) && aligned16(blur);
+        // (w >= 16, h >= 16: one reflection must bring every halo column / row back inside the image)
+        const bool packed = UPR_SS_GENERATION == 2 && w % 8 == 0 && w >= 16 && h >= 16 && aligned16(x) && aligned16(blur);
         // content-aware apply: the result frame is free scratch until the last pass writes it -- its first plane takes luma(x),
         // which the attention pass then reads instead of the 12 B/px frame (not when `out` aliases an input)
         lum_in_out = packed && mode == 2 && lum_ok && aligned16(out);

@@ -60,8 +60,15 @@ __device__ __forceinline__ bool last_cta_of(unsigned* ticket, unsigned nparts, i
 // system-wide, raises the flags, then waits for the W flags of its own buffer and adds the W pairs in rank order -- all
 // ranks add the same numbers in the same order, so every rank derives the bit-identical weight.  Two parities: a rank can
 // be at most one call ahead of its slowest peer (it needs that peer's flag of the current call to finish).
+// A peer that does not arrive within the time-out (wall clock, %globaltimer; default 10 minutes like NCCL's, settable with
+// upr_peer_set_timeout_ms) does NOT trap the kernel: the waiting rank records {seq, missing rank} in the status word at the end of
+// its own buffer, returns NaN statistics / weight (which poison the loss visibly) and the host raises from upr_peer_status /
+// DynamicSmoothWeight.check_peers().  Every rank must call once per step, in lockstep.
 constexpr int kPeerMax = 64;
-constexpr size_t kPeerBufBytes = size_t(2) * kPeerMax * 2 * sizeof(float) + size_t(2) * kPeerMax * sizeof(unsigned);
+constexpr size_t kPeerDataBytes = size_t(2) * kPeerMax * 2 * sizeof(float) + size_t(2) * kPeerMax * sizeof(unsigned);
+constexpr size_t kPeerStatusOff = (kPeerDataBytes + 15) / 16 * 16;     // unsigned[2]: {seq of the failed call, rank waited for}
+constexpr size_t kPeerBufBytes = kPeerStatusOff + 16;
+static unsigned long long g_peer_timeout_ns = 600ull * 1000ull * 1000ull * 1000ull;
 
 struct PeerXchg {
     const unsigned long long* peers;   // device array [world] of peer buffer addresses; nullptr = single process
@@ -69,7 +76,15 @@ struct PeerXchg {
     unsigned seq;                      // >= 1, strictly increasing per call on this buffer set
     float w0;                          // weight_smooth
     float* weight_out;                 // device scalar, may be nullptr
+    unsigned long long timeout_ns;     // wall-clock bound on the wait for a peer's flag
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ float dyn_weight(float sum, float count, float w0)
 {
@@ -94,10 +109,18 @@ __device__ __forceinline__ void peer_exchange(const PeerXchg& px, float& s, floa
     }
     const unsigned long long mine = px.peers[px.rank];
     volatile unsigned* myflags = reinterpret_cast<volatile unsigned*>(mine + size_t(2) * kPeerMax * 2 * sizeof(float)) + size_t(par) * kPeerMax;
+    const unsigned long long t_start = global_timer_ns();
     for (int r = 0; r < px.world; ++r) {
-        long long spins = 0;
+        unsigned spins = 0;
         while (myflags[r] != px.seq) {
-            if (++spins > (1LL << 28)) __trap();   // a peer that never arrives must fail loudly, not hang the device
+            if ((++spins & 1023u) == 0 && global_timer_ns() - t_start > px.timeout_ns) {
+                // a peer that never arrives (skipped step, crashed rank) must neither hang nor fault the device
+                volatile unsigned* status = reinterpret_cast<volatile unsigned*>(mine + kPeerStatusOff);
+                status[1] = unsigned(r);
+                status[0] = px.seq;
+                s = cnt = __int_as_float(0x7fc00000);
+                return;
+            }
         }
     }
     __threadfence_system();
@@ -116,7 +139,7 @@ __device__ __forceinline__ void peer_exchange(const PeerXchg& px, float& s, floa
 // the two numbers the data-parallel all-reduce carries (loss.py:710 batch mean).  With a peer table the all-reduce
 // happens right here and the dynamic smoothness weight is written too.
 __device__ __forceinline__ void finish_batch(unsigned* batch_ticket, int n, const float* per_image, float* stats2,
-                                             const PeerXchg px = PeerXchg{nullptr, 0, 1, 0u, 0.0f, nullptr})
+                                             const PeerXchg px = PeerXchg{nullptr, 0, 1, 0u, 0.0f, nullptr, 0ull})
 {
     if (!stats2) return;
     __threadfence();
@@ -662,7 +685,7 @@ int upr_texture_workspace_init(void* workspace, size_t workspace_bytes, int n, u
 
 static int texture_run(int method, const float* x, int n, int c, int h, int w, float* per_image, float* stats2,
                        void* ws, size_t ws_bytes, cudaStream_t s,
-                       const upr::PeerXchg px = upr::PeerXchg{nullptr, 0, 1, 0u, 0.0f, nullptr})
+                       const upr::PeerXchg px = upr::PeerXchg{nullptr, 0, 1, 0u, 0.0f, nullptr, 0ull})
 {
     if (n < 0 || n > 65535 || c <= 0 || h <= 0 || w <= 0) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
@@ -804,6 +827,23 @@ int upr_enh_losses_grad_f32(const float* enhanced, const float* img_low, int n, 
 
 size_t upr_peer_stats_buffer_bytes(void) { return upr::kPeerBufBytes; }
 
+int upr_peer_set_timeout_ms(double ms)
+{
+    if (!(ms > 0.0) || ms > 1e12) return UPR_E_PARAM;
+    upr::g_peer_timeout_ns = (unsigned long long)(ms * 1e6);
+    return UPR_OK;
+}
+
+int upr_peer_status(const void* own_buffer_dev, unsigned* status2_host, upr_stream_t stream)
+{
+    if (!own_buffer_dev || !status2_host) return UPR_E_NULL;
+    auto s = static_cast<cudaStream_t>(stream);
+    UPR_CUDA_TRY(cudaMemcpyAsync(status2_host, static_cast<const char*>(own_buffer_dev) + upr::kPeerStatusOff, 2 * sizeof(unsigned),
+                                 cudaMemcpyDeviceToHost, s));
+    UPR_CUDA_TRY(cudaStreamSynchronize(s));
+    return UPR_OK;
+}
+
 int upr_texture_weight_peer_f32(const float* x, int n, int c, int h, int w, int method, float* per_image, float* batch_stats2,
                                 void* workspace, size_t workspace_bytes, const unsigned long long* peer_buffers_dev, int rank,
                                 int world, unsigned seq, float weight_smooth, float* weight_out, upr_stream_t stream)
@@ -812,7 +852,7 @@ int upr_texture_weight_peer_f32(const float* x, int n, int c, int h, int w, int 
     if (!batch_stats2 || !weight_out) return UPR_E_NULL;
     if (peer_buffers_dev && (world < 1 || world > upr::kPeerMax || rank < 0 || rank >= world || seq == 0)) return UPR_E_PARAM;
     if (n <= 0) return UPR_E_SHAPE;   // every rank must contribute to the exchange
-    const upr::PeerXchg px{peer_buffers_dev, rank, world, seq, weight_smooth, weight_out};
+    const upr::PeerXchg px{peer_buffers_dev, rank, world, seq, weight_smooth, weight_out, upr::g_peer_timeout_ns};
     return texture_run(method, x, n, c, h, w, per_image, batch_stats2, workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream), px);
 }

@@ -73,6 +73,16 @@ class PeerBatchStats:
         self.seq += 1
         return self.seq
 
+    def check(self) -> None:
+        """Raise if an exchange on this rank timed out waiting for a peer (the kernel then returned NaN statistics instead of
+        hanging or trapping).  Synchronises the current stream: call it once per epoch / when a NaN weight shows up."""
+        import ctypes
+        st = (ctypes.c_uint * 2)()
+        native.check(native.lib().upr_peer_status(self.buf.data_ptr(), st, torch.cuda.current_stream().cuda_stream), "upr_peer_status")
+        if st[0] != 0:
+            raise native.UprError(-4, f"upr_texture_weight_peer_f32: call #{st[0]} on rank {self.rank} timed out waiting for rank "
+                                      f"{st[1]} (every rank must call once per step, in lockstep)")
+
 
 class DynamicSmoothWeight:
     """``TotalLoss``'s dynamic smoothness weight (losses/loss.py:607-656 constructor arguments
@@ -106,6 +116,11 @@ class DynamicSmoothWeight:
         _per_image, stats = batch_texture_stats(img_low, self.texture_method)
         all_reduce_batch_stats(stats, self.group)
         return weight_from_stats(stats, self.weight_smooth)
+
+    def check_peers(self) -> None:
+        """fused_collective only: raise if a peer-memory exchange timed out (see PeerBatchStats.check)."""
+        if self._peer is not None:
+            self._peer.check()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -112,6 +112,10 @@ def _declare(lib):
     lib.upr_edge_smooth_loss_f32.restype = i32
     lib.upr_edge_smooth_loss_f32.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp, sz, vp]
     lib.upr_peer_stats_buffer_bytes.restype = sz
+    lib.upr_peer_set_timeout_ms.restype = i32
+    lib.upr_peer_set_timeout_ms.argtypes = [f64]
+    lib.upr_peer_status.restype = i32
+    lib.upr_peer_status.argtypes = [vp, vp, vp]
     lib.upr_texture_weight_peer_f32.restype = i32
     lib.upr_texture_weight_peer_f32.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, i32, i32, C.c_uint, f32, vp, vp]
     lib.upr_dynamic_smooth_weight_f32.restype = i32

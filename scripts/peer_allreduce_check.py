@@ -60,13 +60,30 @@ def main():
         e.record()
         torch.cuda.synchronize()
         res[name] = {"us_per_step_device": s.elapsed_time(e) * 1e3 / 200, "us_per_step_wall": (time.perf_counter() - t0) * 1e6 / 200}
-    flag = torch.tensor([1.0 if ok else 0.0, 1.0 if close else 0.0, 1.0 if exact_vs_nccl else 0.0], device=dev)
+    # a peer that skips a step: the waiting rank gets NaN after the time-out and an exception from check_peers() -- no hang, no trap
+    from retinex_image_enhancement_b200 import native
+    fused.check_peers()                                   # nothing failed so far
+    native.check(native.lib().upr_peer_set_timeout_ms(150.0), "upr_peer_set_timeout_ms")
+    torch.cuda.synchronize()
+    dist.barrier()
+    timeout_ok = True
+    if rank == 0:
+        w_late = fused(x)                                 # the other ranks never make this call
+        torch.cuda.synchronize()
+        timeout_ok = bool(torch.isnan(w_late).item())
+        try:
+            fused.check_peers()
+            timeout_ok = False
+        except native.UprError as e:
+            timeout_ok = timeout_ok and "timed out waiting for rank" in str(e)
+    dist.barrier()
+    flag = torch.tensor([1.0 if ok else 0.0, 1.0 if close else 0.0, 1.0 if exact_vs_nccl else 0.0, 1.0 if timeout_ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    good = bool(flag[0].item() == 1.0 and flag[1].item() == 1.0)
+    good = bool(flag[0].item() == 1.0 and flag[1].item() == 1.0 and flag[3].item() == 1.0)
     if rank == 0:
         print(json.dumps({"world": world, "weights_identical_across_ranks": bool(flag[0].item() == 1.0),
                           "within_1e-6_of_nccl_path": bool(flag[1].item() == 1.0), "bit_equal_to_nccl_path": bool(flag[2].item() == 1.0),
-                          **res}))
+                          "late_peer_times_out_with_nan_and_status": bool(flag[3].item() == 1.0), **res}))
     dist.destroy_process_group()
     return 0 if good else 1
 

@@ -269,7 +269,8 @@ def test_multiscale_full_shapes_vs_oracle(native, n, h, w):
         assert abs(float(g[i]) - f_ref) <= 2e-7 * f_ref + 6e-8
 
 
-@pytest.mark.parametrize("n,h,w", [(1, 2160, 3840), (2, 1080, 1920), (2, 70, 250), (1, 33, 481), (1, 3, 9), (1, 600, 17), (1, 20, 243)])
+@pytest.mark.parametrize("n,h,w", [(1, 2160, 3840), (2, 1080, 1920), (2, 70, 250), (1, 33, 481), (1, 3, 9), (1, 600, 17), (1, 20, 243),
+                                   (1, 17, 8), (1, 16, 16), (2, 17, 24), (1, 40, 240), (1, 31, 248), (3, 16, 480), (1, 15, 32)])
 def test_saliency_attention_full_shapes_vs_oracle(native, n, h, w):
     """upr_saliency_f32 / upr_attention_f32 / upr_content_aware_apply_f32 against the oracle, FULL maps, at the BASELINE shapes
     and at band edges (w not a multiple of the band width, lanes that straddle the right border), reflect-101 on narrow / short
@@ -409,6 +410,7 @@ def test_fused_peer_allreduce_two_gpus():
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
     rep = json.loads(line)
     assert rep["weights_identical_across_ranks"] and rep["within_1e-6_of_nccl_path"] and rep["bit_equal_to_nccl_path"]
+    assert rep["late_peer_times_out_with_nan_and_status"]
 
 
 def test_texture_weight_peer_single_process(native):
