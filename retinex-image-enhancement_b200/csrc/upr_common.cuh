@@ -129,6 +129,62 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int k)
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 | k)) - 8388608.0f;
 }
 
+// ---------------------------------------------------------------------------------------
+// Blackwell packed fp32: FFMA2 / FADD2 / FMUL2 process two fp32 lanes per issue slot on an aligned register pair.
+// CAUTION: ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2 into one FFMA2 -- with .rn on both, inside asm volatile and under
+// -fmad=false -- so these are only for arithmetic that is exact in fp32 or tolerant of contraction; a mixed-rounding pair
+// (mul.rn then add.rz) is left alone.  (profiles/r4_saliency.md)
+// ---------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;   // (lo, hi) = two fp32 values in an aligned register pair
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2_rz(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    // volatile: ptxas contracts mul.rn.f32x2 + add/sub.f32x2 into FFMA2 (observed), which would skip the rounding of x * 255
+    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm volatile("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 __device__ __forceinline__ int warp_sum(int v)
 {
 #pragma unroll

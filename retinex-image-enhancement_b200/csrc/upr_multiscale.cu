@@ -187,15 +187,27 @@ __device__ __forceinline__ float ms_mag(float dx, float dy)
     return r;
 }
 
-// sum over the lane's pixels of sqrt(dx^2 + dy^2) for one row of 4 / 2 / 1 values; dy is already formed
-__device__ __forceinline__ float ms_edge4(const float v[4], const float dy[4], bool isL, bool isR)
+// sum over the lane's pixels of sqrt(dx^2 + dy^2) for one row of 4 / 2 / 1 values; dy is already formed.
+// Four-value rows: dy arrives as two packed pairs, dx^2 + dy^2 is two FMUL2 + two FFMA2, the four roots are summed as a pair.
+__device__ __forceinline__ float ms_edge4(f32x2 v01, f32x2 v23, f32x2 dy01, f32x2 dy23, bool isL, bool isR)
 {
+    float v[4];
+    upk2(v01, v[0], v[1]);
+    upk2(v23, v[2], v[3]);
     const float left = __shfl_up_sync(0xffffffffu, v[3], 1), right = __shfl_down_sync(0xffffffffu, v[0], 1);
     const float d10 = __fsub_rn(v[1], v[0]), d32 = __fsub_rn(v[3], v[2]);
     const float dx0 = isL ? __fadd_rn(d10, d10) : __fsub_rn(v[1], left);
     const float dx3 = isR ? __fadd_rn(d32, d32) : __fsub_rn(right, v[2]);
-    return __fadd_rn(__fadd_rn(ms_mag(dx0, dy[0]), ms_mag(__fsub_rn(v[2], v[0]), dy[1])),
-                     __fadd_rn(ms_mag(__fsub_rn(v[3], v[1]), dy[2]), ms_mag(dx3, dy[3])));
+    const f32x2 dxa = pk2(dx0, __fsub_rn(v[2], v[0])), dxb = pk2(__fsub_rn(v[3], v[1]), dx3);
+    float m[4];
+    upk2(fma2(dxa, dxa, mul2(dy01, dy01)), m[0], m[1]);
+    upk2(fma2(dxb, dxb, mul2(dy23, dy23)), m[2], m[3]);
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r[i]) : "f"(m[i]));
+    float lo, hi;
+    upk2(add2(pk2(r[0], r[1]), pk2(r[2], r[3])), lo, hi);
+    return __fadd_rn(lo, hi);
 }
 __device__ __forceinline__ float ms_edge2(const float v[2], const float dy[2], bool isL, bool isR)
 {
@@ -229,12 +241,12 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
     const long long plane = (long long)h * w;
     const float* img = x + (long long)f * 3 * plane + cl;
 
-    float P2[3][4], P3[3][4], HB0[3][2], HB1[3][2], Q1[3], Q2[3];
+    // rows 4q-2 / 4q-1 of the previous step as packed column pairs {0,1}, {2,3}; half rows as pairs; quarter pixels as scalars
+    f32x2 P2[3][2], P3[3][2], HB0[3], HB1[3];
+    float Q1[3], Q2[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) P2[c][i] = P3[c][i] = 0.0f;
-        HB0[c][0] = HB0[c][1] = HB1[c][0] = HB1[c][1] = 0.0f;
+        P2[c][0] = P2[c][1] = P3[c][0] = P3[c][1] = HB0[c] = HB1[c] = 0ull;
         Q1[c] = Q2[c] = 0.0f;
     }
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
@@ -269,72 +281,80 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
             for (int c = 0; c < 3; ++c) {
                 const float wsum = c == 0 ? 1.299f : (c == 1 ? 1.587f : 1.114f);   // 1 + luma weight
                 // software pipeline: the four rows of the NEXT (step, channel) are requested before this one is reduced
-                // (ncu: 54 % of the stall samples of the un-pipelined kernel sat on the first use of these loads)
-                float R[4][4];
+                // (ncu: 54 % of the stall samples of the un-pipelined kernel sat on the first use of these loads).
+                // Row j of the step as the two natural column pairs of its 128-bit load: A[j] = {0,1}, B[j] = {2,3}
+                // (packed fp32: differences, squares and block sums run two lanes per issue slot; the kernel is issue-bound).
+                f32x2 A[4], B[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { R[j][0] = N[j].x; R[j][1] = N[j].y; R[j][2] = N[j].z; R[j][3] = N[j].w; }
+                for (int j = 0; j < 4; ++j) { A[j] = pk2(N[j].x, N[j].y); B[j] = pk2(N[j].z, N[j].w); }
                 if (c < 2) { if (have) load_rows(q, c + 1); }
                 else if (q + 1 <= q1 && q + 1 < Q) load_rows(q + 1, 0);
                 // 2x2 block sums (= 4 x half-resolution pixels) and the centre 2x2 (= 4 x quarter-resolution pixel)
-                float B0[2], B1[2];
-                B0[0] = __fadd_rn(__fadd_rn(R[0][0], R[0][1]), __fadd_rn(R[1][0], R[1][1]));
-                B0[1] = __fadd_rn(__fadd_rn(R[0][2], R[0][3]), __fadd_rn(R[1][2], R[1][3]));
-                B1[0] = __fadd_rn(__fadd_rn(R[2][0], R[2][1]), __fadd_rn(R[3][0], R[3][1]));
-                B1[1] = __fadd_rn(__fadd_rn(R[2][2], R[2][3]), __fadd_rn(R[3][2], R[3][3]));
-                const float Qc = __fadd_rn(__fadd_rn(R[1][1], R[1][2]), __fadd_rn(R[2][1], R[2][2]));
+                float s0, s1, s2, s3;
+                upk2(add2(A[0], A[1]), s0, s1);
+                upk2(add2(B[0], B[1]), s2, s3);
+                const f32x2 HBa = pk2(__fadd_rn(s0, s1), __fadd_rn(s2, s3));        // half row 2q
+                upk2(add2(A[2], A[3]), s0, s1);
+                upk2(add2(B[2], B[3]), s2, s3);
+                const f32x2 HBb = pk2(__fadd_rn(s0, s1), __fadd_rn(s2, s3));        // half row 2q+1
+                float c1lo, c1hi, c2lo, c2hi;
+                upk2(add2(A[1], A[2]), c1lo, c1hi);      // rows 1+2, columns 0 | 1
+                upk2(add2(B[1], B[2]), c2lo, c2hi);      // rows 1+2, columns 2 | 3
+                const float Qc = __fadd_rn(c1hi, c2lo);
                 float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+                const f32x2 two = pk2(2.0f, 2.0f);
                 // ---- rows completed by this step: image row 4q-1, half row 2q-1, quarter row q-1 ----
                 if (q >= 1) {
-                    float dy4[4], dy2[2];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float dlast = __fsub_rn(P3[c][i], P2[c][i]);
-                        dy4[i] = have ? __fsub_rn(R[0][i], P2[c][i]) : __fadd_rn(dlast, dlast);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const float dlast = __fsub_rn(HB1[c][i], HB0[c][i]);
-                        dy2[i] = have ? __fsub_rn(B0[i], HB0[c][i]) : __fadd_rn(dlast, dlast);
+                    f32x2 dy4a, dy4b, dy2p;
+                    if (have) {
+                        dy4a = sub2(A[0], P2[c][0]); dy4b = sub2(B[0], P2[c][1]);
+                        dy2p = sub2(HBa, HB0[c]);
+                    } else {
+                        dy4a = mul2(sub2(P3[c][0], P2[c][0]), two); dy4b = mul2(sub2(P3[c][1], P2[c][1]), two);
+                        dy2p = mul2(sub2(HB1[c], HB0[c]), two);
                     }
                     float dy1;
                     if (q == 1) { const float d = __fsub_rn(Qc, Q1[c]); dy1 = __fadd_rn(d, d); }       // quarter row 0: one-sided
                     else if (have) dy1 = __fsub_rn(Qc, Q2[c]);
                     else { const float d = __fsub_rn(Q1[c], Q2[c]); dy1 = __fadd_rn(d, d); }          // last quarter row
-                    const float a0 = ms_edge4(P3[c], dy4, isL, isR);
-                    const float a1 = ms_edge2(HB1[c], dy2, isL, isR);
+                    const float a0 = ms_edge4(P3[c][0], P3[c][1], dy4a, dy4b, isL, isR);
+                    float hv[2], hd[2];
+                    upk2(HB1[c], hv[0], hv[1]);
+                    upk2(dy2p, hd[0], hd[1]);
+                    const float a1 = ms_edge2(hv, hd, isL, isR);
                     const float a2 = ms_edge1(Q1[c], dy1, isL, isR);
                     if (prev_in) { e0 = a0; e1 = a1; e2 = a2; }
                 }
                 // ---- rows 4q .. 4q+2, half row 2q ----
                 if (have) {
-                    float dyA[4], dyB[4], dyC[4], dyH[2];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float d01 = __fsub_rn(R[1][i], R[0][i]);
-                        dyA[i] = q == 0 ? __fadd_rn(d01, d01) : __fsub_rn(R[1][i], P3[c][i]);
-                        dyB[i] = __fsub_rn(R[2][i], R[0][i]);
-                        dyC[i] = __fsub_rn(R[3][i], R[1][i]);
+                    f32x2 dyAa, dyAb, dyHp;
+                    if (q == 0) {
+                        dyAa = mul2(sub2(A[1], A[0]), two); dyAb = mul2(sub2(B[1], B[0]), two);
+                        dyHp = mul2(sub2(HBb, HBa), two);
+                    } else {
+                        dyAa = sub2(A[1], P3[c][0]); dyAb = sub2(B[1], P3[c][1]);
+                        dyHp = sub2(HBb, HB1[c]);
                     }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const float d01 = __fsub_rn(B1[i], B0[i]);
-                        dyH[i] = q == 0 ? __fadd_rn(d01, d01) : __fsub_rn(B1[i], HB1[c][i]);
-                    }
-                    const float a0 = __fadd_rn(__fadd_rn(ms_edge4(R[0], dyA, isL, isR), ms_edge4(R[1], dyB, isL, isR)),
-                                               ms_edge4(R[2], dyC, isL, isR));
-                    const float a1 = ms_edge2(B0, dyH, isL, isR);
+                    const float a0 = __fadd_rn(__fadd_rn(ms_edge4(A[0], B[0], dyAa, dyAb, isL, isR),
+                                                         ms_edge4(A[1], B[1], sub2(A[2], A[0]), sub2(B[2], B[0]), isL, isR)),
+                                               ms_edge4(A[2], B[2], sub2(A[3], A[1]), sub2(B[3], B[1]), isL, isR));
+                    float hv[2], hd[2];
+                    upk2(HBa, hv[0], hv[1]);
+                    upk2(dyHp, hd[0], hd[1]);
+                    const float a1 = ms_edge2(hv, hd, isL, isR);
                     if (inner) {
                         e0 = __fadd_rn(e0, a0);
                         e1 = __fadd_rn(e1, a1);
-                        const float sfull = __fadd_rn(__fadd_rn(B0[0], B0[1]), __fadd_rn(B1[0], B1[1]));
+                        float f0, f1;
+                        upk2(add2(HBa, HBb), f0, f1);
+                        const float sfull = __fadd_rn(f0, f1);
                         // channel sums: full = sum of the 16 pixels, half = 0.25 * the same, quarter = 0.25 * centre sum
                         t0 = __fmaf_rn(wsum, sfull, t0);
                         t1 = __fmaf_rn(wsum * 0.25f, sfull, t1);
                         t2 = __fmaf_rn(wsum * 0.25f, Qc, t2);
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { P2[c][i] = R[2][i]; P3[c][i] = R[3][i]; }
-                    HB0[c][0] = B0[0]; HB0[c][1] = B0[1]; HB1[c][0] = B1[0]; HB1[c][1] = B1[1];
+                    P2[c][0] = A[2]; P2[c][1] = B[2]; P3[c][0] = A[3]; P3[c][1] = B[3];
+                    HB0[c] = HBa; HB1[c] = HBb;
                     Q2[c] = Q1[c]; Q1[c] = Qc;
                 }
                 // |grad| = 0.5 * sqrt(.) of un-halved differences; half / quarter pixels carry their factor 0.25

@@ -304,56 +304,6 @@ k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_
 //     wavefronts: ncu had that variant at 84 % of the L1/shared data pipe with 44 % of the issue slots used.)
 // Same arithmetic as the first generation up to the order of the fp32 tap sums (still far inside the 1e-4 bound, tests).
 // ---------------------------------------------------------------------------------------------
-typedef unsigned long long f32x2;   // (lo, hi) = two fp32 values in an aligned register pair
-
-__device__ __forceinline__ f32x2 pk2(float lo, float hi)
-{
-    f32x2 r;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi)
-{
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ f32x2 fma2_rz(f32x2 a, f32x2 b, f32x2 c)
-{
-    f32x2 r;
-    asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-    f32x2 r;
-    // volatile: ptxas contracts mul.rn.f32x2 + add/sub.f32x2 into FFMA2 (observed), which would skip the rounding of x * 255
-    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
-{
-    f32x2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b)
-{
-    f32x2 r;
-    asm volatile("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
-{
-    f32x2 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
 constexpr int kS2RingRowBytes = 512;                  // 32 lanes x 8 columns x fp16 (integers <= 1020: exact)
 constexpr int kS2RingBytes = 16 * kS2RingRowBytes;    // 16 live |lap| rows
 constexpr int kS2XRowFloats = 2 * 34 * 4;             // one exchanged row: [half][34 lane slots] float4 (slots -1 and 32 are padding)
