@@ -70,7 +70,33 @@ struct MapGeom {
     uint32_t ay_bias;  // 0 - 0x4B400000 * 128 as a parameter (see ClaheGeom::gam_bias)
     int bx[kMaxTiles + 2];  // cell c covers x in [bx[c], bx[c+1]); raw tile index of the cell is c-1
     int by[kMaxTiles + 2];
+    // work-queue order of the persistent map kernel: LARGEST cells first.  Interior cells are a whole tile, border cells half of
+    // one, corner cells a quarter; with the small ones at the very end of the queue the CTAs run dry within a quarter-item of
+    // each other instead of a whole one.  order[] lists the cells by descending area in three size classes of n_class[] cells.
+    int n_class[3];
+    unsigned short order[(kMaxTiles + 1) * (kMaxTiles + 1)];
 };
+
+// queue position -> (frame, cell, strip): all frames' class-0 items, then all class-1 items, then all class-2 items
+__device__ __forceinline__ void map_item(const MapGeom& g, int item, int& f, int& cell, int& strip)
+{
+    int base_rank = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int per = g.n_class[c] * g.nstrips;        // items of this class per frame
+        const int all = per * g.n;
+        if (item < all || c == 2) {
+            f = item / max(per, 1);
+            const int r = item - f * per;
+            const int k = r / g.nstrips;
+            strip = r - k * g.nstrips;
+            cell = g.order[base_rank + k];
+            return;
+        }
+        item -= all;
+        base_rank += g.n_class[c];
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // raw shared/global access helpers of the second-generation kernels
@@ -781,12 +807,9 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, v
     __shared__ int s_nxt[2];
 
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int ncells = (g.tiles_x + 1) * (g.tiles_y + 1);
-    const int per_frame = ncells * g.nstrips;
-
     auto build_quad = [&](int item, uint32_t* dst) {   // tid < 256
-        const int f = item / per_frame, rem = item - f * per_frame;
-        const int cell = rem / g.nstrips;
+        int f, cell, strip_unused;
+        map_item(g, item, f, cell, strip_unused);
         const int cy = cell / (g.tiles_x + 1), cx = cell - cy * (g.tiles_x + 1);
         const int ty1 = max(cy - 1, 0), ty2 = min(cy, g.tiles_y - 1);
         const int tx1 = max(cx - 1, 0), tx2 = min(cx, g.tiles_x - 1);
@@ -841,8 +864,8 @@ k_map_vec5(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ lut_g, v
         if (tid == 0) s_nxt[buf ^ 1] = int(gridDim.x + atomicAdd(work, 1u));
         t.quad = quad0 + uint32_t(buf) * 1024u;
 
-        const int f = cur / per_frame, rem = cur - f * per_frame;
-        const int cell = rem / g.nstrips, strip = rem - cell * g.nstrips;
+        int f, cell, strip;
+        map_item(g, cur, f, cell, strip);
         const int cy = cell / (g.tiles_x + 1), cx = cell - cy * (g.tiles_x + 1);
         const int x0 = g.bx[cx], x1 = g.bx[cx + 1];
         const int rows_cell = g.by[cy + 1] - g.by[cy];
@@ -1096,6 +1119,22 @@ static int clahe_run(const void* in_v, void* out_v, int n, int h, int w, double 
         }
         while (c < tiles_y + 1) m.by[++c] = h;
         for (int i = 0; i <= tiles_x + 1 && fast; ++i) fast = (m.bx[i] % 4 == 0);
+        if (fast) {
+            const int nc = (tiles_x + 1) * (tiles_y + 1);
+            long long area[(kMaxTiles + 1) * (kMaxTiles + 1)], amax = 0;
+            for (int c = 0; c < nc; ++c) {
+                const int cy = c / (tiles_x + 1), cx = c % (tiles_x + 1);
+                area[c] = (long long)(m.bx[cx + 1] - m.bx[cx]) * (m.by[cy + 1] - m.by[cy]);
+                amax = std::max(amax, area[c]);
+                m.order[c] = (unsigned short)c;
+            }
+            std::stable_sort(m.order, m.order + nc, [&](unsigned short a, unsigned short b) { return area[a] > area[b]; });
+            m.n_class[0] = m.n_class[1] = m.n_class[2] = 0;
+            for (int k = 0; k < nc; ++k) {
+                const long long a = area[m.order[k]];
+                ++m.n_class[4 * a >= 3 * amax ? 0 : (10 * a >= 3 * amax ? 1 : 2)];
+            }
+        }
     }
 
     if (rx && !fast) return kNeedUnfused;
@@ -1163,6 +1202,7 @@ static int clahe_run(const void* in_v, void* out_v, int n, int h, int w, double 
                     int ks5 = std::max(1, int((size_t(4) * resident + size_t(nf) * ncells - 1) / (size_t(nf) * ncells)));
                     ks5 = std::min(ks5, std::max(cell_rows / 16, 1));
                     m.nstrips = ks5;
+                    m.n = nf;          // frames of THIS launch: the queue order interleaves them (map_item)
                     const long long nitems = (long long)nf * ncells * ks5;
                     if (nitems > 0x7fffffffLL / 2) return UPR_E_SHAPE;
                     if (!work_cleared) UPR_CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(unsigned), stream));

@@ -108,16 +108,7 @@ __device__ __forceinline__ void ss_load8(const float* __restrict__ row, int c0, 
     }
 }
 
-// resident one-warp CTAs per SM the kernel is compiled for (register cap = 65536 / (32 * kSsMinBlocks))
-#ifndef UPR_SS_MINBLOCKS
-#define UPR_SS_MINBLOCKS 1
-#endif
-constexpr int kSsMinBlocks = UPR_SS_MINBLOCKS;
-#ifndef UPR_SS_GENERATION
-#define UPR_SS_GENERATION 2
-#endif
-
-__global__ void __launch_bounds__(32, kSsMinBlocks)
+__global__ void __launch_bounds__(32)
 k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, float* __restrict__ blur_out,
                   SalMinMax* __restrict__ mm, const GaussTapsF taps)
 {
@@ -799,7 +790,9 @@ static int sal_launch(int mode, const float* x, int n, int h, int w, float* out,
         const int bands = (w + kSsBandCols - 1) / kSsBandCols;
         // one warp per (band, row segment, frame): aim at ~6 warps per resident slot (20 warps/SM) for balance, but keep
         // segments >= 64 rows (16 of every segment's rows are re-computed halo)
-        const long long slots = (long long)std::max(kSsMinBlocks, 18) * kNumSMsB200;
+        // (segments of 96 / 128 / 192 rows re-read fewer halo rows but leave too few warps: content-aware op 1.31 -> 1.34 / 1.38 /
+        // 1.43 ms per 16 x 4K)
+        const long long slots = 18LL * kNumSMsB200;
         long long nseg = (6 * slots + (long long)n * bands - 1) / ((long long)n * bands);
         nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
         const int seg_rows = int((h + nseg - 1) / nseg);
@@ -808,7 +801,7 @@ static int sal_launch(int mode, const float* x, int n, int h, int w, float* out,
         // the packed two-rows-per-iteration kernel serves w % 8 == 0, h >= 16, 16-byte aligned planes; everything else (ragged
         // widths, tiny images, unaligned views) takes the general one-row kernel with its reflect-indexed scalar loads
         // (w >= 16, h >= 16: one reflection must bring every halo column / row back inside the image)
-        const bool packed = UPR_SS_GENERATION == 2 && w % 8 == 0 && w >= 16 && h >= 16 && aligned16(x) && aligned16(blur);
+        const bool packed = w % 8 == 0 && w >= 16 && h >= 16 && aligned16(x) && aligned16(blur);
         // content-aware apply: the result frame is free scratch until the last pass writes it -- its first plane takes luma(x),
         // which the attention pass then reads instead of the 12 B/px frame (not when `out` aliases an input)
         lum_in_out = packed && mode == 2 && lum_ok && aligned16(out);
