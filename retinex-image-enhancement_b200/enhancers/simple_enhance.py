@@ -68,7 +68,7 @@ def _decode_u8(image_path):
     """File -> contiguous uint8 [H,W,3] array and the file's (W, H), decoded like the reference (PIL, RGB)."""
     from PIL import Image
     img = Image.open(image_path).convert("RGB")
-    return np.ascontiguousarray(np.asarray(img, dtype=np.uint8)), img.size
+    return np.array(img, dtype=np.uint8), img.size      # (a writable copy: torch.from_numpy refuses read-only buffers)
 
 
 def _geometry(h, w, max_size):
@@ -180,13 +180,15 @@ def _stream_ring(dev, count=3):
 
 
 def enhance_frames_host_u8(model, frames_u8, out_enh, out_illu, device, max_size=None, enable_multi_scale=False,
-                           enable_content_aware=False, out_low=None, chunk=8):
+                           enable_content_aware=False, out_low=None, chunk=8, frame_fn=None):
     """The device side of the batch driver, end to end at the uint8 boundary: HOST frames as decoded ([N,H,W,3] u8, pinned for
     full PCIe speed) -> HOST frames as ``save_image`` would store them (``out_enh`` [N,H',W',3] u8, ``out_illu`` [N,H',W',1] u8;
     ``out_low`` [N,H',W',3] receives the letterboxed input when ``max_size`` changes it).  The batch is cut into chunks of
     ``chunk`` frames that rotate over three CUDA streams: the upload of chunk k+1 and the download of chunk k-1 overlap the
     kernels of chunk k; 3 B/px go up, 4 B/px come back.  Returns the CUDA events of the chunks, in order: ``event.synchronize()``
-    before reading the corresponding frames of the output buffers (the PNG writers of enhance_batch_images do exactly that)."""
+    before reading the corresponding frames of the output buffers (the PNG writers of enhance_batch_images do exactly that).
+    ``frame_fn(low [n,3,H',W'] f32 CUDA) -> (enhanced u8 [n,H',W',3], illumination u8 [n,H',W',1])`` replaces the enhancer dispatch
+    (predict_batch passes the bare model)."""
     from .. import native
     dev = torch.device(resolve_device(device))
     n, h, w = frames_u8.shape[0], frames_u8.shape[1], frames_u8.shape[2]
@@ -203,7 +205,7 @@ def enhance_frames_host_u8(model, frames_u8, out_enh, out_illu, device, max_size
             st.wait_event(ready)
             with torch.cuda.stream(st):
                 low = native.letterbox(frames_u8[f0:f1].to(dev, non_blocking=True), (rh, rw), top, left, out_hw)
-                enh8, illu8 = enhance_frames_u8(model, low, enable_multi_scale, enable_content_aware)
+                enh8, illu8 = frame_fn(low) if frame_fn is not None else enhance_frames_u8(model, low, enable_multi_scale, enable_content_aware)
                 out_enh[f0:f1].copy_(enh8, non_blocking=True)
                 out_illu[f0:f1].copy_(illu8, non_blocking=True)
                 if out_low is not None:
@@ -286,20 +288,13 @@ class _Staging:
         return slot
 
 
-def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_multi_scale=False,
-                         enable_content_aware=False, batch_size=16, model=None, decode_workers=None, encode_workers=None):
+def run_batch_pipeline(files, output_dir, device, max_size, batch_size, frame_fn, write_files, host_fn,
+                       decode_workers=None, encode_workers=None):
+    """The three-stage pipeline behind enhance_batch_images and predict_batch: decode pool -> pinned double-buffered u8 staging ->
+    one device batch per run of same-shaped frames (``frame_fn``, see enhance_frames_host_u8) -> PNG pool (``write_files(stem,
+    low8, enh8, illu8)`` runs on a writer thread once the batch's CUDA event has fired).  ``host_fn(path, u8 array)`` handles a
+    frame when ``device`` is not a CUDA device."""
     from concurrent.futures import ThreadPoolExecutor
-    device = resolve_device(device)
-    print("正在加载模型...")
-    if model is None:
-        model = UP_Retinex().to(device).eval()
-    files = list_images(input_dir)
-    if not files:
-        print(f"在目录 '{input_dir}' 中未找到有效图像文件")
-        return
-    mine = shard_for_rank(files)
-    print(f"找到 {len(files)} 个图像文件 (本进程处理 {len(mine)} 个)")
-    t0 = time.time()
     os.makedirs(output_dir, exist_ok=True)
     on_gpu = torch.device(device).type == "cuda"
     cores = os.cpu_count() or 1
@@ -308,8 +303,8 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
     futures, last_write_of_stem = [], {}
 
     def submit_write(stem, task):
-        """PNG tasks of inputs that share a stem (a.jpg and a.png) target the same three files: chain them so that they are
-        written one after the other, in list order, like the reference's sequential loop (the last one wins)."""
+        """PNG tasks of inputs that share a stem (a.jpg and a.png) target the same files: chain them so that they are written
+        one after the other, in list order, like the reference's sequential loop (the last one wins)."""
         prev = last_write_of_stem.get(stem)
 
         def run():
@@ -321,28 +316,13 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
         futures.append(fut)
         return fut
 
-    def png_task(path, low8, enh8, illu8, event):
-        stem = os.path.splitext(os.path.basename(path))[0]
-
-        def task():
-            if event is not None:
-                event.synchronize()          # the batch's D2H copies have landed in the pinned buffers
-            save_image(enh8, os.path.join(output_dir, f"{stem}_enhanced.png"))
-            save_image(illu8, os.path.join(output_dir, f"{stem}_illumination.png"))
-            create_comparison(low8, enh8, os.path.join(output_dir, f"{stem}_comparison.png"))
-        return stem, task
-
     staging = _Staging(batch_size)
 
     def run_batch(batch):
         """batch: list of (path, u8 HWC array) of one shape."""
-        if not on_gpu:        # host tensors: the reference's own behaviour, one by one (the hot-path ops will refuse them)
+        if not on_gpu:
             for path, arr in batch:
-                low = torch.from_numpy(arr).permute(2, 0, 1).to(torch.float32).div(255.0).unsqueeze(0)
-                if max_size is not None:
-                    low = letterbox_tensor(low[0], new_shape=max_size, auto=True, scaleup=False)[0].unsqueeze(0)
-                enhanced, illu = _enhance_tensor(model, low, device, enable_multi_scale, enable_content_aware)
-                futures.append(_write_outputs(low, enhanced, illu, path, output_dir, pool=writers))
+                host_fn(path, arr)
             return
         b = len(batch)
         h, w = batch[0][1].shape[:2]
@@ -351,18 +331,22 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
         slot = staging.acquire((h, w), out_hw, not identity)
         for i, (_p, arr) in enumerate(batch):
             slot["in"][i].copy_(torch.from_numpy(arr))
-        event = enhance_frames_host_u8(model, slot["in"][:b], slot["enh"][:b], slot["illu"][:b], device, max_size,
-                                       enable_multi_scale, enable_content_aware, out_low=None if identity else slot["low"][:b],
-                                       chunk=b)[-1]
+        event = enhance_frames_host_u8(None, slot["in"][:b], slot["enh"][:b], slot["illu"][:b], device, max_size,
+                                       out_low=None if identity else slot["low"][:b], chunk=b, frame_fn=frame_fn)[-1]
         for i, (path, arr) in enumerate(batch):
+            stem = os.path.splitext(os.path.basename(path))[0]
             low8 = arr if identity else slot["low"][i].numpy()      # un-letterboxed: the decoded bytes ARE the stored input
-            stem, task = png_task(path, low8, slot["enh"][i].numpy(), slot["illu"][i].numpy(), event)
+            enh8, illu8 = slot["enh"][i].numpy(), slot["illu"][i].numpy()
+
+            def task(stem=stem, low8=low8, enh8=enh8, illu8=illu8):
+                event.synchronize()          # the batch's D2H copies have landed in the pinned buffers
+                write_files(stem, low8, enh8, illu8)
             slot["readers"].append(submit_write(stem, task))
 
     try:
         window = deque()
         ahead = max(2 * batch_size, 4)
-        it = iter(mine)
+        it = iter(files)
         pending = []            # consecutive same-shape frames form one device batch
 
         def top_up():
@@ -389,6 +373,37 @@ def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_mu
     finally:
         decoders.shutdown(wait=True)
         writers.shutdown(wait=True)
+
+
+def enhance_batch_images(input_dir, output_dir, device, max_size=None, enable_multi_scale=False,
+                         enable_content_aware=False, batch_size=16, model=None, decode_workers=None, encode_workers=None):
+    device = resolve_device(device)
+    print("正在加载模型...")
+    if model is None:
+        model = UP_Retinex().to(device).eval()
+    files = list_images(input_dir)
+    if not files:
+        print(f"在目录 '{input_dir}' 中未找到有效图像文件")
+        return
+    mine = shard_for_rank(files)
+    print(f"找到 {len(files)} 个图像文件 (本进程处理 {len(mine)} 个)")
+    t0 = time.time()
+
+    def write_files(stem, low8, enh8, illu8):
+        save_image(enh8, os.path.join(output_dir, f"{stem}_enhanced.png"))
+        save_image(illu8, os.path.join(output_dir, f"{stem}_illumination.png"))
+        create_comparison(low8, enh8, os.path.join(output_dir, f"{stem}_comparison.png"))
+
+    def host_fn(path, arr):      # host tensors: the reference's own behaviour, one by one (the hot-path ops will refuse them)
+        low = torch.from_numpy(arr).permute(2, 0, 1).to(torch.float32).div(255.0).unsqueeze(0)
+        if max_size is not None:
+            low = letterbox_tensor(low[0], new_shape=max_size, auto=True, scaleup=False)[0].unsqueeze(0)
+        enhanced, illu = _enhance_tensor(model, low, device, enable_multi_scale, enable_content_aware)
+        _write_outputs(low, enhanced, illu, path, output_dir)
+
+    run_batch_pipeline(mine, output_dir, device, max_size, batch_size,
+                       lambda low: enhance_frames_u8(model, low, enable_multi_scale, enable_content_aware), write_files, host_fn,
+                       decode_workers, encode_workers)
     total = time.time() - t0
     print("=" * 50)
     print(f"总共处理了 {len(mine)} 张图像")

@@ -41,17 +41,36 @@ def predict_single_image(model, image_path, output_dir, device, max_size=None, s
         create_comparison(img_low, img_enhanced, illu_map, os.path.join(output_dir, f"{stem}_comparison.png"))
 
 
-def predict_batch(model, input_dir, output_dir, device, max_size=None, save_comparison=True):
+def predict_batch(model, input_dir, output_dir, device, max_size=None, save_comparison=True, batch_size=16):
+    """predict.py:186-235 over the batch pipeline of enhancers/simple_enhance.py: files are decoded ahead of
+    the GPU, same-shaped frames run as one device batch (uint8 up, uint8 enhanced + illumination down), PNGs are encoded on a
+    thread pool.  Same three files per image as predict_single_image."""
+    from ..enhancers.simple_enhance import resolve_device, run_batch_pipeline
+    from .. import native
     files = [f for f in list_images(input_dir) if os.path.splitext(f)[1].lower() in {".jpg", ".jpeg", ".png", ".bmp"}]
     if not files:
         print(f"No images found in {input_dir}")
         return
+    device = resolve_device(device)
     mine = shard_for_rank(files)
     print(f"Found {len(files)} images ({len(mine)} on this rank)")
     t0 = time.time()
-    for i, path in enumerate(mine, 1):
-        print(f"Processing [{i}/{len(mine)}]: {os.path.basename(path)}")
+
+    def frame_fn(low):
+        with torch.no_grad():
+            enhanced, _reflectance, illu = model(low)
+        return native.quantize_u8(enhanced.contiguous()), native.quantize_u8(illu.contiguous())
+
+    def write_files(stem, low8, enh8, illu8):
+        save_image(enh8, os.path.join(output_dir, f"{stem}_enhanced.png"))
+        save_image(illu8, os.path.join(output_dir, f"{stem}_illumination.png"))
+        if save_comparison:
+            create_comparison(low8, enh8, illu8, os.path.join(output_dir, f"{stem}_comparison.png"))
+
+    def host_fn(path, _arr):
         predict_single_image(model, path, output_dir, device, max_size, save_comparison)
+
+    run_batch_pipeline(mine, output_dir, device, max_size, batch_size, frame_fn, write_files, host_fn)
     total = time.time() - t0
     print(f"Total images processed: {len(mine)}\nTotal time: {total:.2f}s")
     if mine:

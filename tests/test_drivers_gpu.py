@@ -167,6 +167,24 @@ def test_batch_driver_pipeline(cuda, tmp_path):
     assert np.array_equal(_read_png(tmp_path / "ca1" / "f2_enhanced.png"), _read_png(tmp_path / "ca" / "f2_enhanced.png"))
 
 
+def test_predict_batch_pipeline(cuda, tmp_path):
+    """predict_batch runs on the same decode -> device batch -> PNG pipeline: same bytes as predict_single_image, file by file."""
+    from retinex_image_enhancement_b200.predictors.predict import predict_batch, predict_single_image
+    src = tmp_path / "in"
+    src.mkdir()
+    for i in range(5):
+        _write_png(str(src / f"p{i}.png"), 96, 160, 70 + i)
+    _write_png(str(src / "q.png"), 64, 64, 80)
+    model = MapsStub().to(cuda).eval()
+    predict_batch(model, str(src), str(tmp_path / "batch"), cuda, batch_size=2)
+    for name in [f"p{i}" for i in range(5)] + ["q"]:
+        predict_single_image(model, str(src / f"{name}.png"), str(tmp_path / "single"), cuda)
+        for suffix in ("enhanced", "illumination", "comparison"):
+            assert np.array_equal(_read_png(tmp_path / "batch" / f"{name}_{suffix}.png"), _read_png(tmp_path / "single" / f"{name}_{suffix}.png")), (name, suffix)
+    predict_batch(model, str(src), str(tmp_path / "nocmp"), cuda, save_comparison=False)
+    assert os.path.exists(tmp_path / "nocmp" / "q_enhanced.png") and not os.path.exists(tmp_path / "nocmp" / "q_comparison.png")
+
+
 def test_adaptive_parameters_are_lazy(cuda):
     from retinex_image_enhancement_b200.enhancers.adaptive_params import AdaptiveParameterAdjuster
     adj = AdaptiveParameterAdjuster()
