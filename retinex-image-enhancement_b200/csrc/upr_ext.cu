@@ -306,7 +306,7 @@ static int gauss_launch(const float* x, float* out, int planes, int h, int w, co
     const int tiles_x = (w + kGtTW - 1) / kGtTW, tiles_y = (h + kGtTH - 1) / kGtTH;
     const long long nitems = (long long)planes * tiles_x * tiles_y;
     const size_t smem = size_t(2 * kGtStageFloats + kGtInH * kGtTW + kGtTH * kGtTW) * sizeof(float);
-    static unsigned long long mt = 0, mp = 0;
+    static std::atomic<unsigned long long> mt{0}, mp{0};
     UPR_CUDA_TRY(ensure_dynamic_smem(k_gauss_tile<true>, smem, mt));
     UPR_CUDA_TRY(ensure_dynamic_smem(k_gauss_tile<false>, smem, mp));
     const int grid = int(std::min<long long>(nitems, 2LL * kNumSMsB200));
