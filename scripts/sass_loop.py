@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Offline SASS accounting (no GPU needed): instruction mix of the innermost hot loop of a kernel.
 
-    python scripts/sass_loop.py k_map_vec [--lib path.so] [--px 4] [--dump]
+    python scripts/sass_loop.py k_map_vec5 [--lib path.so] [--px 4] [--dump]
 
 Finds every backward branch in the kernel's SASS, takes the loop with the most instructions (or --loop N) and prints
 its opcode histogram and instructions per pixel (--px = pixels processed per loop iteration per thread).
