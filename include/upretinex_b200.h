@@ -172,6 +172,14 @@ UPR_API int upr_content_aware_apply_f32(const float* x_nchw, const float* enh_nc
 UPR_API int upr_content_multiscale_apply_f32(const float* x_nchw, const float* enh_nchw, const float* ms_gain_per_image,
                                              float* out_nchw, float* att_n1hw, int n, int h, int w, void* workspace,
                                              size_t workspace_bytes, upr_stream_t stream);
+/* The whole chain in one call: the multi-scale statistics of x (means [n][3] and gain [n], as upr_multiscale_stats_f32 writes
+ * them; `ms_workspace` = upr_multiscale_workspace_bytes(n, h, w), zero-filled once) are computed INSIDE the chunk schedule of the
+ * content-aware passes -- the statistics kernel of a chunk runs on the chunk's stream, overlapping the memory-bound passes of the
+ * neighbouring chunk -- and applied in the shared epilogue.  Same results as upr_multiscale_stats_f32 followed by
+ * upr_content_multiscale_apply_f32. */
+UPR_API int upr_content_multiscale_f32(const float* x_nchw, const float* enh_nchw, float* out_nchw, float* att_n1hw,
+                                       float* means_n_by_3, float* gain_per_image, int n, int h, int w, void* workspace,
+                                       size_t workspace_bytes, void* ms_workspace, size_t ms_workspace_bytes, upr_stream_t stream);
 
 /* The quantiser of save_image (enhancers/simple_enhance.py:65-100), on the device: [n][c][h][w] f32 -> [n][h][w][c] u8 with
  * (clip(x, 0, 1) * 255).astype(uint8) -- fp32 product, truncation; c = 1 (illumination maps) or 3 (frames).  What the batch

@@ -26,6 +26,13 @@ namespace upr {
 
 constexpr int kNumSMsB200 = 148;
 
+// upr_multiscale.cu: launches the streaming statistics kernel for frames [f0, f0 + nf) of a batch of n_total frames on stream s
+// (x, means3, gain already point at frame f0; the workspace is the whole batch's).  Returns UPR_OK, an error, or
+// kMsNotStreamable when the shape needs the generic multi-kernel path (the caller then runs upr_multiscale_stats_f32 itself).
+constexpr int kMsNotStreamable = 1000001;
+int ms_stream_launch_range(const float* x, int nf, int h, int w, void* ms_ws, size_t ms_ws_bytes, int n_total, int f0,
+                           float* means3, float* gain, cudaStream_t s);
+
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

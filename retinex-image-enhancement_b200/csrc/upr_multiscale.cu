@@ -424,6 +424,33 @@ static int ms_parts(int n, long long px)
     return int(std::max<long long>(1, std::min<long long>(std::min(by_work, by_fill), kMsMaxParts)));
 }
 
+int ms_stream_launch_range(const float* x, int nf, int h, int w, void* ms_ws, size_t ms_ws_bytes, int n_total, int f0,
+                           float* means3, float* gain, cudaStream_t s)
+{
+    if (nf <= 0 || f0 < 0 || f0 + nf > n_total || n_total > 65535 || h <= 0 || w <= 0) return UPR_E_SHAPE;
+    if (!(h % 4 == 0 && w % 4 == 0 && h / 4 >= 2 && w / 4 >= 2 && aligned16(x))) return kMsNotStreamable;
+    if (!x || !ms_ws || !means3 || !gain) return UPR_E_NULL;
+    const MsLayout lay = ms_layout(n_total, h, w);
+    if (ms_ws_bytes < lay.total || (reinterpret_cast<uintptr_t>(ms_ws) & 255u)) return UPR_E_WORKSPACE;
+    auto* base = static_cast<unsigned char*>(ms_ws);
+    auto* partial = reinterpret_cast<double*>(base + lay.off_partial) + size_t(f0) * kMsMaxParts * 3;
+    auto* tickets = reinterpret_cast<unsigned*>(base + lay.off_tickets) + f0;
+    // one warp per (band, row segment, frame); ~6 warps per resident slot, segments >= 64 rows
+    const int bands = (w + kMsBandCols - 1) / kMsBandCols;
+    const long long slots = 24LL * kNumSMsB200;
+    long long nseg = (6 * slots + (long long)nf * bands - 1) / ((long long)nf * bands);
+    nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
+    int seg_rows = int((h + nseg - 1) / nseg);
+    seg_rows = (seg_rows + 3) / 4 * 4;
+    // (very wide frames: longer segments keep the per-frame partial count inside the workspace)
+    while ((long long)bands * ((h + seg_rows - 1) / seg_rows) > kMsMaxParts && seg_rows < h) seg_rows *= 2;
+    const int segs = (h + seg_rows - 1) / seg_rows;
+    if ((long long)bands * segs > kMsMaxParts) return kMsNotStreamable;
+    k_ms_stream<<<dim3(bands * segs, nf), 32, 0, s>>>(x, h, w, bands, seg_rows, partial, tickets, means3, gain);
+    UPR_LAUNCH_CHECK();
+    return UPR_OK;
+}
+
 static int ms_run(const float* x, int n, int h, int w, float* means, float* gain, float* f1, float* f2, float* f3,
                   void* ws, size_t ws_bytes, cudaStream_t s, bool allow_fused)
 {
@@ -442,23 +469,9 @@ static int ms_run(const float* x, int n, int h, int w, float* means, float* gain
     if (want_feat && !(f1 && f2 && f3)) return UPR_E_NULL;
     if (!want_feat && (!means || !gain)) return UPR_E_NULL;
 
-    const bool stream_ok = allow_fused && !want_feat && h % 4 == 0 && w % 4 == 0 && h / 4 >= 2 && w / 4 >= 2 && aligned16(x);
-    if (stream_ok) {
-        // one warp per (band, row segment, frame); ~6 warps per resident slot, segments >= 64 rows
-        const int bands = (w + kMsBandCols - 1) / kMsBandCols;
-        const long long slots = 24LL * kNumSMsB200;
-        long long nseg = (6 * slots + (long long)n * bands - 1) / ((long long)n * bands);
-        nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
-        int seg_rows = int((h + nseg - 1) / nseg);
-        seg_rows = (seg_rows + 3) / 4 * 4;
-        // (very wide frames: longer segments keep the per-frame partial count inside the workspace)
-        while ((long long)bands * ((h + seg_rows - 1) / seg_rows) > kMsMaxParts && seg_rows < h) seg_rows *= 2;
-        const int segs = (h + seg_rows - 1) / seg_rows;
-        if ((long long)bands * segs <= kMsMaxParts) {
-            k_ms_stream<<<dim3(bands * segs, n), 32, 0, s>>>(x, h, w, bands, seg_rows, partial, tickets, means, gain);
-            UPR_LAUNCH_CHECK();
-            return UPR_OK;
-        }
+    if (allow_fused && !want_feat) {
+        const int rc = ms_stream_launch_range(x, n, h, w, ws, ws_bytes, n, 0, means, gain, s);
+        if (rc != kMsNotStreamable) return rc;
     }
     // generic: down-sample, then one feature kernel per scale
     {

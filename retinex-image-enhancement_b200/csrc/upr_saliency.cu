@@ -875,8 +875,18 @@ static SalSidePool* sal_side_pool()     // call with g_sal_pool_mutex held
     return &p;
 }
 
+// Multi-scale statistics of the same frames, computed inside the schedule (BASELINE config 5 chain): the statistics kernel of a
+// chunk runs on the chunk's stream ahead of its blur kernel, so its issue-bound pass overlaps the memory-bound passes of the
+// neighbouring chunk instead of running alone over the whole batch first.
+struct MsJob {
+    void* ws;
+    size_t ws_bytes;
+    float* means3;      // [n][3]
+    float* gain;        // [n]
+};
+
 static int sal_run(int mode, const float* x, int n, int h, int w, float* out, void* ws, size_t ws_bytes, cudaStream_t s,
-                   const float* enh = nullptr, float* att_out = nullptr, const float* ms_gain = nullptr)
+                   const float* enh = nullptr, float* att_out = nullptr, const float* ms_gain = nullptr, const MsJob* ms = nullptr)
 {
     if (n < 0 || n > 65535 || h <= 0 || w <= 0) return UPR_E_SHAPE;
     if (n == 0) return UPR_OK;
@@ -909,6 +919,9 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
             int rc = UPR_OK;
             for (int f0 = 0, k = 0; f0 < n && rc == UPR_OK; f0 += chunk, ++k) {
                 const int nf = std::min(chunk, n - f0);
+                if (ms) rc = ms_stream_launch_range(x + f0 * step_x, nf, h, w, ms->ws, ms->ws_bytes, n, f0, ms->means3 + 3 * f0, ms->gain + f0,
+                                                    pool->s[k & 1]);
+                if (rc != UPR_OK) break;
                 rc = sal_launch(mode, x + f0 * step_x, nf, h, w, out + f0 * (mode == 2 ? step_x : step_p), mm + f0, blur + f0 * step_p,
                                 pool->s[k & 1], enh ? enh + f0 * step_x : nullptr, att_out ? att_out + f0 * step_p : nullptr,
                                 ms_gain ? ms_gain + f0 : nullptr, lum_ok);
@@ -919,6 +932,10 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
             }
             return rc;
         }
+    }
+    if (ms) {
+        const int rc = ms_stream_launch_range(x, n, h, w, ms->ws, ms->ws_bytes, n, 0, ms->means3, ms->gain, s);
+        if (rc != UPR_OK) return rc;
     }
     return sal_launch(mode, x, n, h, w, out, mm, blur, s, enh, att_out, ms_gain, lum_ok);
 }
@@ -950,6 +967,26 @@ int upr_content_aware_apply_f32(const float* x_nchw, const float* enh_nchw, floa
 {
     return upr::sal_run(2, x_nchw, n, h, w, out_nchw, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), enh_nchw,
                         att_n1hw);
+}
+
+int upr_content_multiscale_f32(const float* x_nchw, const float* enh_nchw, float* out_nchw, float* att_n1hw, float* means_n_by_3,
+                               float* gain_per_image, int n, int h, int w, void* workspace, size_t workspace_bytes,
+                               void* ms_workspace, size_t ms_workspace_bytes, upr_stream_t stream)
+{
+    if (n > 0 && (!means_n_by_3 || !gain_per_image || !ms_workspace)) return UPR_E_NULL;
+    auto s = static_cast<cudaStream_t>(stream);
+    // shapes the streaming statistics kernel does not serve: the generic statistics path over the whole batch first
+    if (n > 0 && !(h % 4 == 0 && w % 4 == 0 && h / 4 >= 2 && w / 4 >= 2 && upr::aligned16(x_nchw))) {
+        const int rc = upr_multiscale_stats_f32(x_nchw, n, h, w, means_n_by_3, gain_per_image, ms_workspace, ms_workspace_bytes, 0, stream);
+        if (rc) return rc;
+        return upr::sal_run(2, x_nchw, n, h, w, out_nchw, workspace, workspace_bytes, s, enh_nchw, att_n1hw, gain_per_image);
+    }
+    const upr::MsJob job{ms_workspace, ms_workspace_bytes, means_n_by_3, gain_per_image};
+    const int rc = upr::sal_run(2, x_nchw, n, h, w, out_nchw, workspace, workspace_bytes, s, enh_nchw, att_n1hw, gain_per_image, &job);
+    if (rc != upr::kMsNotStreamable) return rc;
+    const int rc2 = upr_multiscale_stats_f32(x_nchw, n, h, w, means_n_by_3, gain_per_image, ms_workspace, ms_workspace_bytes, 0, stream);
+    if (rc2) return rc2;
+    return upr::sal_run(2, x_nchw, n, h, w, out_nchw, workspace, workspace_bytes, s, enh_nchw, att_n1hw, gain_per_image);
 }
 
 int upr_content_multiscale_apply_f32(const float* x_nchw, const float* enh_nchw, const float* ms_gain_per_image, float* out_nchw,

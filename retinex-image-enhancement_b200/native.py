@@ -81,6 +81,8 @@ def _declare(lib):
     lib.upr_content_aware_apply_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
     lib.upr_quantize_u8_f32.restype = i32
     lib.upr_quantize_u8_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.upr_content_multiscale_f32.restype = i32
+    lib.upr_content_multiscale_f32.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp, sz, vp]
     lib.upr_content_multiscale_apply_f32.restype = i32
     lib.upr_content_multiscale_apply_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
     lib.upr_retinex_recombine_f32.restype = i32
@@ -537,7 +539,20 @@ def content_multiscale_apply(x: torch.Tensor, enh: torch.Tensor, out: Optional[t
     if c != 3 or enh.shape != x.shape:
         raise ValueError("expected x, enh [N,3,H,W]")
     if gain is None:
-        _means, gain = multiscale_stats(x)
+        # statistics inside the chunk schedule of the content-aware passes (upr_content_multiscale_f32)
+        if int(h * 0.25) < 1 or int(w * 0.25) < 1:
+            raise ValueError("image too small for the 1/4 scale")
+        out = torch.empty_like(enh) if out is None else out
+        means = torch.empty((n, 3), dtype=torch.float32, device=x.device)
+        gain = torch.empty((n,), dtype=torch.float32, device=x.device)
+        L = lib()
+        with torch.cuda.device(x.device):
+            ws = workspace(L.upr_saliency_workspace_bytes(n, h, w), x.device)
+            ms_ws = zero_workspace("ms", L.upr_multiscale_workspace_bytes(n, h, w), x.device)
+            check(L.upr_content_multiscale_f32(x.data_ptr(), enh.data_ptr(), out.data_ptr(), None, means.data_ptr(), gain.data_ptr(),
+                                               n, h, w, ws.data_ptr(), ws.numel(), ms_ws.data_ptr(), ms_ws.numel(), _stream()),
+                  "upr_content_multiscale_f32")
+        return out, gain
     gain = _require_cuda_f32(gain, "gain").reshape(-1)
     if gain.numel() != n:
         raise ValueError("gain must have one entry per image")

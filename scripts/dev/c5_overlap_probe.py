@@ -54,6 +54,7 @@ def main():
         return att_ws
 
     res["chain_sequential"] = time_ms(sequential)
+    res["chain_stats_inside_chunk_schedule"] = time_ms(lambda: native.content_multiscale_apply(x, enh, out=out))
     res["ms_then_saliency_sequential"] = time_ms(lambda: (native.multiscale_stats(x), native.saliency(x)))
     res["ms_side_stream_launched_first + saliency"] = time_ms(lambda: concurrent(True))
     res["saliency + ms_side_stream_launched_second"] = time_ms(lambda: concurrent(False))

@@ -359,7 +359,10 @@ def test_chunked_two_stream_schedule(native):
     enh = torch.rand((n, 3, h, w), device="cuda", generator=g) * 1.2
     out = native.content_aware_apply(x, enh)
     sal, att = native.saliency(x), native.attention(x)
-    chain, gain = native.content_multiscale_apply(x, enh)
+    chain, gain = native.content_multiscale_apply(x, enh)          # statistics inside the chunk schedule
+    means_b, gain_b = native.multiscale_stats(x)                   # statistics over the whole batch first
+    assert torch.equal(gain, gain_b)
+    assert torch.equal(chain, native.content_multiscale_apply(x, enh, gain=gain_b)[0])
     for i in (0, 3, 6):
         assert torch.equal(out[i:i + 1], native.content_aware_apply(x[i:i + 1], enh[i:i + 1]))
         assert torch.equal(sal[i:i + 1], native.saliency(x[i:i + 1])) and torch.equal(att[i:i + 1], native.attention(x[i:i + 1]))
@@ -370,12 +373,13 @@ def test_chunked_two_stream_schedule(native):
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         got = native.content_aware_apply(xs, es)
+        got_chain, got_gain = native.content_multiscale_apply(xs, es)
     xs.zero_(); es.zero_()
     graph.replay()
     xs.copy_(x); es.copy_(enh)
     graph.replay()
     torch.cuda.synchronize()
-    assert torch.equal(got, out)
+    assert torch.equal(got, out) and torch.equal(got_chain, chain) and torch.equal(got_gain, gain)
 
 
 def test_content_multiscale_chain(native):
