@@ -297,7 +297,8 @@ k_saliency_stream(const float* __restrict__ x, int h, int w, int bands, int seg_
 // ---------------------------------------------------------------------------------------------
 constexpr int kS2RingRowBytes = 512;                  // 32 lanes x 8 columns x fp16 (integers <= 1020: exact)
 constexpr int kS2RingBytes = 16 * kS2RingRowBytes;    // 16 live |lap| rows
-constexpr int kS2XRowFloats = 2 * 34 * 4;             // one exchanged row: [half][34 lane slots] float4 (slots -1 and 32 are padding)
+constexpr int kS2XRowFloats = 2 * 34 * 4;
+constexpr int kS2SegRows = 64;                        // rows per warp (+ 16 halo rows)             // one exchanged row: [half][34 lane slots] float4 (slots -1 and 32 are padding)
 
 // gray of 8 pixels from planar f32 rows, packed column pairs.  kFast: every value is in [+0, 1] (see k_saliency_stream).
 __device__ __forceinline__ void s2_gray8(const float (&r)[8], const float (&g)[8], const float (&b)[8], f32x2 (&out)[4])
@@ -365,6 +366,15 @@ k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg
     const int f = blockIdx.y;
     const int r0 = seg * seg_rows, r1 = min(r0 + seg_rows, h);
     if (r0 >= h) return;
+    // Odd segments walk UP from their last row: neighbouring segments then start from a common boundary row at the same time and
+    // arrive at the other boundary together, so the 8 warm-up and 8 tail rows of a segment are being read by its neighbour at that
+    // moment (L2 hits instead of a second trip to DRAM).  The kernel is symmetric in the row direction (symmetric taps, symmetric
+    // Laplacian): `lrow(k)` maps the logical row k of the walk to the image row.  The tap sums of an up-walking segment run in the
+    // opposite row order (last-ulp differences), which is why seg_rows is a constant of the launch geometry: the direction of a
+    // row depends on the frame height only, never on the batch.
+    const int dir = (seg & 1) ? -1 : 1;
+    const int base = (seg & 1) ? r1 - 1 : r0;
+    auto lrow = [&](int k) { return base + dir * k; };
     const int c0 = band * kSsBandCols - kSsLaneCols + lane * kSsLaneCols;   // plane column of this lane's first pixel
     const long long plane = (long long)h * w;
     const float* img = x + (long long)f * 3 * plane + min(max(c0, 0), w - kSsLaneCols);
@@ -388,10 +398,10 @@ k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg
         return img + (long long)k * w;
     };
     float4 nx[2][3][2];
-    auto load_rows = [&](int k) {
+    auto load_rows = [&](int k) {      // logical rows k, k + 1
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            const float* rp = row_ptr(k + rr);
+            const float* rp = row_ptr(lrow(k + rr));
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 nx[rr][c][0] = __ldg(reinterpret_cast<const float4*>(rp + c * plane));
@@ -402,7 +412,7 @@ k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg
     auto prefetch_rows = [&](int k) {
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            const float* rp = row_ptr(k + rr);
+            const float* rp = row_ptr(lrow(k + rr));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + plane));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 2 * plane));
@@ -455,17 +465,17 @@ k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg
         }
     };
 
-    // iteration t converts gray rows G0 + 2t, G0 + 2t + 1, forms |lap| rows G0 + 2t - 1, G0 + 2t and, from t = 8 on, the output
-    // rows m = r0 + 2 (t - 8) and m + 1 (|lap| rows m - 7 .. m + 8 are then in the ring)
-    const int G0 = r0 - 8;
+    // (logical rows of the walk) iteration t converts gray rows G0 + 2t, G0 + 2t + 1, forms |lap| rows G0 + 2t - 1, G0 + 2t and,
+    // from t = 8 on, the output rows m = 2 (t - 8) and m + 1 (|lap| rows m - 7 .. m + 8 are then in the ring)
+    const int G0 = -8;
     const int iters = 8 + (r1 - r0 + 1) / 2;
     load_rows(G0);
     uint32_t p = 0;   // ring row that receives the first of this iteration's two |lap| rows (even)
 #pragma unroll 1
     for (int t = 0; t < iters; ++t) {
         f32x2 ga[4], gb[4];
-        gray_row(nx[0], ga, G0 + 2 * t);
-        gray_row(nx[1], gb, G0 + 2 * t + 1);
+        gray_row(nx[0], ga, lrow(G0 + 2 * t));
+        gray_row(nx[1], gb, lrow(G0 + 2 * t + 1));
         if (t + 1 < iters) load_rows(G0 + 2 * (t + 1));
         if (t + 2 < iters) prefetch_rows(G0 + 2 * (t + 2));
         float la[8], lb[8];
@@ -525,7 +535,7 @@ k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg
                 asm volatile("st.shared.v2.b64 [%0+544], {%1,%2};" ::"r"(b1), "l"(am1[2]), "l"(am1[3]) : "memory");
             }
             __syncwarp();
-            const int m = r0 + 2 * (t - 8);
+            const int m = 2 * (t - 8);
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const float4* rowA = reinterpret_cast<const float4*>(rr == 0 ? xr0 : xr1) + 1;   // slot -1 and slot 32 are padding
@@ -551,8 +561,8 @@ k_saliency_stream2(const float* __restrict__ x, int h, int w, int bands, int seg
                         acc = fma2(T[d], pk2(__fadd_rn(bwin[8 + i - d], bwin[8 + i + d]), __fadd_rn(bwin[9 + i - d], bwin[9 + i + d])), acc);
                     upk2(acc, o[i], o[i + 1]);
                 }
-                const int row = m + rr;
-                if (writer && row < r1) {
+                const int row = lrow(m + rr);
+                if (writer && m + rr < r1 - r0) {
                     float* dst = blur_out + (long long)f * plane + (long long)row * w + c0;
                     __stcg(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
                     __stcg(reinterpret_cast<float4*>(dst + 4), make_float4(o[4], o[5], o[6], o[7]));
@@ -795,13 +805,15 @@ static int sal_launch(int mode, const float* x, int n, int h, int w, float* out,
         const long long slots = 18LL * kNumSMsB200;
         long long nseg = (6 * slots + (long long)n * bands - 1) / ((long long)n * bands);
         nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
-        const int seg_rows = int((h + nseg - 1) / nseg);
-        const int segs = (h + seg_rows - 1) / seg_rows;
-        if ((long long)bands * segs > 0x7fffffffLL) return UPR_E_SHAPE;
         // the packed two-rows-per-iteration kernel serves w % 8 == 0, h >= 16, 16-byte aligned planes; everything else (ragged
         // widths, tiny images, unaligned views) takes the general one-row kernel with its reflect-indexed scalar loads
         // (w >= 16, h >= 16: one reflection must bring every halo column / row back inside the image)
         const bool packed = w % 8 == 0 && w >= 16 && h >= 16 && aligned16(x) && aligned16(blur);
+        // packed kernel: 64-row segments whatever the batch (its odd segments walk upwards: a row's direction, hence the last ulp of
+        // its tap sums, must not depend on n)
+        const int seg_rows = packed ? kS2SegRows : int((h + nseg - 1) / nseg);
+        const int segs = (h + seg_rows - 1) / seg_rows;
+        if ((long long)bands * segs > 0x7fffffffLL) return UPR_E_SHAPE;
         // content-aware apply: the result frame is free scratch until the last pass writes it -- its first plane takes luma(x),
         // which the attention pass then reads instead of the 12 B/px frame (not when `out` aliases an input)
         lum_in_out = packed && mode == 2 && lum_ok && aligned16(out);
