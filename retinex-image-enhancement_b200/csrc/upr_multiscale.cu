@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "upr_common.cuh"
+#include <type_traits>
 
 namespace upr {
 
@@ -225,16 +226,26 @@ __device__ __forceinline__ float ms_edge1(float v, float dy, bool isL, bool isR)
     return ms_mag(dx, dy);
 }
 
-// (128 registers, 16 warps per SM, issue 76 %, XU 47 %, 64 instructions per pixel, DRAM read 1.12x the frames: profiles/r4_ms_stream_full.md.
-// Tighter launch bounds only spill: 20 / 24 / 32 warps per SM -> 0.374 / 0.498 / 0.687 ms against 0.348 ms per 16 x 4K.)
-__global__ void __launch_bounds__(32)
+// History (16 x 4K): one general step body, 60 SASS instructions per pixel (27 % of them MOVs, 38 branches per step), 128 registers,
+// issue 76 %, DRAM read 1.12x the frames: 0.348 ms (profiles/r4_ms_stream_full.md) -> branch-free interior step (42 instructions per
+// pixel) + L2 prefetch two steps ahead: 0.318 ms -> odd segments walk upwards (DRAM read 1.004x the frames): 0.307 ms = 5.2 TB/s.
+// 16 warps per SM (128 registers; the interior body alone would take 136): tighter bounds spill (20 / 24 warps: 0.374 / 0.498 ms on
+// the round-1 body).
+__global__ void __launch_bounds__(32, 16)
 k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, double* __restrict__ partial,
             unsigned* __restrict__ tickets, float* __restrict__ means, float* __restrict__ gain)
 {
     const int lane = threadIdx.x;
     const int band = blockIdx.x % bands, seg = blockIdx.x / bands;
     const int f = blockIdx.y, parts = gridDim.x;
-    const int r0 = seg * seg_rows, r1 = min(r0 + seg_rows, h);
+    // Odd segments work on the vertically FLIPPED frame (every statistic here is symmetric under a row flip: squared differences,
+    // 2x2 / centre block sums on a 4-row grid), i.e. they walk their rows upwards: neighbouring segments start from a common
+    // boundary at the same time and meet at the other one, so the 8 halo rows of a segment are in L2 when it reads them
+    // (same idea as k_saliency_stream2).  seg_rows does not depend on the batch, so neither does a row's direction.
+    const bool flip = seg & 1;
+    int r0 = seg * seg_rows, r1 = min(r0 + seg_rows, h);
+    if (r0 >= h) return;     // (never: segs = ceil(h / seg_rows))
+    if (flip) { const int a = h - r1, b = h - r0; r0 = a; r1 = b; }
     const int q0 = r0 >> 2, q1 = r1 >> 2, Q = h >> 2;
     const int c0 = band * kMsBandCols - 4 + lane * 4;
     const bool counted = lane >= 1 && lane <= 30 && c0 < w;
@@ -256,27 +267,33 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
     float4 N[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) N[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    // row r of the (possibly flipped) frame: base + r * rstep
+    const float* img0 = flip ? img + (long long)(h - 1) * w : img;
+    const long long rstep = flip ? -(long long)w : (long long)w;
     auto load_rows = [&](int q, int c) {
-        const float* p = img + c * plane + (long long)(4 * q) * w;
+        const float* p = img0 + c * plane + (long long)(4 * q) * rstep;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) N[j] = __ldg(reinterpret_cast<const float4*>(p + (long long)j * w));
+        for (int j = 0; j < 4; ++j) N[j] = __ldg(reinterpret_cast<const float4*>(p + (long long)j * rstep));
     };
-    if (r0 < h) {
-        if (max(q0 - 1, 0) < Q) load_rows(max(q0 - 1, 0), 0);
-        for (int q = max(q0 - 1, 0); q <= q1; ++q) {
-            const bool have = q < Q;                 // image rows 4q .. 4q+3 exist
-            const bool inner = q >= q0 && q < q1;    // their statistics belong to this segment
-            const bool prev_in = q > q0;             // rows 4q-1 / 2q-1 / q-1 belong to this segment
+    // One step = the four image rows 4q .. 4q+3.  kI (interior step: 2 <= q, q0 < q < min(q1, Q - 1)) turns every border condition
+    // into a compile-time constant: the segment's inner loop then has no branches, no selects and none of the register copies
+    // that merging the border paths costs (the general body ran 60 instructions per pixel, 27 % of them MOVs).
+    auto step = [&](const int q, auto interior_tag) {
+            constexpr bool kI = decltype(interior_tag)::value;
+            const bool have = kI || q < Q;                 // image rows 4q .. 4q+3 exist
+            const bool inner = kI || (q >= q0 && q < q1);  // their statistics belong to this segment
+            const bool prev_in = kI || q > q0;             // rows 4q-1 / 2q-1 / q-1 belong to this segment
             float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;   // this step's contribution to the three scale totals
-            {   // L2 prefetch of the four rows of the NEXT step, all three channels (swept on 16 x 4K: none 0.400 ms, one step ahead
-                // 0.363, two 0.367, three 0.379, four 0.420, six 0.480); the register loads above run one (step, channel) ahead
-                const int qp = q + 1;
+            {   // L2 prefetch of the four rows two steps ahead, all three channels; the register loads above run one (step, channel)
+                // ahead.  Swept on 16 x 4K with the branch-free interior step and the bidirectional walk: one step ahead 0.318 ms,
+                // two 0.307, three 0.314, four 0.376 (the slower general body of round 1 wanted one step: 0.363 against 0.367 / 0.379)
+                const int qp = q + 2;
                 if (qp <= q1 && qp < Q) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(img + c * plane + (long long)(4 * qp + j) * w));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(img0 + c * plane + (long long)(4 * qp + j) * rstep));
                 }
             }
 #pragma unroll
@@ -290,7 +307,7 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { A[j] = pk2(N[j].x, N[j].y); B[j] = pk2(N[j].z, N[j].w); }
                 if (c < 2) { if (have) load_rows(q, c + 1); }
-                else if (q + 1 <= q1 && q + 1 < Q) load_rows(q + 1, 0);
+                else if (kI || (q + 1 <= q1 && q + 1 < Q)) load_rows(q + 1, 0);
                 // 2x2 block sums (= 4 x half-resolution pixels) and the centre 2x2 (= 4 x quarter-resolution pixel)
                 float s0, s1, s2, s3;
                 upk2(add2(A[0], A[1]), s0, s1);
@@ -306,7 +323,7 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
                 float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
                 const f32x2 two = pk2(2.0f, 2.0f);
                 // ---- rows completed by this step: image row 4q-1, half row 2q-1, quarter row q-1 ----
-                if (q >= 1) {
+                if (kI || q >= 1) {
                     f32x2 dy4a, dy4b, dy2p;
                     if (have) {
                         dy4a = sub2(A[0], P2[c][0]); dy4b = sub2(B[0], P2[c][1]);
@@ -316,7 +333,7 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
                         dy2p = mul2(sub2(HB1[c], HB0[c]), two);
                     }
                     float dy1;
-                    if (q == 1) { const float d = __fsub_rn(Qc, Q1[c]); dy1 = __fadd_rn(d, d); }       // quarter row 0: one-sided
+                    if (!kI && q == 1) { const float d = __fsub_rn(Qc, Q1[c]); dy1 = __fadd_rn(d, d); }       // quarter row 0: one-sided
                     else if (have) dy1 = __fsub_rn(Qc, Q2[c]);
                     else { const float d = __fsub_rn(Q1[c], Q2[c]); dy1 = __fadd_rn(d, d); }          // last quarter row
                     const float a0 = ms_edge4(P3[c][0], P3[c][1], dy4a, dy4b, isL, isR);
@@ -330,7 +347,7 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
                 // ---- rows 4q .. 4q+2, half row 2q ----
                 if (have) {
                     f32x2 dyAa, dyAb, dyHp;
-                    if (q == 0) {
+                    if (!kI && q == 0) {
                         dyAa = mul2(sub2(A[1], A[0]), two); dyAb = mul2(sub2(B[1], B[0]), two);
                         dyHp = mul2(sub2(HBb, HBa), two);
                     } else {
@@ -365,6 +382,18 @@ k_ms_stream(const float* __restrict__ x, int h, int w, int bands, int seg_rows, 
                 t2 = __fmaf_rn(0.125f, e2, t2);
             }
             if (counted) { acc0 += double(t0); acc1 += double(t1); acc2 += double(t2); }
+    };
+    if (r0 < h) {
+        const int qs = max(q0 - 1, 0);
+        const int qi0 = max(max(q0 + 1, 2), qs), qi1 = min(q1, Q - 1);
+        if (qs < Q) load_rows(qs, 0);
+#pragma unroll 1
+        for (int q = qs; q <= q1; ++q) {
+            if (q == qi0) {
+#pragma unroll 1
+                for (; q < qi1; ++q) step(q, std::true_type{});
+            }
+            step(q, std::false_type{});
         }
     }
     acc0 = warp_sum(acc0);
@@ -439,11 +468,8 @@ int ms_stream_launch_range(const float* x, int nf, int h, int w, void* ms_ws, si
     auto* tickets = reinterpret_cast<unsigned*>(base + lay.off_tickets) + f0;
     // one warp per (band, row segment, frame); ~6 warps per resident slot, segments >= 64 rows
     const int bands = (w + kMsBandCols - 1) / kMsBandCols;
-    const long long slots = 24LL * kNumSMsB200;
-    long long nseg = (6 * slots + (long long)nf * bands - 1) / ((long long)nf * bands);
-    nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
-    int seg_rows = int((h + nseg - 1) / nseg);
-    seg_rows = (seg_rows + 3) / 4 * 4;
+    // 64-row segments whatever the batch: odd segments walk upwards, and the direction of a row must not depend on nf
+    int seg_rows = 64;
     // (very wide frames: longer segments keep the per-frame partial count inside the workspace)
     while ((long long)bands * ((h + seg_rows - 1) / seg_rows) > kMsMaxParts && seg_rows < h) seg_rows *= 2;
     const int segs = (h + seg_rows - 1) / seg_rows;
