@@ -146,6 +146,14 @@ UPR_API int upr_multiscale_features_f32(const float* x_nchw, int n, int h, int w
 /* out = clamp(enh * gain_per_image[image], 0, 1)   (enhancers/multi_scale.py:97-98); enh is [n][c][h][w]. */
 UPR_API int upr_scale_clamp_f32(const float* enh, const float* gain_per_image, float* out, int n, int c, int h, int w,
                                 upr_stream_t stream);
+/* a4 + a5 in one call (enhancers/multi_scale.py:62-100 after the CNN): statistics of x, then out = clamp(enh * gain[frame], 0, 1).
+ * Batches of two or more ~25 Mpx chunks run chunk by chunk on two library-owned side streams that fork from and join `stream`
+ * (graph-capturable): the statistics kernel of one chunk overlaps the gain pass of the previous one.  Same results as
+ * upr_multiscale_stats_f32 followed by upr_scale_clamp_f32; means [n][3] and gain [n] are written as by the former;
+ * `workspace` = upr_multiscale_workspace_bytes(n, h, w), zero-filled once.  out may alias enh. */
+UPR_API int upr_multiscale_enhance_f32(const float* x_nchw, const float* enh_nchw, float* out_nchw, float* means_n_by_3,
+                                       float* gain_per_image, int n, int h, int w, void* workspace, size_t workspace_bytes,
+                                       upr_stream_t stream);
 
 /* ---- a6/a7: content-aware saliency / attention ------------------------------------------
  * upr_saliency_f32 replaces ContentAwareEnhancer.compute_saliency_map (enhancers/content_aware.py:19-59):

@@ -1,6 +1,31 @@
 // upr_api.cu -- library-level entry points of the C ABI (include/upretinex_b200.h).
 #include "upr_common.cuh"
 
+namespace upr {
+
+static std::mutex g_side_pool_mutex;
+static SidePool g_side_pools[64];
+
+std::mutex& side_pool_mutex() { return g_side_pool_mutex; }
+
+SidePool* side_pool()     // call with side_pool_mutex() held
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SidePool& p = g_side_pools[dev];
+    if (!p.ready) {
+        bool ok = cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { (void)cudaGetLastError(); return nullptr; }
+        p.ready = true;
+    }
+    return &p;
+}
+
+}  // namespace upr
+
 extern "C" {
 
 const char* upr_version(void) { return "upretinex_b200 0.1.0 (sm_100a)"; }

@@ -1,6 +1,7 @@
 // upr_common.cuh -- shared device/host helpers for the sm_100a kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <mutex>
 #include <atomic>
 #include <cstdint>
 
@@ -25,6 +26,21 @@
 namespace upr {
 
 constexpr int kNumSMsB200 = 148;
+
+// upr_api.cu: two library-owned side streams per device for the chunked two-stream schedules (created on first use, never
+// destroyed).  Hold side_pool_mutex() from side_pool() until the join events are recorded.
+struct SidePool {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    bool ready = false;
+};
+std::mutex& side_pool_mutex();
+SidePool* side_pool();          // nullptr when the streams cannot be created (the caller then runs on its own stream)
+// frames per chunk of the chunked schedules (~25 Mpx: 3 x 4K, 12 x 1080p)
+inline int chunk_frames(long long plane) { return int(plane >= 25000000LL ? 1 : 25000000LL / plane); }
+
+// upr_pointwise.cu: out = clamp(enh * gain[frame], 0, 1) on stream s (the kernel behind upr_scale_clamp_f32)
+int scale_clamp_launch(const float* enh, const float* gain, float* out, int n, int c, int h, int w, cudaStream_t s);
 
 // upr_multiscale.cu: launches the streaming statistics kernel for frames [f0, f0 + nf) of a batch of n_total frames on stream s
 // (x, means3, gain already point at frame f0; the workspace is the whole batch's).  Returns UPR_OK, an error, or

@@ -182,6 +182,11 @@ static int gain_launch(const float* enh, const float* gain, float* out, int n, i
     return UPR_OK;
 }
 
+int scale_clamp_launch(const float* enh, const float* gain, float* out, int n, int c, int h, int w, cudaStream_t s)
+{
+    return gain_launch<false>(enh, gain, out, n, c, h, w, s);
+}
+
 // ---- save_image quantiser (enhancers/simple_enhance.py:65-100) -----------------------------------
 // [n][c][h][w] f32 -> [n][h][w][c] u8 with (clip(x, 0, 1) * 255).astype(uint8): fp32 product, truncation.  NaN clips to NaN and
 // casts to 0 on the host; fmaxf(NaN, 0) = 0 gives the same byte here.  c = 1 (illumination maps) or 3 (frames).  One thread

@@ -862,31 +862,6 @@ static int sal_launch(int mode, const float* x, int n, int h, int w, float* out,
 }
 
 
-// Two library-owned side streams per device for the chunked schedule below (created on first use, never destroyed).
-struct SalSidePool {
-    cudaStream_t s[2] = {nullptr, nullptr};
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
-    bool ready = false;
-};
-static std::mutex g_sal_pool_mutex;
-static SalSidePool g_sal_pools[64];
-
-static SalSidePool* sal_side_pool()     // call with g_sal_pool_mutex held
-{
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SalSidePool& p = g_sal_pools[dev];
-    if (!p.ready) {
-        bool ok = cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int i = 0; i < 2 && ok; ++i)
-            ok = cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) { (void)cudaGetLastError(); return nullptr; }
-        p.ready = true;
-    }
-    return &p;
-}
-
 // Multi-scale statistics of the same frames, computed inside the schedule (BASELINE config 5 chain): the statistics kernel of a
 // chunk runs on the chunk's stream ahead of its blur kernel, so its issue-bound pass overlaps the memory-bound passes of the
 // neighbouring chunk instead of running alone over the whole batch first.
@@ -921,11 +896,11 @@ static int sal_run(int mode, const float* x, int n, int h, int w, float* out, vo
     // the passes of neighbouring chunks overlap.  Measured on 16 x 4K / 64 x 1080p: 1.39 -> 1.28-1.30 ms (profiles/r4_content_aware.md;
     // single-frame chunks lose more to short kernels than they gain).  Results do not depend on the schedule: every frame is
     // normalised on its own.
-    const int chunk = int(std::max<long long>(1, 25000000LL / plane));
+    const int chunk = chunk_frames(plane);
     const long long step_x = 3 * plane, step_p = plane;
     if (n >= 2 * chunk && (mode != 2 || lum_ok)) {
-        std::lock_guard<std::mutex> guard(g_sal_pool_mutex);
-        if (SalSidePool* pool = sal_side_pool()) {
+        std::lock_guard<std::mutex> guard(side_pool_mutex());
+        if (SidePool* pool = side_pool()) {
             UPR_CUDA_TRY(cudaEventRecord(pool->fork, s));
             for (int i = 0; i < 2; ++i) UPR_CUDA_TRY(cudaStreamWaitEvent(pool->s[i], pool->fork, 0));
             int rc = UPR_OK;

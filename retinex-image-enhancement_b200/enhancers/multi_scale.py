@@ -36,10 +36,11 @@ class MultiScaleEnhancer:
 
     def apply_multi_scale_enhancement(self, model, image_tensor, device):
         image_tensor = _to_device(_as_batch(image_tensor), device)
-        _means, gain = native.multiscale_stats(image_tensor)
         with torch.no_grad():
             enhanced_img, _reflectance, illu_map = model(image_tensor)
-        return native.scale_clamp(enhanced_img, gain), illu_map
+        # statistics of the input + gain/clamp of the CNN output in one call (chunked on two streams for large batches)
+        out, _means, _gain = native.multiscale_enhance(image_tensor, enhanced_img.contiguous())
+        return out, illu_map
 
     def enhance_with_pyramid(self, model, image_tensor, device):
         return self.apply_multi_scale_enhancement(model, image_tensor, device)

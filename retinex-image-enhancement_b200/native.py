@@ -81,6 +81,8 @@ def _declare(lib):
     lib.upr_content_aware_apply_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
     lib.upr_quantize_u8_f32.restype = i32
     lib.upr_quantize_u8_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.upr_multiscale_enhance_f32.restype = i32
+    lib.upr_multiscale_enhance_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
     lib.upr_content_multiscale_f32.restype = i32
     lib.upr_content_multiscale_f32.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp, sz, vp]
     lib.upr_content_multiscale_apply_f32.restype = i32
@@ -381,6 +383,30 @@ def multiscale_stats(x: torch.Tensor, force_generic: bool = False):
         check(L.upr_multiscale_stats_f32(x.data_ptr(), n, h, w, means.data_ptr(), gain.data_ptr(), ws.data_ptr(),
                                          ws.numel(), 1 if force_generic else 0, _stream()), "upr_multiscale_stats_f32")
     return means, gain
+
+
+def multiscale_enhance(x: torch.Tensor, enh: torch.Tensor, out: torch.Tensor | None = None):
+    """a4 + a5 in one call: out = clamp(enh * gain(x)[frame], 0, 1) -> (out, means [N,3], gain [N]); large batches run chunk by
+    chunk on two library-owned side streams (upr_multiscale_enhance_f32).  out may be enh."""
+    x = _require_cuda_f32(x, "x")
+    enh = _require_cuda_f32(enh, "enh")
+    n, c, h, w = x.shape
+    if c != 3 or tuple(enh.shape) != (n, 3, h, w):
+        raise ValueError("expected x and enh of shape [N,3,H,W]")
+    if int(h * 0.25) < 1 or int(w * 0.25) < 1:
+        raise ValueError("image too small for the 1/4 scale")
+    if out is None:
+        out = torch.empty_like(enh)
+    elif tuple(out.shape) != tuple(enh.shape) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != enh.device:
+        raise ValueError("out must be a contiguous f32 tensor shaped like enh on the same device")
+    means = torch.empty((n, 3), dtype=torch.float32, device=x.device)
+    gain = torch.empty((n,), dtype=torch.float32, device=x.device)
+    L = lib()
+    with torch.cuda.device(x.device):
+        ws = zero_workspace("ms", L.upr_multiscale_workspace_bytes(n, h, w), x.device)
+        check(L.upr_multiscale_enhance_f32(x.data_ptr(), enh.data_ptr(), out.data_ptr(), means.data_ptr(), gain.data_ptr(), n, h, w,
+                                           ws.data_ptr(), ws.numel(), _stream()), "upr_multiscale_enhance_f32")
+    return out, means, gain
 
 
 def multiscale_features(x: torch.Tensor):

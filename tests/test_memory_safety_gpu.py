@@ -96,6 +96,7 @@ def test_guard_bands_and_poisoned_margins(native, monkeypatch, n, h, w):
     if h >= 4 and w >= 4:
         m, gain = native.multiscale_stats(xd)
         mg, _ = native.multiscale_stats(xd, force_generic=True)
+        native.multiscale_enhance(xd, ed, out=out((n, 3, h, w)))
     native.scale_clamp(ed, torch.ones(n, device="cuda"), out=out((n, 3, h, w)))
     native.quantize_u8(ed, out=out((n, h, w, 3), torch.uint8))
     native.quantize_u8(il, out=out((n, h, w, 1), torch.uint8))

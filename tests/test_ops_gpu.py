@@ -382,6 +382,37 @@ def test_chunked_two_stream_schedule(native):
     assert torch.equal(got, out) and torch.equal(got_chain, chain) and torch.equal(got_gain, gain)
 
 
+def test_multiscale_enhance_one_call(native):
+    """upr_multiscale_enhance_f32 (a4 + a5 in one call, chunked on two side streams from two ~25 Mpx chunks on): same bits as the
+    statistics call followed by the gain call -- small, ragged (generic statistics path), chunked, in place, and graph-captured."""
+    g = torch.Generator(device="cuda").manual_seed(91)
+    for n, h, w in ((2, 400, 600), (3, 33, 51), (7, 2160, 3840), (30, 1080, 1920)):
+        x = torch.rand((n, 3, h, w), device="cuda", generator=g) * 0.8
+        enh = torch.rand((n, 3, h, w), device="cuda", generator=g) * 1.2
+        means, gain = native.multiscale_stats(x, force_generic=(h % 4 != 0))
+        ref = native.scale_clamp(enh, gain)
+        out, means2, gain2 = native.multiscale_enhance(x, enh)
+        assert torch.equal(out, ref) and torch.equal(means, means2) and torch.equal(gain, gain2)
+        if n == 7:
+            for i in (0, 6):      # frame by frame: the schedule does not change a frame's result
+                assert torch.equal(out[i:i + 1], native.multiscale_enhance(x[i:i + 1], enh[i:i + 1])[0])
+            xs, es = x.clone(), enh.clone()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                got, _m, got_gain = native.multiscale_enhance(xs, es)
+            xs.zero_(); es.zero_()
+            graph.replay()
+            xs.copy_(x); es.copy_(enh)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(got, ref) and torch.equal(got_gain, gain)
+            inplace = enh.clone()
+            native.multiscale_enhance(x, inplace, out=inplace)
+            assert torch.equal(inplace, ref)
+        del x, enh, out, ref
+
+
 def test_content_multiscale_chain(native):
     """BASELINE config 5: content-aware then multi-scale on the same CNN output, one shared epilogue -- bit-identical to the two
     enhancers' own epilogues back to back, and equal to the oracle's composition within the attention tolerance."""
