@@ -431,14 +431,23 @@ def record_c4(torch, dist, rank, world, local, steps, warmup, frames=8, size=256
     dev = torch.device("cuda", local)
     x = torch.rand((b, c, h, w), device=dev, generator=torch.Generator(device=dev).manual_seed(11 + rank))
 
+    # the product's default path (losses/loss.py DynamicSmoothWeight): one process = ONE kernel (statistics + batch mean + weight);
+    # data-parallel = statistics kernel + NCCL all-reduce of [sum, count] + weight kernel
+    default_dsw = L.DynamicSmoothWeight(1.0, True, "tv")
+
     def step():
+        return default_dsw(x)
+
+    def three_ops():
         _per, stats = L.batch_texture_stats(x, "tv")
         L.all_reduce_batch_stats(stats)
         return L.weight_from_stats(stats, 1.0)
 
     with ClockSampler(local) as clk:
         ms_step = timed_steps(torch, dist, step, steps, warmup) / steps
-    w_nccl = step().clone()
+    w_nccl = three_ops().clone()
+    assert torch.equal(step(), w_nccl), "the one-kernel path and the three-operation path disagree"
+    three_us = statistics.median(event_time_ms(torch, three_ops, 20)) * 1e3 if world == 1 else None
     # the same three operations captured in one CUDA graph (collective included when world > 1)
     graph_us = None
     try:
@@ -474,10 +483,13 @@ def record_c4(torch, dist, rank, world, local, steps, warmup, frames=8, size=256
            "value": ms_step * 1e3, "unit": "us/step", "higher_is_better": False, "mpix_s": world * px / 1e6 / (ms_step / 1e3),
            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
            "us_per_step": ms_step * 1e3, "us_per_step_cuda_graph": graph_us, "us_per_step_fused_peer_kernel": fused_us,
+           "us_per_step_three_separate_ops": three_us,
            "fused_peer_vs_nccl": fused_equal, "scaling": "weak", "dtype": "f32 (fp64 accumulators)", "data": "synthetic",
-           "config": {"workload": f"c4: upr_texture_tv_f32 on {b}x{c}x{h}x{w} per rank + all-reduce(SUM) of [sum, count] over {world} rank(s) + weight kernel",
+           "config": {"workload": (f"c4: DynamicSmoothWeight on {b}x{c}x{h}x{w}: ONE kernel (upr_texture_weight_peer_f32: TV statistics + batch mean + weight)"
+                                   if world == 1 else
+                                   f"c4: upr_texture_tv_f32 on {b}x{c}x{h}x{w} per rank + all-reduce(SUM) of [sum, count] over {world} rank(s) + weight kernel"),
                       "l2": "latency-bound config (6.3 MB input is L2 resident by construction); reported in us/step"},
-           "clocks": clk.summary(), "gpu_launches": 2 * steps,
+           "clocks": clk.summary(), "gpu_launches": (1 if world == 1 else 2) * steps,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "kernel": "k_texture_tv", "kernel_ms": k_tv, "peak_source": peak_src,
                         "kernels_ms": {"k_texture_tv": k_tv, "k_texture_edge(1+2)": k_ed},

@@ -104,15 +104,17 @@ class DynamicSmoothWeight:
     def __call__(self, img_low: torch.Tensor) -> torch.Tensor:
         if not self.use_dynamic_smooth_weight:
             return torch.tensor(self.weight_smooth, dtype=torch.float32, device=img_low.device)
-        if self.fused_collective and img_low.is_cuda:
+        if img_low.is_cuda:
             import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+            if parallel and self.fused_collective:
                 if self._peer is None:
                     self._peer = PeerBatchStats(img_low.device, self.group)
                 p = self._peer
                 return native.texture_weight_peer(img_low, self.texture_method, self.weight_smooth, p.table, p.rank, p.world,
                                                   p.next_seq())[2]
-            return native.texture_weight_peer(img_low, self.texture_method, self.weight_smooth, None, 0, 1, 1)[2]
+            if not parallel:      # one process: nothing to exchange -- statistics + batch mean + weight in ONE kernel
+                return native.texture_weight_peer(img_low, self.texture_method, self.weight_smooth, None, 0, 1, 1)[2]
         _per_image, stats = batch_texture_stats(img_low, self.texture_method)
         all_reduce_batch_stats(stats, self.group)
         return weight_from_stats(stats, self.weight_smooth)
