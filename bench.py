@@ -575,8 +575,8 @@ def record_c5(torch, dist, rank, world, local, steps, warmup, frames=128, chunk=
                                   "multi-scale statistics -> saliency blur -> raw attention -> ONE epilogue clamp(clamp(enh*(1+0.2 att))*gain), "
                                   "one call per chunk (upr_content_multiscale_f32)", "frames_per_gpu": n, "chunk": chunk, "h": h, "w": w,
                       "l2": "inputs larger than L2"},
-           # per call: the library schedules sub-chunks of ~25 Mpx, each = statistics + blur + raw attention + epilogue kernels
-           "clocks": clk.summary(), "gpu_launches": 4 * sum(-(-(b - a) // max(1, 25000000 // (h * w))) for a, b in chunks) * steps,
+           # per call: the library schedules sub-chunks of ~25 Mpx, each = statistics + min/max reset + blur + raw attention + epilogue kernels
+           "clocks": clk.summary(), "gpu_launches": 5 * sum(-(-(b - a) // max(1, 25000000 // (h * w))) for a, b in chunks) * steps,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "kernel": "upr_content_aware_apply_f32 chain (k_saliency_stream + k_sal_normalize + k_att_gain) on one chunk",
                         "kernel_ms": k_ca, "peak_source": peak_src, "algorithmic_bytes_per_px": 36,
