@@ -466,7 +466,7 @@ int ms_stream_launch_range(const float* x, int nf, int h, int w, void* ms_ws, si
     auto* base = static_cast<unsigned char*>(ms_ws);
     auto* partial = reinterpret_cast<double*>(base + lay.off_partial) + size_t(f0) * kMsMaxParts * 3;
     auto* tickets = reinterpret_cast<unsigned*>(base + lay.off_tickets) + f0;
-    // one warp per (band, row segment, frame); ~6 warps per resident slot, segments >= 64 rows
+    // one warp per (band, row segment, frame)
     const int bands = (w + kMsBandCols - 1) / kMsBandCols;
     // 64-row segments whatever the batch: odd segments walk upwards, and the direction of a row must not depend on nf
     int seg_rows = 64;

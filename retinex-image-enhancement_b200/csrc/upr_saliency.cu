@@ -798,10 +798,9 @@ static int sal_launch(int mode, const float* x, int n, int h, int w, float* out,
     {
         static const GaussTapsF taps = sal_taps_f();
         const int bands = (w + kSsBandCols - 1) / kSsBandCols;
-        // one warp per (band, row segment, frame): aim at ~6 warps per resident slot (20 warps/SM) for balance, but keep
-        // segments >= 64 rows (16 of every segment's rows are re-computed halo)
-        // (segments of 96 / 128 / 192 rows re-read fewer halo rows but leave too few warps: content-aware op 1.31 -> 1.34 / 1.38 /
-        // 1.43 ms per 16 x 4K)
+        // one warp per (band, row segment, frame).  General kernel: aim at ~6 warps per resident slot (20 warps/SM) for balance, but
+        // keep segments >= 64 rows (16 of every segment's rows are re-computed halo; segments of 96 / 128 / 192 rows leave too few
+        // warps: content-aware op 1.31 -> 1.34 / 1.38 / 1.43 ms per 16 x 4K)
         const long long slots = 18LL * kNumSMsB200;
         long long nseg = (6 * slots + (long long)n * bands - 1) / ((long long)n * bands);
         nseg = std::max<long long>(1, std::min<long long>(nseg, (h + 63) / 64));
