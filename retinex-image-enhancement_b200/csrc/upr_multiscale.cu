@@ -469,6 +469,7 @@ int ms_stream_launch_range(const float* x, int nf, int h, int w, void* ms_ws, si
     // one warp per (band, row segment, frame)
     const int bands = (w + kMsBandCols - 1) / kMsBandCols;
     // 64-row segments whatever the batch: odd segments walk upwards, and the direction of a row must not depend on nf
+    // (96 / 128 / 192 / 256 rows: 0.300 / 0.302 / 0.331 / 0.324 ms against 0.308 ms per 16 x 4K -- fewer general border steps, fewer warps)
     int seg_rows = 64;
     // (very wide frames: longer segments keep the per-frame partial count inside the workspace)
     while ((long long)bands * ((h + seg_rows - 1) / seg_rows) > kMsMaxParts && seg_rows < h) seg_rows *= 2;
