@@ -97,6 +97,10 @@ k_recombine_scalar(const float* __restrict__ x, const float* __restrict__ illu, 
 
 // ---- a5 / a7 ----------------------------------------------------------------------------
 // kPerPixel == false: gain[f] per frame (a5);  true: gain = 1 + 0.2*att[f][p] per pixel (a7)
+// One 128-bit load and one store per trip, all CTAs sweeping the batch linearly inside a ~5 MB window: 6.2-6.3 TB/s on 16 - 192 4K
+// frames (a device-to-device copy: 6.5-6.6).  Measured and NOT kept (scripts/dev/clamp_probe.py): 2 / 4 loads in flight per thread
+// (window x2 / x4) 5.87 / 5.76 TB/s; a (parts, frame) grid without the index divisions but with every frame open at once 5.70 TB/s
+// -- this stream is limited by DRAM page locality, not by bytes in flight or by its 64-bit index arithmetic.
 template <bool kPerPixel>
 __global__ void __launch_bounds__(kPwThreads)
 k_gain_clamp_vec(const float* __restrict__ enh, const float* __restrict__ gain, float* __restrict__ out, int c,
