@@ -259,10 +259,13 @@ def _frames(n, h, w, base):
     return np.concatenate([O.kat_input(base + i, h, w, ("uniform", "dark", "ramp")[i % 3]) for i in range(n)])
 
 
-@pytest.mark.parametrize("n,h,w", [(1, 2160, 3840), (2, 1080, 1920), (3, 400, 600), (1, 64, 120), (1, 8, 8), (2, 68, 244), (1, 128, 4096)])
+@pytest.mark.parametrize("n,h,w", [(1, 2160, 3840), (2, 1080, 1920), (3, 400, 600), (1, 64, 120), (1, 8, 8), (2, 68, 244), (1, 128, 4096),
+                                   (1, 4320, 7680), (1, 132, 240), (2, 60, 480)])
 def test_multiscale_full_shapes_vs_oracle(native, n, h, w):
     """upr_multiscale_stats_f32 against the oracle at the BASELINE shapes and at band edges (w not a multiple of 120), segment
-    edges, one-sided differences on all four borders, batches.  Stated bound 1e-4 relative; achieved 2e-6."""
+    edges (64-row segments, odd ones walking upwards; a last segment of 4 rows; an 8K frame, whose 64 x 68 parts exceed the
+    per-frame partial slots so that the segments double to 128 rows), one-sided differences on all four borders, batches.
+    Stated bound 1e-4 relative; achieved 2e-6."""
     x = _frames(n, h, w, 500)
     m, g = native.multiscale_stats(dev(x))
     m, g = m.cpu().numpy(), g.cpu().numpy()
