@@ -276,7 +276,8 @@ def test_multiscale_full_shapes_vs_oracle(native, n, h, w):
 
 
 @pytest.mark.parametrize("n,h,w", [(1, 2160, 3840), (2, 1080, 1920), (2, 70, 250), (1, 33, 481), (1, 3, 9), (1, 600, 17), (1, 20, 243),
-                                   (1, 17, 8), (1, 16, 16), (2, 17, 24), (1, 40, 240), (1, 31, 248), (3, 16, 480), (1, 15, 32)])
+                                   (1, 17, 8), (1, 16, 16), (2, 17, 24), (1, 40, 240), (1, 31, 248), (3, 16, 480), (1, 15, 32),
+                                   (1, 70, 256), (1, 132, 256), (2, 65, 64), (1, 129, 496), (1, 4320, 7680)])
 def test_saliency_attention_full_shapes_vs_oracle(native, n, h, w):
     """upr_saliency_f32 / upr_attention_f32 / upr_content_aware_apply_f32 against the oracle, FULL maps, at the BASELINE shapes
     and at band edges (w not a multiple of the band width, lanes that straddle the right border), reflect-101 on narrow / short
