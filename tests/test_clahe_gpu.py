@@ -63,7 +63,7 @@ def test_golden_kats(native, golden):
     ((1080, 1920), "ramp"), ((1080, 1920), "const"), ((2160, 3840), "dark"), ((403, 601), "uniform"),
     ((400, 601), "dark"), ((401, 600), "uniform"), ((256, 256), "uniform"), ((640, 640), "dark"),
     ((64, 128), "uniform"), ((17, 23), "uniform"), ((9, 9), "dark"), ((8, 8), "uniform"), ((1024, 1000), "uniform"),
-    ((1024, 1024), "ramp"), ((64, 4096), "uniform"),
+    ((1024, 1024), "ramp"), ((64, 4096), "uniform"), ((4320, 7680), "dark"), ((4320, 7680), "uniform"),
 ])
 def test_against_oracle(native, shape, kind):
     compare(native, O.kat_input(shape[0] * 7 + shape[1] + len(kind), shape[0], shape[1], kind))
