@@ -1,0 +1,95 @@
+"""Seeded random-shape sweeps of the hot-path ops against the oracle (GPU).  The parametrised tests pin the named shapes and the
+edges that were thought of; these sweep (shape, batch, tile grid, clip limit, content kind) combinations nobody picked by hand --
+ragged widths, frames smaller than a tile grid, single rows / columns where the reference allows them."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def native():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from retinex_image_enhancement_b200 import native as nat
+    assert nat.lib().upr_device_check() == 0
+    return nat
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+KINDS = ("uniform", "dark", "ramp", "const")
+
+
+def _frames(rng, n, h, w):
+    return np.concatenate([O.kat_input(int(rng.integers(1 << 30)), h, w, KINDS[int(rng.integers(len(KINDS)))]) for _ in range(n)])
+
+
+def test_clahe_random_shapes_grids_and_clips(native):
+    """CLAHE-in-Lab bit-exact against the oracle on 40 random (n, h, w, tiles, clip) combinations: the vector kernels (tile width a
+    multiple of 4, no padding) and the generic ones (OpenCV's reflect-101 padding when the grid does not divide the frame)."""
+    rng = np.random.default_rng(20260)
+    for case in range(40):
+        tx, ty = int(rng.integers(1, 13)), int(rng.integers(1, 13))
+        if case % 2 == 0:      # divisible, 4-px aligned tiles: the fast path
+            h, w = ty * int(rng.integers(2, 40)), tx * 4 * int(rng.integers(1, 30))
+        else:
+            h, w = int(rng.integers(max(2, ty), 300)), int(rng.integers(max(2, tx), 400))
+        n = int(rng.integers(1, 4))
+        clip = float(rng.choice([0.0, 0.5, 1.0, 2.0, 3.7, 40.0]))
+        x = _frames(rng, n, h, w)
+        got = native.clahe_lab(dev(x), clip_limit=clip, tiles=(tx, ty)).cpu().numpy()
+        for i in range(n):
+            ref = O.clahe_lab(x[i], clip, (tx, ty))
+            assert np.array_equal(got[i], ref[0]), (case, n, h, w, tx, ty, clip, float(np.abs(got[i] - ref[0]).max()))
+
+
+def test_multiscale_and_texture_random_shapes(native):
+    """Multi-scale means / gain and both texture statistics on 40 random shapes (streaming kernel when h, w are multiples of 4,
+    generic kernels otherwise), 2e-6 relative against the oracle."""
+    rng = np.random.default_rng(20261)
+    for case in range(40):
+        if case % 2 == 0:
+            h, w = 4 * int(rng.integers(2, 120)), 4 * int(rng.integers(2, 160))
+        else:
+            h, w = int(rng.integers(4, 300)), int(rng.integers(4, 500))
+        n = int(rng.integers(1, 4))
+        x = _frames(rng, n, h, w)
+        xd = dev(x)
+        m, g = native.multiscale_stats(xd)
+        tv = native.texture_complexity(xd, "tv").cpu().numpy()
+        ed = native.texture_complexity(xd, "edge_density").cpu().numpy()
+        m, g = m.cpu().numpy(), g.cpu().numpy()
+        for i in range(n):
+            m_ref, f_ref = O.multiscale_means(x[i:i + 1])
+            np.testing.assert_allclose(m[i], m_ref, rtol=2e-6, atol=1e-7, err_msg=str((case, n, h, w)))
+            assert abs(float(g[i]) - f_ref) <= 2e-7 * f_ref + 6e-8, (case, n, h, w)
+            np.testing.assert_allclose(tv[i:i + 1], O.texture_tv(x[i:i + 1]), rtol=2e-6, atol=1e-7, err_msg=str((case, n, h, w)))
+            assert abs(float(ed[i]) - float(O.texture_edge_density(x[i:i + 1])[0])) <= 4.0 / (h * w) + 1e-7, (case, n, h, w)
+
+
+def test_content_aware_random_shapes(native):
+    """Saliency / attention maps and the fused apply on 30 random shapes (packed kernel for w % 8 == 0, h, w >= 16; the general
+    kernel otherwise), full maps against the oracle."""
+    rng = np.random.default_rng(20262)
+    for case in range(30):
+        if case % 2 == 0:
+            h, w = int(rng.integers(16, 260)), 8 * int(rng.integers(2, 70))
+        else:
+            h, w = int(rng.integers(3, 200)), int(rng.integers(3, 300))
+        n = int(rng.integers(1, 4))
+        x = _frames(rng, n, h, w)
+        enh = rng.random((n, 3, h, w), dtype=np.float32) * np.float32(1.2)
+        xd = dev(x)
+        sal, att = native.saliency(xd).cpu().numpy(), native.attention(xd).cpu().numpy()
+        out = native.content_aware_apply(xd, dev(enh)).cpu().numpy()
+        for i in range(n):
+            s_ref, a_ref = O.saliency(x[i:i + 1]), O.attention(x[i:i + 1])
+            np.testing.assert_allclose(sal[i:i + 1], s_ref, rtol=0, atol=1e-6, err_msg=str((case, n, h, w)))
+            np.testing.assert_allclose(att[i:i + 1], a_ref, rtol=0, atol=2e-6, err_msg=str((case, n, h, w)))
+            np.testing.assert_allclose(out[i:i + 1], O.attention_apply(enh[i], a_ref), rtol=0, atol=2e-6, err_msg=str((case, n, h, w)))
