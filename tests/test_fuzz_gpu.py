@@ -93,3 +93,49 @@ def test_content_aware_random_shapes(native):
             np.testing.assert_allclose(sal[i:i + 1], s_ref, rtol=0, atol=1e-6, err_msg=str((case, n, h, w)))
             np.testing.assert_allclose(att[i:i + 1], a_ref, rtol=0, atol=2e-6, err_msg=str((case, n, h, w)))
             np.testing.assert_allclose(out[i:i + 1], O.attention_apply(enh[i], a_ref), rtol=0, atol=2e-6, err_msg=str((case, n, h, w)))
+
+
+def test_fused_retinex_clahe_and_u8_boundaries_random_shapes(native):
+    """upr_retinex_clahe_f32 (+ its u8-output form) and the packed u8 CLAHE entry on 30 random shapes / grids: bit-exact against the
+    oracle's recombination followed by its CLAHE-in-Lab, resp. against the oracle on the same bytes."""
+    rng = np.random.default_rng(20263)
+    for case in range(30):
+        tx, ty = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        if case % 3 != 2:
+            h, w = ty * int(rng.integers(2, 40)), tx * 4 * int(rng.integers(1, 30))
+        else:
+            h, w = int(rng.integers(max(2, ty), 200)), int(rng.integers(max(2, tx), 300))
+        n = int(rng.integers(1, 3))
+        clip = float(rng.choice([0.0, 1.0, 2.0, 5.0]))
+        x = _frames(rng, n, h, w)
+        illu = (rng.random((n, 1, h, w), dtype=np.float32) * np.float32(0.9) + np.float32(0.05)).astype(np.float32)
+        e = rng.random((n, 3, h, w), dtype=np.float32)
+        got = native.retinex_clahe(dev(x), dev(illu), dev(e), clip_limit=clip, tiles=(tx, ty)).cpu().numpy()
+        got8 = native.retinex_clahe_u8(dev(x), dev(illu), dev(e), clip_limit=clip, tiles=(tx, ty)).cpu().numpy()
+        x8 = (rng.integers(0, 256, (n, h, w, 3))).astype(np.uint8)
+        out8 = native.clahe_lab_u8(dev(x8), clip_limit=clip, tiles=(tx, ty)).cpu().numpy()
+        for i in range(n):
+            _refl, enh = O.retinex_recombine(x[i:i + 1], illu[i:i + 1], e[i:i + 1])
+            ref = O.clahe_lab(enh[0], clip, (tx, ty))[0]
+            assert np.array_equal(got[i], ref), (case, n, h, w, tx, ty, clip)
+            ref8 = np.rint(ref * 255.0).astype(np.uint8).transpose(1, 2, 0)      # ref is k / 255 exactly: the stored byte is k
+            assert np.array_equal(got8[i], ref8), (case, n, h, w, tx, ty, clip)
+            want8 = O.clahe_lab((x8[i].astype(np.float32) / np.float32(255.0)).transpose(2, 0, 1), clip, (tx, ty))[0]
+            assert np.array_equal(out8[i], np.rint(want8 * 255.0).astype(np.uint8).transpose(1, 2, 0)), (case, n, h, w, tx, ty, clip)
+
+
+def test_letterbox_random_geometry(native):
+    """The --max_size letterbox (down-scaling) on 30 random (frame, target) pairs: bit-exact against the reference recipe run by
+    OpenCV on the host (oracle/cv2_chain.letterbox_ref)."""
+    pytest.importorskip("cv2")
+    from oracle import cv2_chain
+    from retinex_image_enhancement_b200.utils.letterbox import letterbox_tensor
+    rng = np.random.default_rng(20264)
+    for case in range(30):
+        h, w = int(rng.integers(40, 900)), int(rng.integers(40, 1200))
+        new_shape = int(rng.integers(32, max(33, min(h, w))))
+        x = rng.random((3, h, w), dtype=np.float32)
+        ref, ratio, pad = cv2_chain.letterbox_ref(x, new_shape, auto=True, scaleup=False)
+        got, ratio2, pad2 = letterbox_tensor(torch.from_numpy(x).cuda(), new_shape=new_shape, auto=True, scaleup=False)
+        assert tuple(got.shape) == ref.shape and np.array_equal(got.cpu().numpy(), ref), (case, h, w, new_shape)
+        assert ratio == ratio2 and tuple(pad) == tuple(pad2)
