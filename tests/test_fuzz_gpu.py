@@ -139,3 +139,28 @@ def test_letterbox_random_geometry(native):
         got, ratio2, pad2 = letterbox_tensor(torch.from_numpy(x).cuda(), new_shape=new_shape, auto=True, scaleup=False)
         assert tuple(got.shape) == ref.shape and np.array_equal(got.cpu().numpy(), ref), (case, h, w, new_shape)
         assert ratio == ratio2 and tuple(pad) == tuple(pad2)
+
+
+def test_loss_kernels_random_shapes(native):
+    """the smoothness loss + gradient and the three enhanced-image losses + gradients on 24 random shapes against
+    the NumPy restatements of the reference's loss modules (themselves pinned to the reference's autograd, tests/test_oracle_pin)."""
+    rng = np.random.default_rng(20265)
+    for case in range(24):
+        b = int(rng.integers(1, 5))
+        h, w = int(rng.integers(16, 200)), int(rng.integers(16, 260))
+        ci = int(rng.choice([1, 3]))
+        illu = rng.random((b, ci, h, w), dtype=np.float32)
+        low = rng.random((b, 3, h, w), dtype=np.float32) * np.float32(0.5)
+        enh = rng.random((b, 3, h, w), dtype=np.float32)
+        lam, alpha = float(rng.choice([1.0, 10.0])), float(rng.choice([0.5, 1.0]))
+        loss, _lh, _lv, grad = O.edge_smooth_loss(illu, low, lam, alpha)
+        loss3, g = native.edge_smooth_loss(dev(illu), dev(low), lam, alpha)
+        assert abs(float(loss3[0]) - float(loss)) <= 2e-6 * abs(float(loss)) + 1e-12, (case, b, ci, h, w)
+        assert np.abs(g.cpu().numpy() - grad).max() <= 2e-6 * np.abs(grad).max() + 1e-12, (case, b, ci, h, w)
+        (l_exp, l_col, l_spa), grads = O.enhanced_image_losses(enh, low)
+        losses, saved = native.enhanced_image_losses(dev(enh), dev(low))
+        for k, want in enumerate((l_exp, l_col, l_spa)):
+            assert abs(float(losses[k]) - float(want)) <= 3e-6 * abs(float(want)) + 1e-12, (case, k, b, h, w)
+            up = torch.zeros(3, device="cuda"); up[k] = 1.0
+            got = native.enhanced_image_losses_grad(dev(enh), dev(low), saved, up).cpu().numpy()
+            assert np.abs(got - grads[k]).max() <= 3e-6 * np.abs(grads[k]).max() + 1e-12, (case, k, b, h, w)
