@@ -85,9 +85,15 @@ static int host_pipeline(int mode, const void* in_host, void* out_host, int n, i
     }
     int rc = UPR_OK;
     int idx = 0;
-    for (int f0 = 0; f0 < n && rc == UPR_OK; f0 += chunk, ++idx) {
+    // The first upload and the last download overlap with nothing: a half-sized first and last chunk shortens both ends of the
+    // pipeline (64 x 1080p, chunks of 2: head and tail of one frame).
+    const int edge = n > 2 * chunk ? std::max(1, chunk / 2) : chunk;
+    for (int f0 = 0, nf = 0; f0 < n && rc == UPR_OK; f0 += nf, ++idx) {
         HostSlot& s = pool.slot[idx % kSlots];
-        const int nf = std::min(chunk, n - f0);
+        const int left = n - f0;
+        nf = idx == 0 ? edge : chunk;
+        if (left - nf < edge && left > edge) nf = left - edge;      // leave exactly `edge` frames for the last chunk
+        nf = std::min(nf, left);
         const size_t bytes = size_t(nf) * frame_bytes;
         if (s.busy) {  // the slot's previous D2H must have drained before its buffers are reused
             cudaError_t e = cudaEventSynchronize(s.done);
