@@ -179,6 +179,24 @@ def _stream_ring(dev, count=3):
     return ring
 
 
+def _chunk_bounds(n, chunk):
+    """[(f0, f1)] covering n frames in chunks of ``chunk`` with a half-sized first and last chunk: the first upload and the last
+    download of the pipeline overlap with nothing, so both ends are kept short."""
+    chunk = max(1, int(chunk))
+    edge = max(1, chunk // 2) if n > 2 * chunk else chunk
+    bounds, f0, first = [], 0, True
+    while f0 < n:
+        left = n - f0
+        nf = edge if first else chunk
+        if left - nf < edge < left:
+            nf = left - edge          # leave exactly ``edge`` frames for the last chunk
+        nf = min(nf, left)
+        bounds.append((f0, f0 + nf))
+        f0 += nf
+        first = False
+    return bounds
+
+
 def enhance_frames_host_u8(model, frames_u8, out_enh, out_illu, device, max_size=None, enable_multi_scale=False,
                            enable_content_aware=False, out_low=None, chunk=8, frame_fn=None):
     """The device side of the batch driver, end to end at the uint8 boundary: HOST frames as decoded ([N,H,W,3] u8, pinned for
@@ -199,8 +217,7 @@ def enhance_frames_host_u8(model, frames_u8, out_enh, out_illu, device, max_size
     ready.record(launch)
     events = []
     with torch.cuda.device(dev):
-        for k, f0 in enumerate(range(0, n, chunk)):
-            f1 = min(f0 + chunk, n)
+        for k, (f0, f1) in enumerate(_chunk_bounds(n, chunk)):
             st = ring[k % len(ring)]
             st.wait_event(ready)
             with torch.cuda.stream(st):
