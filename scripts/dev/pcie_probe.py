@@ -3,6 +3,8 @@ import json, os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from retinex_image_enhancement_b200 import native
+if os.environ.get('UPR_LIB'):
+    native.LIB_PATH = os.environ['UPR_LIB']
 
 n, h, w = 64, 1080, 1920
 hx = torch.rand((n, 3, h, w), dtype=torch.float32).pin_memory()
